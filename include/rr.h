@@ -1,0 +1,178 @@
+/*
+ * rr.h — C ABI of the B200-native rasteriser that replaces OpenCLRenderer's OpenCL layer for ONE path:
+ * the per-frame draw path  engine::generate_realtime_shadowing -> engine::draw_bulk_objs_n
+ * (prearrange -> kernel1 -> kernel2 -> kernel3, plus the shadow-cubemap pair).
+ *
+ * Every entry point names the reference interface it replaces (file:line under the reference tree).
+ * Conventions (same as the reference's single render thread):
+ *   - plain C, opaque handle, `int` return: 0 = RR_OK, negative = error; rr_last_error() gives the text;
+ *   - caller owns all host pointers; the context owns all device memory unless bound with rr_bind_external();
+ *   - every call is asynchronous on the context's CUDA stream unless it is named rr_read_* / rr_sync;
+ *   - a context is NOT thread-safe (neither is the reference: one cl::cqueue, main thread only);
+ *   - there is no CPU fallback: rr_create() fails with RR_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RR_H_INCLUDED
+#define RR_H_INCLUDED
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RR_OK            0
+#define RR_ERR_INVALID  (-1)   /* bad argument / call order */
+#define RR_ERR_CUDA     (-2)   /* CUDA runtime failure (text in rr_last_error) */
+#define RR_ERR_OOM      (-3)
+#define RR_ERR_OVERFLOW (-4)   /* fragment / projected-triangle storage exhausted (reference: silent corruption, cl2.cl:4392) */
+
+/* ---- device-visible PODs: byte-identical to the reference's host/device structs ------------------------------- */
+
+/* struct vertex, cl2.cl:131-138 / vertex.hpp:33-37 — 48 bytes */
+typedef struct rr_vertex {
+    float    pos[4];
+    float    normal[4];
+    float    vt[2];
+    uint32_t object_id;   /* host name `pad`; only vertex 0's is read (cl2.cl:4296) */
+    uint32_t vertex_col;  /* RGBA8 packed r<<24|g<<16|b<<8|a, 0 = use texture (cl2.cl:5676-5686, 5933) */
+} rr_vertex;
+
+/* struct triangle, cl2.cl:148-151 / triangle.hpp:8-15 — 144 bytes */
+typedef struct rr_triangle { rr_vertex vertices[3]; } rr_triangle;
+
+/* struct obj_g_descriptor, cl2.cl:99-124 / obj_g_descriptor.hpp:9-36 — 136 bytes padded to 144 */
+typedef struct rr_obj_desc {
+    float    world_pos[4];
+    float    world_rot_quat[4];
+    float    old_world_pos_1[4];
+    float    old_world_pos_2[4];
+    float    old_world_rot_quat_1[4];
+    float    old_world_rot_quat_2[4];
+    float    scale;
+    uint32_t tid, rid, ssid;
+    uint32_t has_bump;
+    float    specular, spec_mult, diffuse;
+    int32_t  buffer_offset;
+    int32_t  feature_flag;
+    uint32_t _pad[2];
+} rr_obj_desc;
+
+/* enum object_feature_flag, cl2.cl:90-97 */
+#define RR_FEATURE_SS_REFLECTIVE               1
+#define RR_FEATURE_TWO_SIDED                   2
+#define RR_FEATURE_OUTLINE                     4
+#define RR_FEATURE_IS_STATIC                   8
+#define RR_FEATURE_NO_DYNAMIC_SHADOWS         16
+
+/* struct light, cl2.cl:77-87 / light.hpp:25-34 — 56 bytes padded to 64 */
+typedef struct rr_light {
+    float    pos[4];
+    float    col[4];
+    uint32_t shadow;
+    float    brightness, radius, diffuse, godray_intensity;
+    int32_t  is_static;
+    uint32_t _pad[2];
+} rr_light;
+
+/* What the reference passes as OpenCL -D macros (ocl.h:227-236, main.cpp:80-85, cl2.cl:7-23) plus placement. */
+typedef struct rr_config {
+    int32_t width, height;         /* SCREENWIDTH / SCREENHEIGHT */
+    int32_t light_dim;             /* LIGHTBUFFERDIM (engine::l_size, engine.cpp:471 = 1024) */
+    float   fov_const;             /* FOV_CONST literal; <= 0 -> rr_fov_const_from_hfov(hfov_deg, width) */
+    float   hfov_deg;              /* engine.hpp:115 default 120 */
+    int32_t depth_icutoff;         /* 20 */
+    float   ambient;               /* AMBIENT 0.2 */
+    float   ssao_rad;              /* SSAO_RAD 5 (main.cpp uses 2) */
+    float   ssao_div;              /* SSAO_DIV 2.5 */
+    float   mip_bias;              /* MIP_BIAS 1.1 */
+    float   shadow_bias;           /* SHADOWBIAS 50 */
+    float   shadow_exp;            /* SHADOWEXP 1 */
+    int32_t test_linear;           /* -D TEST_LINEAR */
+    int32_t use_linear_rendering;  /* object_context_data::use_linear_rendering (object_context.hpp:87) */
+    int32_t no_ssao;               /* -D NO_SSAO */
+    int32_t device;                /* CUDA device ordinal */
+    /* sort-first split (no reference counterpart). 0,0 = whole screen. */
+    int32_t band_y0, band_y1;      /* this context resolves ids and shades rows [band_y0, band_y1) */
+    int32_t band_halo;             /* depth rows rasterised outside the band for SSAO; < 0 = every row */
+    int32_t face_rank, face_world; /* shadow (light,face) pair p is rendered here iff p % face_world == face_rank; 0,0 = all */
+    uint32_t max_fragments;        /* fragment-record capacity; 0 = 16 Mi (reference: 2 Mi, engine.cpp:601) */
+    uint32_t max_cutdown;          /* projected-triangle capacity; 0 = derived from the triangle count */
+} rr_config;
+
+typedef struct rr_timings {      /* CUDA-event milliseconds of the last rr_frame_* calls (reference: -DPROFILING, engine.hpp:625-640) */
+    float shadow_clear_ms, shadow_setup_ms, shadow_depth_ms;
+    float setup_ms, depth_ms, id_ms, shade_ms, frame_ms;
+    uint32_t n_cutdown, n_fragments;        /* totals of the main pass (id_cutdown_tris / id_buffer_atomc) */
+    uint32_t n_shadow_fragments;            /* sum over shadow passes */
+    uint32_t overflow;                      /* non-zero if any capacity was exceeded */
+    uint32_t launches;                      /* kernels launched by this library since rr_create */
+} rr_timings;
+
+typedef struct rr_ctx rr_ctx;
+
+enum rr_buffer {                 /* names for rr_bind_external / rr_device_ptr */
+    RR_BUF_RGBA8 = 0,            /* uchar4[W*H] headless colour target (replaces cl_gl_interop_texture.hpp:273-331) */
+    RR_BUF_SHADOW_DYNAMIC = 1,   /* uint32[6*L*L*n_shadow]  engine::g_shadow_light_buffer (light.cpp:236) */
+    RR_BUF_SHADOW_STATIC = 2,    /* uint32[6*L*L*n_static]  engine::g_static_shadow_light_buffer (light.cpp:253) */
+    RR_BUF_DEPTH = 3,            /* uint32[W*H] current depth buffer (object_context.cpp:47) */
+    RR_BUF_IDS = 4               /* uint32[W*H] fragment-id image (object_context.cpp:36-38) */
+};
+
+/* ---- context -------------------------------------------------------------------------------------------------- */
+void     rr_default_config(rr_config* cfg);                         /* reference defaults, SURVEY.md §5 */
+float    rr_fov_const_from_hfov(float hfov_deg, float screenwidth); /* engine.cpp:119-133 + std::to_string literal, engine.cpp:474-477 */
+rr_ctx*  rr_create(const rr_config* cfg);                           /* oclstuff()+build() ocl.h:185-537, engine::load buffers engine.cpp:600-666, ensure_screen_buffers object_context.cpp:27-65 */
+void     rr_destroy(rr_ctx* ctx);
+const char* rr_last_error(void);
+const char* rr_version(void);
+
+/* ---- scene (object_context::build -> alloc_gpu, object_context.cpp:346-484) ------------------------------------ */
+int rr_scene_alloc(rr_ctx*, uint32_t n_tris, uint32_t n_objs);                                   /* g_tri_mem / g_obj_desc / g_cut_tri_mem allocation */
+int rr_scene_write_tris(rr_ctx*, uint32_t first, uint32_t count, const rr_triangle* tris);       /* enqueue_write_buffer_async(g_tri_mem) object_context.cpp:409-441 (+ fill_ids cl2.cl:4231 is the caller's job: object_id must be set) */
+int rr_scene_write_objs(rr_ctx*, uint32_t first, uint32_t count, const rr_obj_desc* objs);       /* alloc_object_descriptors object_context.cpp:460-484 */
+int rr_scene_patch_obj(rr_ctx*, uint32_t obj_id, uint32_t byte_off, uint32_t nbytes, const void* src); /* object::g_flush partial writes object.cpp:652-857 */
+
+/* ---- texture atlas (texture_context::alloc_gpu texture_context.cpp:350-517) ------------------------------------ */
+int rr_atlas_alloc(rr_ctx*, uint32_t n_slices, const uint32_t* nums, uint32_t n_nums,
+                   const uint32_t* sizes, uint32_t n_sizes, uint32_t mipmap_start);              /* g_texture_array / g_texture_nums / g_texture_sizes */
+int rr_atlas_upload(rr_ctx*, uint32_t gpu_id, const uint8_t* rgba, uint32_t w, uint32_t h, int flip); /* texture::update_me_to_gpu texture.cpp:323-358 = update_gpu_tex + generate_mips + 3x generate_mip_mips */
+int rr_atlas_write_raw(rr_ctx*, const uint8_t* atlas, size_t nbytes);                            /* test hook: inject a prebuilt atlas (decouples shading parity from atlas parity) */
+int rr_atlas_read_raw(rr_ctx*, uint8_t* dst, size_t nbytes);
+
+/* ---- lights (light::build light.cpp:145-276; engine::set_light_data engine.cpp:741) ---------------------------- */
+int rr_lights_write(rr_ctx*, const rr_light* lights, uint32_t n_active);                         /* active lights in lightlist order; allocates the cubemap slabs */
+
+/* ---- per frame ------------------------------------------------------------------------------------------------- */
+int rr_frame_shadows(rr_ctx*, int static_lights_dirty);                                          /* engine::generate_realtime_shadowing engine.cpp:1601-1790 */
+int rr_frame_draw(rr_ctx*, const float c_pos[4], const float c_rot[4], const float clear_rgba[4]); /* engine::draw_bulk_objs_n engine.cpp:2356 -> render_tris 1794-2025 */
+int rr_swap_buffers(rr_ctx*);                                                                    /* object_context_data::swap_buffers object_context.cpp:17-25 */
+int rr_sync(rr_ctx*);                                                                            /* cl::cqueue.finish(); reports RR_ERR_OVERFLOW */
+
+/* ---- read-back of the frame just drawn (replaces clEnqueueReadImage cl_gl_interop_texture.hpp:235, async_read.hpp:51) */
+int rr_read_depth(rr_ctx*, uint32_t* dst);            /* W*H uint32, the depth buffer kernel1 filled */
+int rr_read_ids(rr_ctx*, uint32_t* dst);              /* W*H uint32 fragment indices (0 where nothing was drawn) */
+int rr_read_rgba8(rr_ctx*, uint8_t* dst);             /* W*H*4, q = (uint8)(clamp(c,0,1)*255+0.5) */
+int rr_read_normals(rr_ctx*, uint16_t* dst);          /* W*H*2 ushort2, screen_normals_optional cl2.cl:6390 */
+int rr_read_shadow(rr_ctx*, int is_static, uint32_t slab, uint32_t* dst);  /* 6*L*L uint32 of one light's cubemap */
+int rr_read_fragments(rr_ctx*, uint32_t* dst, uint32_t max_records, uint32_t* n_records);   /* 5 words each, g_tid_buf engine.cpp:601 */
+int rr_read_cutdown(rr_ctx*, float* dst, uint32_t max_tris, uint32_t* n_tris);              /* 12 floats each, g_cut_tri_mem */
+int rr_get_timings(rr_ctx*, rr_timings* out);
+
+/* ---- multi-GPU plumbing hooks ---------------------------------------------------------------------------------- */
+int   rr_bind_external(rr_ctx*, int which /*enum rr_buffer*/, void* device_ptr, size_t nbytes); /* render straight into caller-owned (e.g. torch / peer-mapped) memory */
+void* rr_device_ptr(rr_ctx*, int which /*enum rr_buffer*/);
+void* rr_stream(rr_ctx*);                                                                       /* cudaStream_t the context launches on */
+
+/* ---- host-to-host frame for e2e timing: upload camera, draw, read RGBA8 back into pinned host memory ------------ */
+int rr_frame_e2e(rr_ctx*, const float c_pos[4], const float c_rot[4], const float clear_rgba[4],
+                 int with_shadows, uint8_t* host_rgba8);
+
+/* ---- roofline micro-benchmarks (R_atomic is not in MEASURED_PEAKS.json) ------------------------- */
+int rr_microbench_atomic_min(rr_ctx*, size_t footprint_bytes, uint64_t n_ops, float* ms_out);
+int rr_microbench_copy(rr_ctx*, size_t nbytes, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_H_INCLUDED */

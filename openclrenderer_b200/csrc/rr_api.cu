@@ -1,0 +1,680 @@
+// rr_api.cu — C ABI (include/rr.h) over the sm_100a kernels in rr_kernels.cuh.
+// Replaces the reference's OpenCL layer for the draw path: ocl.h / ocl.cpp / clstate.* (context, queue, program),
+// engine.cpp's render_tris / generate_realtime_shadowing launch code, and cl_gl_interop_texture.hpp (colour targets).
+// There is no CPU fallback anywhere in this file: without a usable CUDA device rr_create() fails.
+#include "rr_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace rr;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) return fail(e__ == cudaErrorMemoryAllocation ? RR_ERR_OOM : RR_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+RotSC make_rotsc(float rx, float ry, float rz) {      // native_sin / native_cos pinned: double on the host, rounded to float
+    RotSC r;
+    r.sx = (float)sin((double)rx); r.sy = (float)sin((double)ry); r.sz = (float)sin((double)rz);
+    r.cx = (float)cos((double)rx); r.cy = (float)cos((double)ry); r.cz = (float)cos((double)rz);
+    return r;
+}
+
+FaceTable make_face_table() {                         // r_struct, cl2.cl:4487-4511 / 2538-2558 (float arithmetic on M_PI = 3.1415927f)
+    const float PI = RR_PI_F;
+    const float e[6][3] = {{0, 0, 0}, {PI / 2.0f, 0, 0}, {0, PI, 0}, {3.0f * PI / 2.0f, 0, 0}, {0, 3.0f * PI / 2.0f, 0}, {0, PI / 2.0f, 0}};
+    FaceTable t;
+    for (int k = 0; k < 6; k++) t.r[k] = make_rotsc(e[k][0], e[k][1], e[k][2]);
+    return t;
+}
+
+enum { EV_SH0, EV_SH1, EV_F0, EV_SETUP, EV_DEPTH, EV_IDS, EV_SHADE, EV_COUNT };
+
+}  // namespace
+
+struct rr_ctx {
+    rr_config cfg;
+    float fov = 0;
+    int W = 0, H = 0, L = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool have_shadow_ev = false, have_frame_ev = false;
+    // scene
+    uint32_t n_tris = 0, n_objs = 0;
+    rr_triangle* d_tris = nullptr;
+    float4 *d_pa = nullptr, *d_pb = nullptr;
+    float2* d_pc = nullptr;
+    rr_obj_desc* d_objs = nullptr;
+    ObjLite* d_objlite = nullptr;
+    bool objlite_dirty = true;
+    // atlas
+    uchar4* d_atlas = nullptr;
+    size_t atlas_texels = 0;
+    uint32_t *d_nums = nullptr, *d_sizes = nullptr;
+    uint32_t n_nums = 0, n_sizes = 0, mipmap_start = 0;
+    uchar4* d_upload = nullptr;
+    size_t upload_cap = 0;
+    // lights
+    std::vector<rr_light> lights;
+    rr_light* d_lights = nullptr;
+    uint32_t n_shadow = 0, n_static = 0;
+    uint32_t *d_shadow_dyn = nullptr, *d_shadow_static = nullptr;
+    bool ext_shadow_dyn = false, ext_shadow_static = false;
+    size_t shadow_dyn_words = 0, shadow_static_words = 0;
+    // frame targets
+    uint32_t* d_depth[2] = {nullptr, nullptr};
+    uint32_t* d_ids[2] = {nullptr, nullptr};
+    int cur = 0;
+    uchar4* d_rgba8 = nullptr;
+    bool ext_rgba8 = false;
+    ushort2* d_normals = nullptr;
+    // raster storage
+    uint32_t* d_frags = nullptr;
+    uint32_t cap_frags = 0;
+    float4* d_cutdown = nullptr;
+    uint32_t cap_cut = 0;
+    uint32_t* d_counters = nullptr;
+    unsigned long long* d_lookback = nullptr;
+    uint32_t lookback_blocks = 0;
+    uint32_t* h_counters = nullptr;      // pinned
+    // e2e staging (pinned)
+    rr_obj_desc* h_objs_pinned = nullptr;
+    uint8_t* h_rgba_pinned = nullptr;
+    // stats
+    uint32_t launches = 0;
+    FaceTable faces;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(T*& p, size_t count) {
+    if (p) { cudaFree(p); p = nullptr; }
+    if (count == 0) count = 1;
+    CU(cudaMalloc((void**)&p, count * sizeof(T)));
+    return RR_OK;
+}
+
+inline int grid_for(const rr_ctx* c, int per_sm) { return c->sm_count * per_sm; }
+
+int fill_u32(rr_ctx* c, uint32_t* p, size_t n, uint32_t v) {
+    if (n == 0) return RR_OK;
+    k_fill_u32<<<grid_for(c, 8), 256, 0, c->stream>>>(p, n, v);
+    c->launches++;
+    CU(cudaGetLastError());
+    return RR_OK;
+}
+
+int ensure_objlite(rr_ctx* c) {
+    if (!c->objlite_dirty || c->n_objs == 0) return RR_OK;
+    k_objlite<<<(c->n_objs + 127) / 128, 128, 0, c->stream>>>(c->d_objs, c->n_objs, c->d_objlite);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->objlite_dirty = false;
+    return RR_OK;
+}
+
+void band_rows(const rr_ctx* c, int& band0, int& band1, int& row0, int& row1) {
+    band0 = 0; band1 = c->H;
+    if (c->cfg.band_y1 > c->cfg.band_y0) { band0 = std::max(0, c->cfg.band_y0); band1 = std::min(c->H, c->cfg.band_y1); }
+    if (c->cfg.band_halo < 0 || (band0 == 0 && band1 == c->H)) { row0 = 0; row1 = c->H; }
+    else { row0 = std::max(0, band0 - c->cfg.band_halo); row1 = std::min(c->H, band1 + c->cfg.band_halo); }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rr_last_error(void) { return g_err; }
+const char* rr_version(void) { return "openclrenderer_b200 0.1 (sm_100a)"; }
+
+void rr_default_config(rr_config* cfg) {
+    memset(cfg, 0, sizeof *cfg);
+    cfg->width = 800; cfg->height = 600; cfg->light_dim = 1024;
+    cfg->fov_const = 0.f; cfg->hfov_deg = 120.f;
+    cfg->depth_icutoff = 20;
+    cfg->ambient = 0.2f; cfg->ssao_rad = 5.f; cfg->ssao_div = 2.5f; cfg->mip_bias = 1.1f;
+    cfg->shadow_bias = 50.f; cfg->shadow_exp = 1.f;
+    cfg->test_linear = 0; cfg->use_linear_rendering = 1; cfg->no_ssao = 0;
+    cfg->device = 0;
+    cfg->band_y0 = cfg->band_y1 = 0; cfg->band_halo = -1;
+    cfg->face_rank = 0; cfg->face_world = 0;
+    cfg->max_fragments = 0; cfg->max_cutdown = 0;
+}
+
+float rr_fov_const_from_hfov(float hfov_deg, float screenwidth) {
+    // engine.cpp:119-133: float fov_radians = (hfov/360.f)*2*M_PI; fov = (w/2)/tan(fov_radians/2); then the kernel sees
+    // std::to_string(fov) + "f" (engine.cpp:474-477), i.e. the value rounded to 6 decimals and re-parsed as float.
+    double fr = ((double)(hfov_deg / 360.f) * 2) * M_PI;
+    float fov_radians = (float)fr;
+    float triangle_angle = fov_radians / 2;
+    float fov_constant = (float)((double)(screenwidth / 2) / tan((double)triangle_angle));
+    char buf[64];
+    snprintf(buf, sizeof buf, "%f", fov_constant);
+    return strtof(buf, nullptr);
+}
+
+rr_ctx* rr_create(const rr_config* cfg) {
+    if (!cfg || cfg->width <= 0 || cfg->height <= 0 || cfg->light_dim <= 0) { fail(RR_ERR_INVALID, "rr_create: bad config"); return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { fail(RR_ERR_CUDA, "rr_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e)); return nullptr; }
+    if (cfg->device < 0 || cfg->device >= ndev) { fail(RR_ERR_INVALID, "rr_create: device %d out of range (%d devices)", cfg->device, ndev); return nullptr; }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { fail(RR_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { fail(RR_ERR_CUDA, "cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major < 10) { fail(RR_ERR_CUDA, "rr_create: device is sm_%d%d; this build carries only sm_100a code", prop.major, prop.minor); return nullptr; }
+    rr_ctx* c = new (std::nothrow) rr_ctx();
+    if (!c) { fail(RR_ERR_OOM, "host alloc"); return nullptr; }
+    c->cfg = *cfg;
+    c->W = cfg->width; c->H = cfg->height; c->L = cfg->light_dim;
+    c->fov = cfg->fov_const > 0 ? cfg->fov_const : rr_fov_const_from_hfov(cfg->hfov_deg, (float)cfg->width);
+    c->sm_count = prop.multiProcessorCount;
+    c->faces = make_face_table();
+    auto bail = [&](const char* what) { fail(RR_ERR_CUDA, "rr_create: %s: %s", what, cudaGetErrorString(cudaGetLastError())); rr_destroy(c); return (rr_ctx*)nullptr; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+    for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail("event");
+    const size_t P = (size_t)c->W * c->H;
+    for (int i = 0; i < 2; i++) {
+        if (cudaMalloc((void**)&c->d_depth[i], P * 4) != cudaSuccess) return bail("depth");
+        if (cudaMalloc((void**)&c->d_ids[i], P * 4) != cudaSuccess) return bail("ids");
+    }
+    if (cudaMalloc((void**)&c->d_rgba8, P * 4) != cudaSuccess) return bail("rgba8");
+    if (cudaMalloc((void**)&c->d_normals, P * 4) != cudaSuccess) return bail("normals");
+    c->cap_frags = cfg->max_fragments ? cfg->max_fragments : (16u << 20);
+    if (cudaMalloc((void**)&c->d_frags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("fragment buffer");
+    if (cudaMalloc((void**)&c->d_counters, CTR_COUNT * 4) != cudaSuccess) return bail("counters");
+    if (cudaMallocHost((void**)&c->h_counters, CTR_COUNT * 4) != cudaSuccess) return bail("pinned counters");
+    if (cudaMallocHost((void**)&c->h_rgba_pinned, P * 4) != cudaSuccess) return bail("pinned frame");
+    cudaMemsetAsync(c->d_counters, 0, CTR_COUNT * 4, c->stream);
+    // depth_buffer[0..1] start at UINT_MAX (object_context.cpp:43-52); the id image starts at 0
+    for (int i = 0; i < 2; i++) {
+        cudaMemsetAsync(c->d_depth[i], 0xFF, P * 4, c->stream);
+        cudaMemsetAsync(c->d_ids[i], 0, P * 4, c->stream);
+    }
+    cudaMemsetAsync(c->d_rgba8, 0, P * 4, c->stream);
+    cudaMemsetAsync(c->d_normals, 0, P * 4, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("init sync");
+    return c;
+}
+
+void rr_destroy(rr_ctx* c) {
+    if (!c) return;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite);
+    cudaFree(c->d_atlas); cudaFree(c->d_nums); cudaFree(c->d_sizes); cudaFree(c->d_upload);
+    cudaFree(c->d_lights);
+    if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
+    if (!c->ext_shadow_static) cudaFree(c->d_shadow_static);
+    for (int i = 0; i < 2; i++) { cudaFree(c->d_depth[i]); cudaFree(c->d_ids[i]); }
+    if (!c->ext_rgba8) cudaFree(c->d_rgba8);
+    cudaFree(c->d_normals); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
+    if (c->h_rgba_pinned) cudaFreeHost(c->h_rgba_pinned);
+    for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ---- scene ---------------------------------------------------------------------------------------------------------
+int rr_scene_alloc(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    if (n_tris >= (1u << 26)) return fail(RR_ERR_INVALID, "rr_scene_alloc: %u triangles exceeds the 2^26 limit of the scan descriptor", n_tris);
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_tris = n_tris; c->n_objs = n_objs;
+    int r;
+    if ((r = dev_alloc(c->d_tris, n_tris))) return r;
+    if ((r = dev_alloc(c->d_pa, n_tris))) return r;
+    if ((r = dev_alloc(c->d_pb, n_tris))) return r;
+    if ((r = dev_alloc(c->d_pc, n_tris))) return r;
+    if ((r = dev_alloc(c->d_objs, n_objs))) return r;
+    if ((r = dev_alloc(c->d_objlite, n_objs))) return r;
+    // projected triangles: main pass needs <= 2T; a shadow pass <= 12T in the worst case (reference allocates 12T,
+    // object_context.cpp:354). Default 4T + slack, overflow is detected and reported.
+    c->cap_cut = c->cfg.max_cutdown ? c->cfg.max_cutdown : (uint32_t)std::min<uint64_t>((uint64_t)n_tris * 4 + 1024, 0x7FFFFFFu);
+    if ((r = dev_alloc(c->d_cutdown, (size_t)c->cap_cut * 3))) return r;
+    c->lookback_blocks = (n_tris + SETUP_THREADS - 1) / SETUP_THREADS;
+    if ((r = dev_alloc(c->d_lookback, (size_t)c->lookback_blocks))) return r;
+    if (c->h_objs_pinned) { cudaFreeHost(c->h_objs_pinned); c->h_objs_pinned = nullptr; }
+    CU(cudaMallocHost((void**)&c->h_objs_pinned, std::max<size_t>(1, n_objs) * sizeof(rr_obj_desc)));
+    c->objlite_dirty = true;
+    return RR_OK;
+}
+
+int rr_scene_write_tris(rr_ctx* c, uint32_t first, uint32_t count, const rr_triangle* tris) {
+    if (!c || !tris) return fail(RR_ERR_INVALID, "null argument");
+    if ((uint64_t)first + count > c->n_tris) return fail(RR_ERR_INVALID, "rr_scene_write_tris: range [%u,+%u) outside %u", first, count, c->n_tris);
+    if (count == 0) return RR_OK;
+    CU(cudaMemcpyAsync(c->d_tris + first, tris, (size_t)count * sizeof(rr_triangle), cudaMemcpyHostToDevice, c->stream));
+    k_repack<<<(count + 255) / 256, 256, 0, c->stream>>>(c->d_tris, first, count, c->d_pa, c->d_pb, c->d_pc);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));      // caller may free `tris` on return (the reference keeps staging alive instead, object.cpp:729)
+    return RR_OK;
+}
+
+int rr_scene_write_objs(rr_ctx* c, uint32_t first, uint32_t count, const rr_obj_desc* objs) {
+    if (!c || !objs) return fail(RR_ERR_INVALID, "null argument");
+    if ((uint64_t)first + count > c->n_objs) return fail(RR_ERR_INVALID, "rr_scene_write_objs: range outside %u", c->n_objs);
+    if (count == 0) return RR_OK;
+    memcpy(c->h_objs_pinned + first, objs, (size_t)count * sizeof(rr_obj_desc));
+    CU(cudaMemcpyAsync(c->d_objs + first, c->h_objs_pinned + first, (size_t)count * sizeof(rr_obj_desc), cudaMemcpyHostToDevice, c->stream));
+    c->objlite_dirty = true;
+    return RR_OK;
+}
+
+int rr_scene_patch_obj(rr_ctx* c, uint32_t obj_id, uint32_t byte_off, uint32_t nbytes, const void* src) {
+    if (!c || !src) return fail(RR_ERR_INVALID, "null argument");
+    if (obj_id >= c->n_objs || (uint64_t)byte_off + nbytes > sizeof(rr_obj_desc)) return fail(RR_ERR_INVALID, "rr_scene_patch_obj: out of range");
+    memcpy((char*)(c->h_objs_pinned + obj_id) + byte_off, src, nbytes);
+    CU(cudaMemcpyAsync((char*)(c->d_objs + obj_id) + byte_off, (char*)(c->h_objs_pinned + obj_id) + byte_off, nbytes, cudaMemcpyHostToDevice, c->stream));
+    c->objlite_dirty = true;
+    return RR_OK;
+}
+
+// ---- atlas ---------------------------------------------------------------------------------------------------------
+int rr_atlas_alloc(rr_ctx* c, uint32_t n_slices, const uint32_t* nums, uint32_t n_nums, const uint32_t* sizes, uint32_t n_sizes, uint32_t mipmap_start) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    CU(cudaStreamSynchronize(c->stream));
+    uint32_t slices = std::max(n_slices, 2u);                                      // clamped_array_len, texture_context.cpp:441
+    c->atlas_texels = (size_t)slices * RR_ATLAS_DIM * RR_ATLAS_DIM;
+    int r;
+    if ((r = dev_alloc(c->d_atlas, c->atlas_texels))) return r;
+    if ((r = dev_alloc(c->d_nums, std::max(n_nums, 2u)))) return r;
+    if ((r = dev_alloc(c->d_sizes, std::max(n_sizes, 2u)))) return r;
+    CU(cudaMemsetAsync(c->d_atlas, 0, c->atlas_texels * 4, c->stream));
+    if (n_nums) CU(cudaMemcpyAsync(c->d_nums, nums, (size_t)n_nums * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n_sizes) CU(cudaMemcpyAsync(c->d_sizes, sizes, (size_t)n_sizes * 4, cudaMemcpyHostToDevice, c->stream));
+    c->n_nums = n_nums; c->n_sizes = n_sizes; c->mipmap_start = mipmap_start;
+    CU(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+
+int rr_atlas_upload(rr_ctx* c, uint32_t gpu_id, const uint8_t* rgba, uint32_t w, uint32_t h, int flip) {
+    if (!c || !rgba) return fail(RR_ERR_INVALID, "null argument");
+    if (!c->d_atlas) return fail(RR_ERR_INVALID, "rr_atlas_upload before rr_atlas_alloc");
+    if (gpu_id * RR_MIP_LEVELS + c->mipmap_start + RR_MIP_LEVELS > c->n_nums) return fail(RR_ERR_INVALID, "rr_atlas_upload: texture %u has no mip descriptors", gpu_id);
+    size_t n = (size_t)w * h;
+    if (n > c->upload_cap) { int r = dev_alloc(c->d_upload, n); if (r) return r; c->upload_cap = n; }
+    CU(cudaMemcpyAsync(c->d_upload, rgba, n * 4, cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((w + 15) / 16, (h + 15) / 16);
+    k_atlas_upload<<<grid, 256, 0, c->stream>>>(c->d_upload, (int)w, (int)h, gpu_id, flip, c->d_atlas, c->d_nums, c->d_sizes);
+    c->launches++;
+    // texture::update_gpu_mipmaps, texture.cpp:465-493: generate_mips then generate_mip_mips for levels 0..2, all with the base image's global size
+    uint32_t m0 = gpu_id * RR_MIP_LEVELS + c->mipmap_start;
+    k_atlas_mip<<<grid, 256, 0, c->stream>>>(gpu_id, m0, (int)w, (int)h, c->d_atlas, c->d_nums, c->d_sizes);
+    c->launches++;
+    for (uint32_t i = 0; i < RR_MIP_LEVELS - 1; i++) {
+        k_atlas_mip<<<grid, 256, 0, c->stream>>>(m0 + i, m0 + i + 1, (int)w, (int)h, c->d_atlas, c->d_nums, c->d_sizes);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+
+int rr_atlas_write_raw(rr_ctx* c, const uint8_t* atlas, size_t nbytes) {
+    if (!c || !atlas || nbytes > c->atlas_texels * 4) return fail(RR_ERR_INVALID, "rr_atlas_write_raw: bad size");
+    CU(cudaMemcpyAsync(c->d_atlas, atlas, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+int rr_atlas_read_raw(rr_ctx* c, uint8_t* dst, size_t nbytes) {
+    if (!c || !dst || nbytes > c->atlas_texels * 4) return fail(RR_ERR_INVALID, "rr_atlas_read_raw: bad size");
+    CU(cudaMemcpyAsync(dst, c->d_atlas, nbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+
+// ---- lights --------------------------------------------------------------------------------------------------------
+int rr_lights_write(rr_ctx* c, const rr_light* lights, uint32_t n_active) {
+    if (!c || (!lights && n_active)) return fail(RR_ERR_INVALID, "null argument");
+    CU(cudaStreamSynchronize(c->stream));
+    c->lights.assign(lights, lights + n_active);
+    uint32_t ns = 0, nst = 0;
+    for (uint32_t i = 0; i < n_active; i++) {
+        if (lights[i].shadow == 1) ns++;                              // light.cpp:203-208
+        if (lights[i].shadow && lights[i].is_static) nst++;
+    }
+    int r;
+    if ((r = dev_alloc(c->d_lights, std::max(n_active, 1u)))) return r;   // clamped_num, light.cpp:172
+    if (n_active) CU(cudaMemcpyAsync(c->d_lights, lights, (size_t)n_active * sizeof(rr_light), cudaMemcpyHostToDevice, c->stream));
+    const size_t slab = (size_t)6 * c->L * c->L;
+    if (!c->ext_shadow_dyn && (ns != c->n_shadow || !c->d_shadow_dyn)) {
+        c->shadow_dyn_words = std::max<size_t>(slab * ns, 4);
+        if ((r = dev_alloc(c->d_shadow_dyn, c->shadow_dyn_words))) return r;
+        if ((r = fill_u32(c, c->d_shadow_dyn, c->shadow_dyn_words, 0xFFFFFFFFu))) return r;
+    }
+    if (!c->ext_shadow_static && (nst != c->n_static || !c->d_shadow_static)) {
+        c->shadow_static_words = std::max<size_t>(slab * nst, 4);
+        if ((r = dev_alloc(c->d_shadow_static, c->shadow_static_words))) return r;
+        if ((r = fill_u32(c, c->d_shadow_static, c->shadow_static_words, 0xFFFFFFFFu))) return r;
+    }
+    if (c->ext_shadow_dyn && slab * ns > c->shadow_dyn_words) return fail(RR_ERR_INVALID, "bound dynamic shadow buffer too small");
+    if (c->ext_shadow_static && slab * nst > c->shadow_static_words) return fail(RR_ERR_INVALID, "bound static shadow buffer too small");
+    c->n_shadow = ns; c->n_static = nst;
+    CU(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+
+// ---- per frame -----------------------------------------------------------------------------------------------------
+static int shadow_pass(rr_ctx* c, const rr_light& l, int only_static, uint32_t* slab, uint32_t pair_base) {
+    uint32_t mask = 0;
+    for (int kk = 0; kk < 6; kk++) {
+        bool mine = c->cfg.face_world <= 1 || ((pair_base + kk) % (uint32_t)c->cfg.face_world) == (uint32_t)c->cfg.face_rank;
+        if (mine) mask |= 1u << kk;
+    }
+    if (!mask || c->n_tris == 0) return RR_OK;
+    ShadowSetupParams sp;
+    sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
+    sp.lpos = make_float3(l.pos[0], l.pos[1], l.pos[2]);
+    sp.faces = c->faces;
+    sp.L = (float)c->L; sp.icut = (float)c->cfg.depth_icutoff;
+    sp.only_static = only_static; sp.face_mask = mask;
+    sp.frags = c->d_frags; sp.cap_frags = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS) / RR_SFRAG_WORDS);
+    sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut; sp.counters = c->d_counters;
+    k_shadow_setup<<<(c->n_tris + 255) / 256, 256, 0, c->stream>>>(sp);
+    ShadowDepthParams dp;
+    dp.frags = c->d_frags; dp.cutdown = c->d_cutdown; dp.counters = c->d_counters; dp.cap_frags = sp.cap_frags;
+    dp.slab = slab; dp.L = (float)c->L; dp.Li = c->L;
+    k_shadow_depth<<<grid_for(c, 8), 256, 0, c->stream>>>(dp);
+    k_shadow_pass_end<<<1, 1, 0, c->stream>>>(c->d_counters);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return RR_OK;
+}
+
+int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    int r;
+    if ((r = ensure_objlite(c))) return r;
+    CU(cudaEventRecord(c->ev[EV_SH0], c->stream));
+    const size_t slab = (size_t)6 * c->L * c->L;
+    if (!c->lights.empty()) {                                                              // engine.cpp:1611-1626
+        // only the faces this context owns need clearing when faces are sharded, but a full clear keeps the slab
+        // contents defined for the all-gather that follows; it is one streaming fill.
+        if (c->n_shadow && (r = fill_u32(c, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
+        if (static_lights_dirty && c->n_static && (r = fill_u32(c, c->d_shadow_static, slab * c->n_static, 0xFFFFFFFFu))) return r;
+    }
+    CU(cudaMemsetAsync(c->d_counters + CTR_S_NCUT, 0, 3 * 4, c->stream));
+    uint32_t nn = 0, kk = 0;
+    for (size_t i = 0; i < c->lights.size(); i++) {                                        // engine.cpp:1629-1784
+        const rr_light& l = c->lights[i];
+        if (l.shadow == 1) {
+            if ((r = shadow_pass(c, l, 0, c->d_shadow_dyn + slab * nn, nn * 6))) return r;
+            nn++;
+        }
+        if (l.shadow && l.is_static && static_lights_dirty) {
+            if ((r = shadow_pass(c, l, 1, c->d_shadow_static + slab * kk, (c->n_shadow + kk) * 6))) return r;
+            kk++;
+        }
+    }
+    CU(cudaEventRecord(c->ev[EV_SH1], c->stream));
+    c->have_shadow_ev = true;
+    return RR_OK;
+}
+
+int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const float clear_rgba[4]) {
+    if (!c || !c_pos || !c_rot) return fail(RR_ERR_INVALID, "null argument");
+    if (c->n_tris == 0) return RR_OK;                                                      // engine.cpp:1806
+    int r;
+    if ((r = ensure_objlite(c))) return r;
+    CamParams cam;
+    cam.pos = make_float3(c_pos[0], c_pos[1], c_pos[2]);
+    cam.rot = make_rotsc(c_rot[0], c_rot[1], c_rot[2]);
+    int band0, band1, row0, row1;
+    band_rows(c, band0, band1, row0, row1);
+
+    CU(cudaEventRecord(c->ev[EV_F0], c->stream));
+    // prearrange
+    CU(cudaMemsetAsync(c->d_counters, 0, 4 * 4, c->stream));                               // n_cut, n_frag, overflow, ticket
+    CU(cudaMemsetAsync(c->d_lookback, 0, (size_t)c->lookback_blocks * 8, c->stream));
+    SetupMainParams sp;
+    sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
+    sp.cam = cam; sp.width = (float)c->W; sp.height = (float)c->H; sp.fov = c->fov; sp.icut = (float)c->cfg.depth_icutoff;
+    sp.frags = c->d_frags; sp.cap_frags = c->cap_frags; sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut;
+    sp.counters = c->d_counters; sp.lookback = c->d_lookback;
+    k_setup_main<<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
+    CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
+    // kernel1 / kernel2
+    RasterParams rp;
+    rp.frags = c->d_frags; rp.cutdown = c->d_cutdown; rp.counters = c->d_counters; rp.cap_frags = c->cap_frags;
+    rp.depth = c->d_depth[c->cur]; rp.ids = c->d_ids[c->cur];
+    rp.width = (float)c->W; rp.height = (float)c->H; rp.W = c->W;
+    rp.row_lo = row0; rp.row_hi = row1;
+    k_depth<<<grid_for(c, 8), 256, 0, c->stream>>>(rp);
+    CU(cudaEventRecord(c->ev[EV_DEPTH], c->stream));
+    rp.row_lo = band0; rp.row_hi = band1;
+    k_ids<<<grid_for(c, 8), 256, 0, c->stream>>>(rp);
+    CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
+    // kernel3
+    ShadeParams hp;
+    hp.tris = c->d_tris; hp.objs = c->d_objs; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown;
+    hp.depth = c->d_depth[c->cur]; hp.ids = c->d_ids[c->cur];
+    hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
+    hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
+    hp.atlas.texels = c->d_atlas; hp.atlas.nums = c->d_nums; hp.atlas.sizes = c->d_sizes; hp.atlas.mip_start = c->mipmap_start;
+    hp.lights = c->d_lights; hp.n_lights = (int)c->lights.size();
+    hp.shadow_dyn = c->d_shadow_dyn; hp.shadow_static = c->d_shadow_static;
+    hp.faces = c->faces; hp.cam = cam;
+    hp.clear = clear_rgba ? make_float4(clear_rgba[0], clear_rgba[1], clear_rgba[2], clear_rgba[3]) : make_float4(0, 0, 0, 0);
+    hp.W = c->W; hp.H = c->H; hp.L = c->L; hp.fov = c->fov;
+    hp.ambient = c->cfg.ambient; hp.ssao_rad = c->cfg.ssao_rad; hp.ssao_div = c->cfg.ssao_div;
+    hp.inv_mip_bias = 1.f / c->cfg.mip_bias;
+    hp.shadow_bias = c->cfg.shadow_bias; hp.shadow_bias_max = powf(c->cfg.shadow_bias, c->cfg.shadow_exp);
+    hp.linear = (c->cfg.test_linear && c->cfg.use_linear_rendering) ? 1 : 0;
+    hp.no_ssao = c->cfg.no_ssao;
+    hp.row0 = row0; hp.row1 = row1; hp.band_y0 = band0; hp.band_y1 = band1;
+    if (hp.n_lights > 0 && (!c->d_lights)) return fail(RR_ERR_INVALID, "lights not written");
+    dim3 grid((c->W + 31) / 32, (row1 - row0 + 7) / 8);
+    k_shade<<<grid, 256, 0, c->stream>>>(hp);
+    CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
+    c->launches += 4;
+    c->have_frame_ev = true;
+    CU(cudaGetLastError());
+    return RR_OK;
+}
+
+int rr_swap_buffers(rr_ctx* c) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    c->cur ^= 1;                                           // depth_buffer.flip(), object_context.cpp:21
+    return RR_OK;
+}
+
+int rr_sync(rr_ctx* c) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, CTR_COUNT * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_counters[CTR_OVERFLOW])
+        return fail(RR_ERR_OVERFLOW, "raster storage exhausted (flags %u): fragments cap %u, projected-triangle cap %u", c->h_counters[CTR_OVERFLOW], c->cap_frags, c->cap_cut);
+    return RR_OK;
+}
+
+// ---- read-back -----------------------------------------------------------------------------------------------------
+static int read_back(rr_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst) return fail(RR_ERR_INVALID, "null argument");
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+int rr_read_depth(rr_ctx* c, uint32_t* dst) { return read_back(c, dst, c->d_depth[c->cur], (size_t)c->W * c->H * 4); }
+int rr_read_ids(rr_ctx* c, uint32_t* dst) { return read_back(c, dst, c->d_ids[c->cur], (size_t)c->W * c->H * 4); }
+int rr_read_rgba8(rr_ctx* c, uint8_t* dst) { return read_back(c, dst, c->d_rgba8, (size_t)c->W * c->H * 4); }
+int rr_read_normals(rr_ctx* c, uint16_t* dst) { return read_back(c, dst, c->d_normals, (size_t)c->W * c->H * 4); }
+int rr_read_shadow(rr_ctx* c, int is_static, uint32_t slab_idx, uint32_t* dst) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    const size_t slab = (size_t)6 * c->L * c->L;
+    if (slab_idx >= (is_static ? c->n_static : c->n_shadow)) return fail(RR_ERR_INVALID, "rr_read_shadow: slab %u out of range", slab_idx);
+    return read_back(c, dst, (is_static ? c->d_shadow_static : c->d_shadow_dyn) + slab * slab_idx, slab * 4);
+}
+int rr_read_fragments(rr_ctx* c, uint32_t* dst, uint32_t max_records, uint32_t* n_records) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    int r = rr_sync(c);
+    if (r && r != RR_ERR_OVERFLOW) return r;
+    uint32_t n = c->h_counters[CTR_NFRAG];
+    if (n_records) *n_records = n;
+    uint32_t k = std::min(std::min(n, max_records), c->cap_frags);
+    if (dst && k) return read_back(c, dst, c->d_frags, (size_t)k * RR_FRAG_WORDS * 4);
+    return RR_OK;
+}
+int rr_read_cutdown(rr_ctx* c, float* dst, uint32_t max_tris, uint32_t* n_tris) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    int r = rr_sync(c);
+    if (r && r != RR_ERR_OVERFLOW) return r;
+    uint32_t n = c->h_counters[CTR_NCUT];
+    if (n_tris) *n_tris = n;
+    uint32_t k = std::min(std::min(n, max_tris), c->cap_cut);
+    if (dst && k) return read_back(c, dst, c->d_cutdown, (size_t)k * 48);
+    return RR_OK;
+}
+
+int rr_get_timings(rr_ctx* c, rr_timings* t) {
+    if (!c || !t) return fail(RR_ERR_INVALID, "null argument");
+    memset(t, 0, sizeof *t);
+    int r = rr_sync(c);
+    if (r && r != RR_ERR_OVERFLOW) return r;
+    if (c->have_shadow_ev) cudaEventElapsedTime(&t->shadow_depth_ms, c->ev[EV_SH0], c->ev[EV_SH1]);
+    if (c->have_frame_ev) {
+        cudaEventElapsedTime(&t->setup_ms, c->ev[EV_F0], c->ev[EV_SETUP]);
+        cudaEventElapsedTime(&t->depth_ms, c->ev[EV_SETUP], c->ev[EV_DEPTH]);
+        cudaEventElapsedTime(&t->id_ms, c->ev[EV_DEPTH], c->ev[EV_IDS]);
+        cudaEventElapsedTime(&t->shade_ms, c->ev[EV_IDS], c->ev[EV_SHADE]);
+        cudaEventElapsedTime(&t->frame_ms, c->ev[EV_F0], c->ev[EV_SHADE]);
+    }
+    t->n_cutdown = c->h_counters[CTR_NCUT];
+    t->n_fragments = c->h_counters[CTR_NFRAG];
+    t->n_shadow_fragments = c->h_counters[CTR_S_TOTAL];
+    t->overflow = c->h_counters[CTR_OVERFLOW];
+    t->launches = c->launches;
+    return RR_OK;
+}
+
+// ---- multi-GPU hooks -----------------------------------------------------------------------------------------------
+int rr_bind_external(rr_ctx* c, int which, void* p, size_t nbytes) {
+    if (!c || !p) return fail(RR_ERR_INVALID, "null argument");
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t P = (size_t)c->W * c->H;
+    switch (which) {
+        case RR_BUF_RGBA8:
+            if (nbytes < P * 4) return fail(RR_ERR_INVALID, "external RGBA8 buffer too small");
+            if (!c->ext_rgba8) cudaFree(c->d_rgba8);
+            c->d_rgba8 = (uchar4*)p; c->ext_rgba8 = true; return RR_OK;
+        case RR_BUF_SHADOW_DYNAMIC:
+            if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
+            c->d_shadow_dyn = (uint32_t*)p; c->ext_shadow_dyn = true; c->shadow_dyn_words = nbytes / 4; return RR_OK;
+        case RR_BUF_SHADOW_STATIC:
+            if (!c->ext_shadow_static) cudaFree(c->d_shadow_static);
+            c->d_shadow_static = (uint32_t*)p; c->ext_shadow_static = true; c->shadow_static_words = nbytes / 4; return RR_OK;
+        default: return fail(RR_ERR_INVALID, "rr_bind_external: buffer %d cannot be bound", which);
+    }
+}
+void* rr_device_ptr(rr_ctx* c, int which) {
+    if (!c) return nullptr;
+    switch (which) {
+        case RR_BUF_RGBA8: return c->d_rgba8;
+        case RR_BUF_SHADOW_DYNAMIC: return c->d_shadow_dyn;
+        case RR_BUF_SHADOW_STATIC: return c->d_shadow_static;
+        case RR_BUF_DEPTH: return c->d_depth[c->cur];
+        case RR_BUF_IDS: return c->d_ids[c->cur];
+        default: return nullptr;
+    }
+}
+void* rr_stream(rr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---- host-to-host frame --------------------------------------------------------------------------------------------
+int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const float clear_rgba[4], int with_shadows, uint8_t* host_rgba8) {
+    if (!c || !host_rgba8) return fail(RR_ERR_INVALID, "null argument");
+    int r;
+    // per-frame input: the object descriptors (object_context::flush_locations, object_context.cpp:819) from pinned memory
+    if (c->n_objs) {
+        CU(cudaMemcpyAsync(c->d_objs, c->h_objs_pinned, (size_t)c->n_objs * sizeof(rr_obj_desc), cudaMemcpyHostToDevice, c->stream));
+        c->objlite_dirty = true;
+    }
+    if (with_shadows && (r = rr_frame_shadows(c, 0))) return r;
+    if ((r = rr_frame_draw(c, c_pos, c_rot, clear_rgba))) return r;
+    const size_t P = (size_t)c->W * c->H;
+    int band0, band1, row0, row1;
+    band_rows(c, band0, band1, row0, row1);
+    const size_t off = (size_t)band0 * c->W * 4, len = (size_t)(band1 - band0) * c->W * 4;
+    (void)P;
+    CU(cudaMemcpyAsync(c->h_rgba_pinned + off, (uint8_t*)c->d_rgba8 + off, len, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(host_rgba8 + off, c->h_rgba_pinned + off, len);
+    if ((r = rr_swap_buffers(c))) return r;
+    return RR_OK;
+}
+
+// ---- micro-benchmarks ----------------------------------------------------------------------------------------------
+int rr_microbench_atomic_min(rr_ctx* c, size_t footprint_bytes, uint64_t n_ops, float* ms_out) {
+    if (!c || !ms_out) return fail(RR_ERR_INVALID, "null argument");
+    size_t words = 1;
+    while (words * 2 * 4 <= footprint_bytes) words *= 2;
+    uint32_t* buf = nullptr;
+    CU(cudaMalloc((void**)&buf, words * 4));
+    CU(cudaMemsetAsync(buf, 0xFF, words * 4, c->stream));
+    const int blocks = grid_for(c, 8), threads = 256;
+    uint32_t iters = (uint32_t)std::max<uint64_t>(1, n_ops / ((uint64_t)blocks * threads));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    k_bench_atomic_min<<<blocks, threads, 0, c->stream>>>(buf, (uint32_t)(words - 1), 16);      // warm-up
+    cudaEventRecord(a, c->stream);
+    k_bench_atomic_min<<<blocks, threads, 0, c->stream>>>(buf, (uint32_t)(words - 1), iters);
+    cudaEventRecord(b, c->stream);
+    c->launches += 2;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(RR_ERR_CUDA, "atomic microbench: %s", cudaGetErrorString(e));
+    // report the time normalised to exactly n_ops
+    *ms_out = ms * (float)((double)n_ops / ((double)iters * blocks * threads));
+    return RR_OK;
+}
+
+int rr_microbench_copy(rr_ctx* c, size_t nbytes, float* ms_out) {
+    if (!c || !ms_out) return fail(RR_ERR_INVALID, "null argument");
+    uint4 *src = nullptr, *dst = nullptr;
+    size_t n16 = nbytes / 16;
+    CU(cudaMalloc((void**)&src, n16 * 16));
+    CU(cudaMalloc((void**)&dst, n16 * 16));
+    CU(cudaMemsetAsync(src, 1, n16 * 16, c->stream));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    k_bench_copy<<<grid_for(c, 16), 256, 0, c->stream>>>(src, dst, n16);
+    cudaEventRecord(a, c->stream);
+    k_bench_copy<<<grid_for(c, 16), 256, 0, c->stream>>>(src, dst, n16);
+    cudaEventRecord(b, c->stream);
+    c->launches += 2;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaEventElapsedTime(ms_out, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(src); cudaFree(dst);
+    if (e != cudaSuccess) return fail(RR_ERR_CUDA, "copy microbench: %s", cudaGetErrorString(e));
+    return RR_OK;
+}
+
+}  // extern "C"

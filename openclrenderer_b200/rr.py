@@ -1,0 +1,86 @@
+"""ctypes binding of the product library (include/rr.h). No fallback: a missing library is an error."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._abi import CApi, Config, RRError, RR_OK, _F4, _P, _ptr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def library_path():
+    return os.path.join(_HERE, "librr_b200.so")
+
+
+def load_library():
+    """dlopen librr_b200.so. Raises if it has not been built (python -m openclrenderer_b200._build / __graft_entry__.build())."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RRError(-2, f"{path} is missing: build it with `python -m openclrenderer_b200._build` (nvcc, sm_100a). "
+                              "There is no CPU implementation to fall back to.")
+        _LIB = C.CDLL(path)
+        _LIB.rr_fov_const_from_hfov.restype = C.c_float
+        _LIB.rr_fov_const_from_hfov.argtypes = [C.c_float, C.c_float]
+        _LIB.rr_version.restype = C.c_char_p
+        _LIB.rr_default_config.argtypes = [C.POINTER(Config)]
+        _LIB.rr_bind_external.restype = C.c_int
+        _LIB.rr_bind_external.argtypes = [_P, C.c_int, _P, C.c_size_t]
+        _LIB.rr_device_ptr.restype = _P
+        _LIB.rr_device_ptr.argtypes = [_P, C.c_int]
+        _LIB.rr_stream.restype = _P
+        _LIB.rr_stream.argtypes = [_P]
+        _LIB.rr_frame_e2e.restype = C.c_int
+        _LIB.rr_frame_e2e.argtypes = [_P, _F4, _F4, _F4, C.c_int, _P]
+        _LIB.rr_microbench_atomic_min.restype = C.c_int
+        _LIB.rr_microbench_atomic_min.argtypes = [_P, C.c_size_t, C.c_uint64, C.POINTER(C.c_float)]
+        _LIB.rr_microbench_copy.restype = C.c_int
+        _LIB.rr_microbench_copy.argtypes = [_P, C.c_size_t, C.POINTER(C.c_float)]
+    return _LIB
+
+
+def fov_const_from_hfov(hfov_deg, width):
+    return float(load_library().rr_fov_const_from_hfov(hfov_deg, width))
+
+
+class Renderer(CApi):
+    """One rr_ctx: the CUDA rasteriser on one B200."""
+
+    def __init__(self, cfg):
+        super().__init__(load_library(), "rr_", cfg)
+
+    def bind_external(self, which, device_ptr, nbytes):
+        r = self._lib.rr_bind_external(self._ctx, which, device_ptr, nbytes)
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+
+    def device_ptr(self, which):
+        return self._lib.rr_device_ptr(self._ctx, which)
+
+    def stream(self):
+        return self._lib.rr_stream(self._ctx)
+
+    def frame_e2e(self, c_pos, c_rot, clear, with_shadows, host_rgba8):
+        def f4(v):
+            v = list(v) + [0.0] * (4 - len(v))
+            return _F4(*[float(x) for x in v[:4]])
+        r = self._lib.rr_frame_e2e(self._ctx, f4(c_pos), f4(c_rot), f4(clear), int(with_shadows), _ptr(host_rgba8))
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+
+    def microbench_atomic_min(self, footprint_bytes, n_ops):
+        ms = C.c_float(0)
+        r = self._lib.rr_microbench_atomic_min(self._ctx, footprint_bytes, n_ops, C.byref(ms))
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+        return ms.value
+
+    def microbench_copy(self, nbytes):
+        ms = C.c_float(0)
+        r = self._lib.rr_microbench_copy(self._ctx, nbytes, C.byref(ms))
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+        return ms.value
