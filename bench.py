@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — headline metric of BASELINE.json: Mtri/s (and frames/s, Mfrag/s) of the per-frame raster path on
+config 3 (synthetic 1 M-triangle sphere field, texture atlas with mips, 4 shadow-casting lights, 3840x2160).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                         the reference algorithm on the host cores (CPU oracle)
+
+A step = one whole frame: 4 shadow-cubemap passes (24 faces) + prearrange + depth + id resolve + deferred shading.
+N > 1: the same frame split sort-first into N screen bands, the 24 cubemap faces sharded over the ranks and
+all-gathered, the bands gathered to rank 0 over NCCL ("scaling": "strong").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from openclrenderer_b200 import scene as scn  # noqa: E402
+
+METRIC = "Mtri_per_s_4K_1Mtri_frame"
+UNIT = "Mtri/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c3_small", "c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", type=int, default=-1, help="band halo rows at N>1 (-1 = rasterise depth for every row: exact SSAO)")
+    return ap.parse_args()
+
+
+def make_scene(name):
+    if name == "c3":
+        return scn.scene_c3()
+    if name == "c5":
+        return scn.scene_c5()
+    return scn.scene_spheres(1920, 1080, 60, (10, 6), 20260, 4, 512, name="c3_small_spheres_120ktri_1920x1080_4lights")
+
+
+def config_dict(s, extra=None):
+    d = {"workload": s.name, "triangles": int(len(s.tris)), "objects": int(len(s.objs)), "resolution": f"{s.cfg.width}x{s.cfg.height}",
+         "lights": int(len(s.lights)), "shadow_lights": int((s.lights["shadow"] == 1).sum()), "light_dim": int(s.cfg.light_dim),
+         "textures": [int(t.shape[0]) for t in s.textures], "macro_profile": "A (main.cpp:80-85: SSAO_RAD=2, TEST_LINEAR)",
+         "l2": "inputs larger than L2 (per-frame working set ~0.6 GB vs 126 MB L2); camera jittered every step"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+def camera(s, i):
+    """static scene, camera jittered deterministically per step (SURVEY.md §8d timing method)."""
+    j = (i % 7) - 3
+    return (s.c_pos[0] + 3.0 * j, s.c_pos[1] + 1.0 * j, s.c_pos[2]), (s.c_rot[0] + 0.001 * j, s.c_rot[1], s.c_rot[2])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_frame_loop(s, steps, warmup, threads=0):
+    from oracle.binding import Oracle
+    o = Oracle(s.cfg, threads=threads)
+    s.upload(o)
+    times = []
+    for i in range(warmup + steps):
+        c_pos, c_rot = camera(s, i)
+        t0 = time.perf_counter()
+        o.frame_shadows(1 if i == 0 else 0)
+        o.frame_draw(c_pos, c_rot, s.clear)
+        o.swap_buffers()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    stats = {"depth_samples": o.depth_samples, "shadow_samples": o.shadow_samples, "threads": o.threads, "timings": o.timings()}
+    return times, stats
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    s = make_scene(args.workload)
+    times, st = cpu_frame_loop(s, args.steps, args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    T = len(s.tris)
+    val = T / (ms * 1e-3) / 1e6
+    sample = f"{args.steps} full frames of {s.name} (shadows + draw), mean after {args.warmup} warm-up, OpenMP over work-groups"
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": config_dict(s), "fps": round(1e3 / ms, 3),
+            "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": st["threads"], "kind": "port", "sample": sample,
+                             "note": "CPU restatement of cl2.cl (PoCL / OpenCL unavailable in the image, SURVEY.md §8c)"},
+            "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openclrenderer_b200 import Renderer, rr
+    from openclrenderer_b200._abi import RR_BUF_RGBA8, RR_BUF_SHADOW_DYNAMIC
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    s = make_scene(args.workload)
+    W, H, L = s.cfg.width, s.cfg.height, s.cfg.light_dim
+    n_shadow = int((s.lights["shadow"] == 1).sum())
+    rows = (H + world - 1) // world
+    assert H % world == 0, "band gather needs equal bands"
+    cfg = s.cfg.copy(device=local)
+    if world > 1:
+        cfg = cfg.copy(band_y0=rank * rows, band_y1=(rank + 1) * rows, band_halo=args.halo, face_rank=rank, face_world=world)
+    r = Renderer(cfg)
+    # colour target and cubemap slab live in torch tensors so torch.distributed (NCCL) can move them
+    fb = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+    r.bind_external(RR_BUF_RGBA8, fb.data_ptr(), fb.numel())
+    pairs = 6 * n_shadow
+    chunk = (pairs + world - 1) // world
+    shadow = torch.full((chunk * world * L * L,), -1, dtype=torch.int32, device=dev)
+    r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
+    s.upload(r)
+    stream = torch.cuda.ExternalStream(r.stream(), device=dev)
+    my_faces = shadow[rank * chunk * L * L:(rank + 1) * chunk * L * L]
+
+    def frame(i):
+        c_pos, c_rot = camera(s, i)
+        r.frame_shadows(0)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(shadow, my_faces)                    # faces rendered elsewhere arrive in place
+        r.frame_draw(c_pos, c_rot, s.clear)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                band = fb[rank * rows:(rank + 1) * rows]
+                dist.gather(band, [fb[k * rows:(k + 1) * rows] for k in range(world)] if rank == 0 else None, dst=0)
+        r.swap_buffers()
+
+    def barrier():
+        r.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    r.frame_shadows(1)                     # static-light pass of the first frame (none in this scene) outside the loop
+    for i in range(args.warmup):
+        frame(i)
+    barrier()
+    l0 = r.timings()["launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    tw0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        frame(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    tw1 = time.perf_counter()
+    ms_total = e0.elapsed_time(e1)
+    launches = r.timings()["launches"] - l0
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    t = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, launches = float(tmax[0]), int(tsum[1])
+    ms = ms_total / args.steps
+    T = len(s.tris)
+    val = T / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the public API with host buffers: H2D of the per-frame inputs (object descriptors from
+    # pinned memory, as object_context::flush_locations does) and D2H of the finished frame, inside the timed region
+    host_fb = rr.host_alloc((H, W, 4), np.uint8) if rank == 0 else None
+    pinned_t = torch.from_numpy(host_fb) if rank == 0 else None
+
+    def frame_e2e(i):
+        c_pos, c_rot = camera(s, i)
+        if world == 1:
+            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_fb)
+            r.swap_buffers()
+        else:
+            r.scene_write_objs(s.objs)
+            frame(i)
+            if rank == 0:
+                with torch.cuda.stream(stream):
+                    pinned_t.copy_(fb, non_blocking=True)
+            r.sync()
+
+    for i in range(3):
+        frame_e2e(i)
+    barrier()
+    te0 = time.perf_counter()
+    for i in range(args.steps):
+        frame_e2e(3 + i)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - te0) / args.steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te[0])
+    e2e = {"value": round(T / (e2e_ms * 1e-3) / 1e6, 3), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
+           "h2d_bytes_per_step": int(len(s.objs) * 144 * world + 32 * world), "d2h_bytes_per_step": int(W * H * 4)}
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u32",
+                "data": "synthetic", "config": config_dict(s, {"parallelism": f"bands{world}+faces{world}" if world > 1 else "single",
+                                                                "band_halo": args.halo if world > 1 else None}),
+                "fps": round(1e3 / ms, 2), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+
+    # ---- stage profile + roofline + CPU baseline (rank 0, N = 1 only)
+    if world == 1:
+        stage = {k: 0.0 for k in ("shadow_depth_ms", "setup_ms", "depth_ms", "id_ms", "shade_ms", "frame_ms")}
+        n_prof = 8
+        tm = None
+        for i in range(n_prof):
+            frame(1000 + i)
+            tm = r.timings()
+            for k in stage:
+                stage[k] += tm[k] / n_prof
+        # the frame just drawn is in the previous buffer after swap: swap back to read it
+        r.swap_buffers()
+        ids, depth, frags = r.read_ids(), r.read_depth(), r.read_fragments()
+        r.swap_buffers()
+        cov = depth != 0xFFFFFFFF
+        P = W * H
+        V = int(len(np.unique(frags[ids[cov], 0]))) if cov.any() else 0
+        C, F = tm["n_cutdown"], tm["n_fragments"]
+        S = n_shadow
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        atom_ms = r.microbench_atomic_min(32 << 20, 1 << 30)
+        r_atomic = (1 << 30) / (atom_ms * 1e-3)
+        copy_ms = r.microbench_copy(1 << 30)
+        # algorithmic bytes per stage
+        B = {"setup": 40 * T + 48 * C + 20 * F,
+             "shadow": S * (40 * T + 2 * 4 * 6 * L * L),
+             "depth": 4 * P,
+             "id": 8 * P,
+             "shade": 8 * P + 144 * V + 144 * len(s.objs) + 5 * P + 4 * P + 4 * P + 4 * P}
+        B_lookup = S * min(P, 6 * L * L) * 4
+        ms_of = {"setup": stage["setup_ms"], "shadow": stage["shadow_depth_ms"], "depth": stage["depth_ms"], "id": stage["id_ms"], "shade": stage["shade_ms"]}
+        dom = max(ms_of, key=lambda k: ms_of[k])
+        achieved = B[dom] / (ms_of[dom] * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": {"setup": "k_setup_main", "shadow": "k_shadow_setup+k_shadow_depth (x%d lights)" % S, "depth": "k_depth",
+                                                        "id": "k_ids", "shade": "k_shade"}[dom],
+                            "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4), "traffic": None,
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch": int(B[dom]), "avg_ms": round(ms_of[dom], 4)}
+        line["stages_ms"] = {k: round(v, 4) for k, v in stage.items()}
+        line["counts"] = {"cutdown": int(C), "fragments": int(F), "visible_tris": V, "covered_px": int(cov.sum()), "shadow_fragments": int(tm["n_shadow_fragments"])}
+        line["microbench"] = {"atomic_min_Gops": round(r_atomic / 1e9, 2), "copy_GBs": round(2 * (1 << 30) / (copy_ms * 1e-3) / 1e9, 1)}
+        if not args.no_cpu_baseline:
+            n_cpu = 5
+            times, st = cpu_frame_loop(s, n_cpu, 1)
+            cms = 1e3 * sum(times) / len(times)
+            line["cpu_baseline"] = {"value": round(T / (cms * 1e-3) / 1e6, 4), "unit": UNIT, "cores": st["threads"], "kind": "port",
+                                    "sample": f"{n_cpu} full frames of {s.name} after 1 warm-up ({cms:.0f} ms/frame), OpenMP over reference work-groups",
+                                    "ms_per_step": round(cms, 2)}
+            A_depth, A_shadow = st["depth_samples"], st["shadow_samples"]
+            B_frame = B["setup"] + B["depth"] + B["id"] + B["shade"] + B["shadow"] + B_lookup
+            t_roof_ms = 1e3 * (B_frame / (hbm * 1e9) + (A_depth + A_shadow) / r_atomic)
+            line["roofline_frame"] = {"B_frame_bytes": int(B_frame), "atomics": int(A_depth + A_shadow), "t_roof_ms": round(t_roof_ms, 4),
+                                      "frac": round(t_roof_ms / ms, 4), "formula": "B_frame/BW_hbm + (A_depth+A_shadow)/R_atomic (SURVEY.md §8d)"}
+            line["Mfrag_per_s"] = round((A_depth + A_shadow) / (ms * 1e-3) / 1e6, 1)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -95,7 +95,7 @@ typedef struct rr_config {
     /* sort-first split (no reference counterpart). 0,0 = whole screen. */
     int32_t band_y0, band_y1;      /* this context resolves ids and shades rows [band_y0, band_y1) */
     int32_t band_halo;             /* depth rows rasterised outside the band for SSAO; < 0 = every row */
-    int32_t face_rank, face_world; /* shadow (light,face) pair p is rendered here iff p % face_world == face_rank; 0,0 = all */
+    int32_t face_rank, face_world; /* shadow (light,face) pair p = 6*slab+face is rendered here iff p / ceil(6S/face_world) == face_rank; 0,0 = all */
     uint32_t max_fragments;        /* fragment-record capacity; 0 = 16 Mi (reference: 2 Mi, engine.cpp:601) */
     uint32_t max_cutdown;          /* projected-triangle capacity; 0 = derived from the triangle count */
 } rr_config;
@@ -163,6 +163,9 @@ int rr_get_timings(rr_ctx*, rr_timings* out);
 int   rr_bind_external(rr_ctx*, int which /*enum rr_buffer*/, void* device_ptr, size_t nbytes); /* render straight into caller-owned (e.g. torch / peer-mapped) memory */
 void* rr_device_ptr(rr_ctx*, int which /*enum rr_buffer*/);
 void* rr_stream(rr_ctx*);                                                                       /* cudaStream_t the context launches on */
+
+void* rr_host_alloc(size_t nbytes);            /* page-locked host memory for read-backs (CL_MEM_ALLOC_HOST_PTR role; async_read.hpp:30-60 host buffers) */
+void  rr_host_free(void* p);
 
 /* ---- host-to-host frame for e2e timing: upload camera, draw, read RGBA8 back into pinned host memory ------------ */
 int rr_frame_e2e(rr_ctx*, const float c_pos[4], const float c_rot[4], const float clear_rgba[4],

@@ -101,7 +101,6 @@ struct rr_ctx {
     uint32_t* h_counters = nullptr;      // pinned
     // e2e staging (pinned)
     rr_obj_desc* h_objs_pinned = nullptr;
-    uint8_t* h_rgba_pinned = nullptr;
     // stats
     uint32_t launches = 0;
     FaceTable faces;
@@ -207,7 +206,6 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaMalloc((void**)&c->d_frags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("fragment buffer");
     if (cudaMalloc((void**)&c->d_counters, CTR_COUNT * 4) != cudaSuccess) return bail("counters");
     if (cudaMallocHost((void**)&c->h_counters, CTR_COUNT * 4) != cudaSuccess) return bail("pinned counters");
-    if (cudaMallocHost((void**)&c->h_rgba_pinned, P * 4) != cudaSuccess) return bail("pinned frame");
     cudaMemsetAsync(c->d_counters, 0, CTR_COUNT * 4, c->stream);
     // depth_buffer[0..1] start at UINT_MAX (object_context.cpp:43-52); the id image starts at 0
     for (int i = 0; i < 2; i++) {
@@ -233,7 +231,6 @@ void rr_destroy(rr_ctx* c) {
     cudaFree(c->d_normals); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
-    if (c->h_rgba_pinned) cudaFreeHost(c->h_rgba_pinned);
     for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -382,9 +379,13 @@ int rr_lights_write(rr_ctx* c, const rr_light* lights, uint32_t n_active) {
 
 // ---- per frame -----------------------------------------------------------------------------------------------------
 static int shadow_pass(rr_ctx* c, const rr_light& l, int only_static, uint32_t* slab, uint32_t pair_base) {
+    // (light, face) pairs are owned in contiguous chunks of ceil(total / face_world) so that the owned part of the
+    // cubemap buffer is one contiguous range (in-place all-gather across contexts).
     uint32_t mask = 0;
+    const uint32_t total_pairs = 6u * (only_static ? c->n_static : c->n_shadow);
+    const uint32_t chunk = c->cfg.face_world > 1 ? (total_pairs + c->cfg.face_world - 1) / c->cfg.face_world : total_pairs;
     for (int kk = 0; kk < 6; kk++) {
-        bool mine = c->cfg.face_world <= 1 || ((pair_base + kk) % (uint32_t)c->cfg.face_world) == (uint32_t)c->cfg.face_rank;
+        bool mine = c->cfg.face_world <= 1 || ((pair_base + kk) / chunk) == (uint32_t)c->cfg.face_rank;
         if (mine) mask |= 1u << kk;
     }
     if (!mask || c->n_tris == 0) return RR_OK;
@@ -428,7 +429,7 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
             nn++;
         }
         if (l.shadow && l.is_static && static_lights_dirty) {
-            if ((r = shadow_pass(c, l, 1, c->d_shadow_static + slab * kk, (c->n_shadow + kk) * 6))) return r;
+            if ((r = shadow_pass(c, l, 1, c->d_shadow_static + slab * kk, kk * 6))) return r;
             kk++;
         }
     }
@@ -604,6 +605,13 @@ void* rr_device_ptr(rr_ctx* c, int which) {
 }
 void* rr_stream(rr_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+void* rr_host_alloc(size_t nbytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) { fail(RR_ERR_OOM, "rr_host_alloc(%zu) failed", nbytes); return nullptr; }
+    return p;
+}
+void rr_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 // ---- host-to-host frame --------------------------------------------------------------------------------------------
 int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const float clear_rgba[4], int with_shadows, uint8_t* host_rgba8) {
     if (!c || !host_rgba8) return fail(RR_ERR_INVALID, "null argument");
@@ -615,14 +623,11 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     }
     if (with_shadows && (r = rr_frame_shadows(c, 0))) return r;
     if ((r = rr_frame_draw(c, c_pos, c_rot, clear_rgba))) return r;
-    const size_t P = (size_t)c->W * c->H;
     int band0, band1, row0, row1;
     band_rows(c, band0, band1, row0, row1);
     const size_t off = (size_t)band0 * c->W * 4, len = (size_t)(band1 - band0) * c->W * 4;
-    (void)P;
-    CU(cudaMemcpyAsync(c->h_rgba_pinned + off, (uint8_t*)c->d_rgba8 + off, len, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(host_rgba8 + off, (uint8_t*)c->d_rgba8 + off, len, cudaMemcpyDeviceToHost, c->stream));   // direct DMA when host_rgba8 is pinned (rr_host_alloc)
     CU(cudaStreamSynchronize(c->stream));
-    memcpy(host_rgba8 + off, c->h_rgba_pinned + off, len);
     if ((r = rr_swap_buffers(c))) return r;
     return RR_OK;
 }

@@ -35,11 +35,30 @@ def load_library():
         _LIB.rr_stream.argtypes = [_P]
         _LIB.rr_frame_e2e.restype = C.c_int
         _LIB.rr_frame_e2e.argtypes = [_P, _F4, _F4, _F4, C.c_int, _P]
+        _LIB.rr_host_alloc.restype = _P
+        _LIB.rr_host_alloc.argtypes = [C.c_size_t]
+        _LIB.rr_host_free.argtypes = [_P]
         _LIB.rr_microbench_atomic_min.restype = C.c_int
         _LIB.rr_microbench_atomic_min.argtypes = [_P, C.c_size_t, C.c_uint64, C.POINTER(C.c_float)]
         _LIB.rr_microbench_copy.restype = C.c_int
         _LIB.rr_microbench_copy.argtypes = [_P, C.c_size_t, C.POINTER(C.c_float)]
     return _LIB
+
+
+def host_alloc(shape, dtype=np.uint8):
+    """numpy array over page-locked memory from rr_host_alloc (freed when the array's base is collected)."""
+    lib = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.rr_host_alloc(n)
+    if not p:
+        raise RRError(-3, "rr_host_alloc failed")
+    buf = (C.c_uint8 * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED[id(buf)] = (buf, p)
+    return arr
+
+
+_PINNED = {}
 
 
 def fov_const_from_hfov(hfov_deg, width):

@@ -276,9 +276,9 @@ def scene_c2(width=1920, height=1080, light_dim=1024):
 # synthetic tessellated-sphere field (configs 3-5)
 # ---------------------------------------------------------------------------------------------------------------------
 def uv_sphere(slices=40, stacks=26):
-    """Unit UV sphere: `stacks` latitude rings incl. the two poles -> 2*slices*(stacks-1) triangles (40x26 -> 2000),
-    poles as single fans, outward winding, smooth normals (= positions), spherical UVs."""
-    bands = stacks - 1
+    """Unit UV sphere: `stacks` latitude bands, the two polar bands as single fans -> 2*slices*(stacks-1) triangles
+    (40 x 26 -> 2000), outward winding, smooth normals (= positions), spherical UVs."""
+    bands = stacks
 
     def vert(i, j):
         th = math.pi * i / bands

@@ -1,0 +1,186 @@
+"""-m gpu: CUDA product vs CPU oracle through the C ABI, on the configurations of BASELINE.json at sizes the oracle
+finishes in seconds, plus size-independent properties at full size."""
+import numpy as np
+import pytest
+
+from openclrenderer_b200 import Renderer, scene
+from openclrenderer_b200._abi import Config, TRIANGLE, OBJ_DESC, LIGHT, FEATURE_TWO_SIDED, FEATURE_IS_STATIC, FEATURE_NO_DYNAMIC_SHADOWS
+from oracle.binding import Oracle
+from tests.parity import render_both, assert_frame_parity, colour_stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("profile", ["A", "B"])
+def test_c1_cube(profile):
+    s = scene.scene_c1(profile)
+    g, o = render_both(s, frames=2)
+    st = assert_frame_parity(g, o, label=f"c1/{profile}")
+    assert st["covered"] > 10000
+
+
+def test_c1_atlas_bit_exact():
+    s = scene.scene_c1()
+    g, o = Renderer(s.cfg), Oracle(s.cfg)
+    s.upload(g), s.upload(o)
+    assert np.array_equal(g.atlas_read_raw(), o.atlas_read_raw())
+
+
+def test_c2_cylinder_shadowed():
+    s = scene.scene_c2()
+    g, o = render_both(s, frames=2, threads=0)
+    assert np.array_equal(g.read_shadow(0, 0), o.read_shadow(0, 0)), "shadow cubemap differs"
+    st = assert_frame_parity(g, o, label="c2")
+    assert st["covered"] > 100000
+
+
+def test_c2_atlas_bit_exact():
+    s = scene.scene_c2(640, 360, 256)
+    g, o = Renderer(s.cfg), Oracle(s.cfg)
+    s.upload(g), s.upload(o)
+    assert np.array_equal(g.atlas_read_raw(), o.atlas_read_raw())
+
+
+def test_spheres_small_all_features():
+    """scaled-down config 3: 24 spheres (48k triangles), multi-slice atlas with mips, 4 shadow lights, 960x540."""
+    s = scene.scene_spheres(960, 540, n_spheres=24, grid=(6, 4), seed=7, n_lights=4, light_dim=256, tex_sizes=(256, 128, 64, 64))
+    # make the scene exercise the feature flags: two-sided, static (skipped by dynamic shadow passes), no-dynamic-shadow receivers
+    s.objs["feature_flag"][::5] |= FEATURE_TWO_SIDED
+    s.objs["feature_flag"][1::7] |= FEATURE_IS_STATIC
+    s.objs["feature_flag"][2::9] |= FEATURE_NO_DYNAMIC_SHADOWS
+    s.lights["is_static"][1] = 1
+    g, o = render_both(s, frames=2, threads=0)
+    for k in range(4):
+        assert np.array_equal(g.read_shadow(0, k), o.read_shadow(0, k)), f"dynamic cubemap {k} differs"
+    assert np.array_equal(g.read_shadow(1, 0), o.read_shadow(1, 0)), "static cubemap differs"
+    assert_frame_parity(g, o, label="spheres24")
+
+
+def _soup(seed, n, w, h, big=False):
+    """random triangle soup in front of (and through) the camera: near-plane clipping, screen-edge clamping, huge bboxes."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tris = np.zeros(n, dtype=TRIANGLE)
+    c = rng.uniform([-600, -400, -100], [600, 400, 1500], size=(n, 1, 3))
+    ext = rng.uniform(5, 900 if big else 120, size=(n, 1, 1))
+    tris["vertices"]["pos"][:, :, :3] = (c + rng.normal(size=(n, 3, 3)) * ext).astype(np.float32)
+    nrm = rng.normal(size=(n, 3, 3))
+    tris["vertices"]["normal"][:, :, :3] = (nrm / np.linalg.norm(nrm, axis=-1, keepdims=True)).astype(np.float32)
+    tris["vertices"]["vt"] = rng.uniform(-1.5, 2.5, size=(n, 3, 2)).astype(np.float32)
+    col = rng.integers(1, 2 ** 32, size=(n, 1), dtype=np.uint64).astype(np.uint32)
+    tris["vertices"]["vertex_col"] = np.where(rng.uniform(size=(n, 1)) < 0.3, col, 0)          # 30 % vertex-coloured
+    tris["vertices"]["object_id"][:, 0] = rng.integers(0, 3, size=n)
+    objs = np.array([scene.make_obj_desc(pos=(0, 0, 200), scale=1.0, tid=0, feature_flag=FEATURE_TWO_SIDED),
+                     scene.make_obj_desc(pos=(50, -20, 300), quat=(0.1, 0.7, 0.2, 0.6), scale=0.8, tid=1),
+                     scene.make_obj_desc(pos=(-80, 60, 500), quat=(-0.3, 0.2, 0.9, 0.1), scale=1.7, tid=0, specular=0.5)], dtype=OBJ_DESC)
+    lights = np.array([scene.make_light((300, -500, -200), shadow=1), scene.make_light((-400, 300, 100), col=(0.9, 0.8, 1.0), shadow=0)], dtype=LIGHT)
+    cfg = Config.default(w, h, light_dim=128)
+    tex = [scene.procedural_texture(64, 5), scene.procedural_texture(128, 6)]
+    return scene.Scene(cfg, tris, objs, lights, tex, c_pos=(10, -20, -150), c_rot=(0.1, -0.2, 0.05), clear=(0.1, 0.2, 0.3, 1.0), name=f"soup{seed}")
+
+
+@pytest.mark.parametrize("seed,big", [(1, False), (2, True), (3, True)])
+def test_triangle_soup(seed, big):
+    s = _soup(seed, 600 if big else 3000, 640, 360, big)
+    g, o = render_both(s, frames=2, threads=0)
+    assert np.array_equal(g.read_shadow(0, 0), o.read_shadow(0, 0))
+    assert_frame_parity(g, o, label=s.name)
+
+
+def test_odd_resolution_and_empty_scene():
+    s = _soup(4, 500, 333, 217, True)
+    g, o = render_both(s, frames=1, threads=0)
+    assert_frame_parity(g, o, label="odd")
+    # empty scene: draw is a no-op (engine.cpp:1806), buffers stay cleared
+    cfg = Config.default(64, 48)
+    g2 = Renderer(cfg)
+    g2.scene_alloc(0, 0)
+    g2.lights_write(np.zeros(0, dtype=LIGHT))
+    g2.frame_draw((0, 0, 0), (0, 0, 0))
+    g2.sync()
+    assert (g2.read_depth() == 0xFFFFFFFF).all()
+
+
+def test_band_split_equals_full_frame():
+    """sort-first bands: compositing the bands of 4 contexts == the single-context frame, bit for bit."""
+    s = scene.scene_spheres(640, 384, n_spheres=12, grid=(4, 3), seed=11, n_lights=2, light_dim=128, tex_sizes=(128, 64))
+    full = Renderer(s.cfg)
+    s.upload(full)
+    s.render(full, frames=2)
+    fd, fi, fc = full.read_depth(), full.read_ids(), full.read_rgba8()
+    n = 4
+    for k in range(n):
+        y0, y1 = k * 96, (k + 1) * 96
+        cfg = s.cfg.copy(band_y0=y0, band_y1=y1, band_halo=-1, face_rank=0, face_world=0)
+        b = Renderer(cfg)
+        s.upload(b)
+        s.render(b, frames=2)
+        assert np.array_equal(b.read_depth()[y0:y1], fd[y0:y1])
+        cov = fd[y0:y1] != 0xFFFFFFFF
+        assert np.array_equal(b.read_ids()[y0:y1][cov], fi[y0:y1][cov])
+        assert np.array_equal(b.read_rgba8()[y0:y1], fc[y0:y1])
+
+
+def test_face_sharding_union_equals_full_cubemap():
+    """shadow (light, face) pairs split over 3 contexts: the element-wise min of their slabs == the full cubemap."""
+    s = scene.scene_spheres(320, 200, n_spheres=12, grid=(4, 3), seed=13, n_lights=2, light_dim=128, tex_sizes=(64,))
+    full = Renderer(s.cfg)
+    s.upload(full)
+    full.frame_shadows(1)
+    full.sync()
+    ref = [full.read_shadow(0, k) for k in range(2)]
+    acc = [np.full_like(ref[0], 0xFFFFFFFF) for _ in range(2)]
+    for rank in range(3):
+        b = Renderer(s.cfg.copy(face_rank=rank, face_world=3))
+        s.upload(b)
+        b.frame_shadows(1)
+        b.sync()
+        for k in range(2):
+            part = b.read_shadow(0, k)
+            owned = [(k * 6 + f) // 4 == rank for f in range(6)]      # 12 pairs over 3 contexts -> chunks of 4
+            for f in range(6):
+                if not owned[f]:
+                    assert (part[f] == 0xFFFFFFFF).all()
+            acc[k] = np.minimum(acc[k], part)
+    for k in range(2):
+        assert np.array_equal(acc[k], ref[k])
+
+
+def test_overflow_is_reported():
+    s = _soup(5, 400, 320, 200, True)
+    cfg = s.cfg.copy(max_fragments=64)
+    g = Renderer(cfg)
+    s.upload(g)
+    g.frame_draw(s.c_pos, s.c_rot)
+    from openclrenderer_b200 import RRError
+    with pytest.raises(RRError) as e:
+        g.sync()
+    assert e.value.code == -4
+
+
+def test_full_size_properties_c3():
+    """config 3 at full size (1 M triangles, 3840x2160, 4 shadow lights): properties that need no oracle run.
+    determinism (two contexts, identical buffers), idempotence (re-rendering the same frame gives the same frame),
+    id/depth consistency (every covered pixel's id names a fragment whose triangle covers that pixel at that depth +-20)."""
+    s = scene.scene_c3()
+    a = Renderer(s.cfg)
+    s.upload(a)
+    s.render(a, frames=2)
+    d1, i1, c1 = a.read_depth(), a.read_ids(), a.read_rgba8()
+    a.swap_buffers()
+    a.frame_shadows(0)
+    a.frame_draw(s.c_pos, s.c_rot, s.clear)
+    a.sync()
+    assert np.array_equal(a.read_depth(), d1) and np.array_equal(a.read_ids(), i1) and np.array_equal(a.read_rgba8(), c1)
+    b = Renderer(s.cfg)
+    s.upload(b)
+    s.render(b, frames=1)
+    assert np.array_equal(b.read_depth(), d1) and np.array_equal(b.read_ids(), i1) and np.array_equal(b.read_rgba8(), c1)
+    cov = d1 != 0xFFFFFFFF
+    assert cov.sum() > 100000
+    frags = a.read_fragments()
+    assert i1[cov].max() < len(frags)
+    # fragment records are prefix sums in triangle order: triangle ids non-decreasing, chunk numbers restart at 0
+    assert (np.diff(frags[:, 0].astype(np.int64)) >= 0).all()
+    assert (np.diff(frags[:, 2].astype(np.int64)) >= 0).all()
+    t = a.timings()
+    assert t["overflow"] == 0 and t["n_fragments"] == len(frags)
