@@ -164,34 +164,31 @@ def run_ours(args):
     s = make_scene(args.workload)
     W, H, L = s.cfg.width, s.cfg.height, s.cfg.light_dim
     n_shadow = int((s.lights["shadow"] == 1).sum())
-    rows = (H + world - 1) // world
-    assert H % world == 0, "band gather needs equal bands"
+    from openclrenderer_b200 import distributed as rrd
+    rows = H // world
     cfg = s.cfg.copy(device=local)
     if world > 1:
-        cfg = cfg.copy(band_y0=rank * rows, band_y1=(rank + 1) * rows, band_halo=args.halo, face_rank=rank, face_world=world)
+        cfg = rrd.band_config(cfg, world, rank, args.halo)
     r = Renderer(cfg)
     # colour target and cubemap slab live in torch tensors so torch.distributed (NCCL) can move them
     fb = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
     r.bind_external(RR_BUF_RGBA8, fb.data_ptr(), fb.numel())
-    pairs = 6 * n_shadow
-    chunk = (pairs + world - 1) // world
+    chunk = rrd.face_chunk(n_shadow, world)
     shadow = torch.full((chunk * world * L * L,), -1, dtype=torch.int32, device=dev)
     r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
     s.upload(r)
     stream = torch.cuda.ExternalStream(r.stream(), device=dev)
-    my_faces = shadow[rank * chunk * L * L:(rank + 1) * chunk * L * L]
 
     def frame(i):
         c_pos, c_rot = camera(s, i)
         r.frame_shadows(0)
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(shadow, my_faces)                    # faces rendered elsewhere arrive in place
+                rrd.all_gather_faces(shadow, chunk * L * L, rank)                # faces rendered elsewhere arrive in place
         r.frame_draw(c_pos, c_rot, s.clear)
         if world > 1:
             with torch.cuda.stream(stream):
-                band = fb[rank * rows:(rank + 1) * rows]
-                dist.gather(band, [fb[k * rows:(k + 1) * rows] for k in range(world)] if rank == 0 else None, dst=0)
+                rrd.gather_bands(fb, rows, rank, world, dst=0)
         r.swap_buffers()
 
     def barrier():

@@ -1,8 +1,5 @@
-"""Build recipes (in-tree, offline): the sm_100a product library, the CPU oracle, and — when the reference tree is
-present — oracle/_ref (cl2.cl's own source ranges compiled as C++ through oracle/cl_shim.h).
-
-Only the first is product. The other two are checkers; building a checker is not using it.
-"""
+"""Build recipe of the product (in-tree, offline): csrc/*.cu -> librr_b200.so for sm_100a.
+(The checkers have their own recipe in oracle/build.py.)"""
 import os
 import shutil
 import subprocess
@@ -11,9 +8,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "openclrenderer_b200", "csrc")
 LIB_PRODUCT = os.path.join(ROOT, "openclrenderer_b200", "librr_b200.so")
-LIB_ORACLE = os.path.join(ROOT, "oracle", "liboracle.so")
-LIB_REF = os.path.join(ROOT, "oracle", "_ref", "libcl2ref.so")
-REFERENCE = "/root/reference"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -47,32 +41,5 @@ def build_product(force=False, verbose=False):
     return LIB_PRODUCT
 
 
-def build_oracle(force=False):
-    """g++ -O2 -ffp-contract=off -fopenmp -> oracle/liboracle.so (test infrastructure)"""
-    srcs = [os.path.join(ROOT, "oracle", "oracle.cpp"), os.path.join(ROOT, "include", "rr.h")]
-    if not force and _newer(LIB_ORACLE, srcs):
-        return LIB_ORACLE
-    _run(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC", "-o", LIB_ORACLE, srcs[0]])
-    return LIB_ORACLE
-
-
-def build_ref(force=False):
-    """oracle/_ref/libcl2ref.so from /root/reference/cl2.cl (only where the reference tree exists)."""
-    if not os.path.isdir(REFERENCE):
-        return LIB_REF if os.path.exists(LIB_REF) else None
-    script = os.path.join(ROOT, "oracle", "build_ref.py")
-    if not os.path.exists(script):
-        return None
-    srcs = [script, os.path.join(ROOT, "oracle", "cl_shim.h"), os.path.join(ROOT, "oracle", "ref_driver.cpp")]
-    if not force and _newer(LIB_REF, [s for s in srcs if os.path.exists(s)]):
-        return LIB_REF
-    _run([sys.executable, script])
-    return LIB_REF
-
-
-def build_all(force=False):
-    return build_product(force), build_oracle(force), build_ref(force)
-
-
 if __name__ == "__main__":
-    print(build_all(force="--force" in sys.argv))
+    print(build_product(force="--force" in sys.argv, verbose="-v" in sys.argv))

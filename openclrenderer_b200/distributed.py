@@ -1,0 +1,48 @@
+"""Sort-first multi-GPU plumbing: one process per GPU, torch.distributed for the exchange.
+
+  bands       : the screen is cut into `world` equal horizontal bands; rank k resolves ids and shades rows [k*rows, (k+1)*rows)
+                and the finished bands are gathered to rank 0 (RGBA8, 4*W*H*(world-1)/world bytes over NVLink).
+  shadow faces: the 6*S (light, face) cubemap faces are owned in contiguous chunks of ceil(6S/world); every rank renders
+                its chunk, then one in-place all-gather makes all faces visible everywhere (4*L*L bytes per face).
+
+Works on any backend: NCCL on the B200s, gloo in the CPU tests (tests/test_multiproc_gloo.py).
+"""
+import torch
+import torch.distributed as dist
+
+
+def band_rows(height, world, rank):
+    if height % world:
+        raise ValueError(f"height {height} is not divisible into {world} equal bands")
+    rows = height // world
+    return rank * rows, (rank + 1) * rows
+
+
+def face_chunk(n_shadow_lights, world):
+    """faces per rank; the cubemap buffer is padded to chunk*world faces so the all-gather is uniform."""
+    pairs = 6 * n_shadow_lights
+    return (pairs + world - 1) // world
+
+
+def band_config(cfg, world, rank, halo=-1):
+    y0, y1 = band_rows(cfg.height, world, rank)
+    return cfg.copy(band_y0=y0, band_y1=y1, band_halo=halo, face_rank=rank, face_world=world)
+
+
+def all_gather_faces(shadow_flat, chunk_words, rank, group=None):
+    """shadow_flat: 1-D int32/uint32 tensor of chunk_words*world words holding this rank's faces at [rank*chunk_words, ...)."""
+    mine = shadow_flat[rank * chunk_words:(rank + 1) * chunk_words]
+    dist.all_gather_into_tensor(shadow_flat, mine, group=group)
+
+
+def gather_bands(fb, rows, rank, world, dst=0, group=None):
+    """fb: (H, W, 4) uint8 tensor; rank k's band is fb[k*rows:(k+1)*rows]; after the call rank `dst` holds the whole frame."""
+    band = fb[rank * rows:(rank + 1) * rows]
+    if dist.get_backend(group) == "gloo":
+        lst = [torch.empty_like(band) for _ in range(world)] if rank == dst else None
+        dist.gather(band.contiguous(), lst, dst=dst, group=group)
+        if rank == dst:
+            for k in range(world):
+                fb[k * rows:(k + 1) * rows].copy_(lst[k])
+    else:
+        dist.gather(band, [fb[k * rows:(k + 1) * rows] for k in range(world)] if rank == dst else None, dst=dst, group=group)

@@ -15,8 +15,8 @@ def load_oracle():
     if _LIB is None:
         path = os.path.join(_HERE, "liboracle.so")
         if not os.path.exists(path):
-            from openclrenderer_b200 import _build
-            _build.build_oracle()
+            from oracle import build as obuild
+            obuild.build_oracle()
         _LIB = C.CDLL(path)
         L = _LIB
         L.orc_fov_const_from_hfov.restype = C.c_float

@@ -11,9 +11,9 @@
 // round() == half away from zero, min/max == fminf/fmaxf, allocation order == sequential global-id order (so cutdown
 // ids and fragment ids are exclusive prefix sums in triangle order, and the id winner is the highest fragment index).
 //
-// Parity pin: the reference holds no golden vectors or tests for this path. The pin is oracle/_ref
-// (cl2.cl's own source ranges compiled as C++ through oracle/cl_shim.h, see oracle/build_ref.py) plus the fixtures it
-// generated under tests/golden/.
+// Parity pin: the reference holds no golden vectors or tests for this path. The pin is the reference
+// itself: oracle/ref_opencl.py runs the unmodified cl2.cl through the NVIDIA OpenCL ICD on the GPU box
+// (tests/test_gpu_reference_cl.py) and tests/golden/ holds the outputs it produced (tests/golden/make_golden.py).
 //
 // Each function cites the cl2.cl lines it restates.
 
@@ -503,7 +503,15 @@ face_tab make_face_tab() {       // r_struct, cl2.cl:4487-4511 / 2538-2558, floa
     return t;
 }
 
-void shadow_pass(orc_ctx* c, const float lpos4[4], int only_static, uint32_t* slab) {
+void shadow_pass(orc_ctx* c, const float lpos4[4], int only_static, uint32_t* slab, uint32_t pair_base) {
+    // (light, face) pair ownership of the sort-first split (include/rr.h rr_config.face_rank/face_world)
+    bool owned[6];
+    {
+        const uint32_t total = 6u * (only_static ? c->n_static : c->n_shadow);
+        const uint32_t world = c->cfg.face_world > 1 ? (uint32_t)c->cfg.face_world : 1u;
+        const uint32_t chunk = (total + world - 1) / world;
+        for (int kk = 0; kk < 6; kk++) owned[kk] = world <= 1 || ((pair_base + kk) / chunk) == (uint32_t)c->cfg.face_rank;
+    }
     const uint32_t T = (uint32_t)c->tris.size();
     const float L = (float)c->L;
     const float efov = L / 2.0f;
@@ -533,7 +541,7 @@ void shadow_pass(orc_ctx* c, const float lpos4[4], int only_static, uint32_t* sl
         }
         bool two_sided = (feature_flag & RR_FEATURE_TWO_SIDED) > 0;
         for (int kk = 0; kk < 6; kk++) {
-            if (!skip_structure[kk]) continue;
+            if (!skip_structure[kk] || !owned[kk]) continue;
             f3 proj[2][3];
             int num = 0;
             full_rotate_quat(v3(Tt.vertices[0].pos), v3(Tt.vertices[1].pos), v3(Tt.vertices[2].pos), proj, &num, lpos, ft.r[kk],
@@ -1135,13 +1143,11 @@ int orc_frame_shadows(orc_ctx* c, int static_dirty) {
     for (size_t i = 0; i < c->lights.size(); i++) {
         const rr_light& l = c->lights[i];
         if (l.shadow == 1) {
-            uint32_t pair0 = nn * 6;
-            (void)pair0;
-            shadow_pass(c, l.pos, 0, &c->shadow_dyn[slab * nn]);
+            shadow_pass(c, l.pos, 0, &c->shadow_dyn[slab * nn], nn * 6);
             nn++;
         }
         if (l.shadow && l.is_static && static_dirty) {
-            shadow_pass(c, l.pos, 1, &c->shadow_static[slab * kk]);
+            shadow_pass(c, l.pos, 1, &c->shadow_static[slab * kk], kk * 6);
             kk++;
         }
     }
@@ -1202,12 +1208,14 @@ int orc_write_shadow(orc_ctx* c, int is_static, uint32_t slab, const uint32_t* s
 int orc_read_fragments(orc_ctx* c, uint32_t* d, uint32_t max_records, uint32_t* n) {
     uint32_t k = std::min(max_records, c->n_frags);
     if (d) memcpy(d, c->frags.data(), (size_t)k * FRAG_MUL * 4);
-    if (n) *n = c->n_frags; return RR_OK;
+    if (n) *n = c->n_frags;
+    return RR_OK;
 }
 int orc_read_cutdown(orc_ctx* c, float* d, uint32_t max_tris, uint32_t* n) {
     uint32_t k = std::min(max_tris, c->n_cut);
     if (d) memcpy(d, c->cutdown.data(), (size_t)k * 48);
-    if (n) *n = c->n_cut; return RR_OK;
+    if (n) *n = c->n_cut;
+    return RR_OK;
 }
 int orc_get_timings(orc_ctx* c, rr_timings* t) { *t = c->tm; return RR_OK; }
 uint64_t orc_depth_samples(orc_ctx* c) { return c->depth_samples; }

@@ -14,8 +14,8 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def oracle_lib():
-    from openclrenderer_b200 import _build
-    _build.build_oracle()
+    from oracle import build as obuild
+    obuild.build_oracle()
     from oracle.binding import load_oracle
     return load_oracle()
 
