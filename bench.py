@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c3_small", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-opencl-reference", action="store_true")
     ap.add_argument("--halo", type=int, default=-1, help="band halo rows at N>1 (-1 = rasterise depth for every row: exact SSAO)")
     return ap.parse_args()
 
@@ -102,6 +103,48 @@ def run_reference(args):
                              "note": "CPU restatement of cl2.cl (PoCL / OpenCL unavailable in the image, SURVEY.md §8c)"},
             "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def opencl_reference(s, steps):
+    """The reference's own, unmodified cl2.cl kernels on the same B200 through the NVIDIA OpenCL ICD, launched as
+    engine.cpp launches them in steady state. Reported beside the CUDA path; a checker/baseline, never the product."""
+    from oracle import ref_opencl
+    if not ref_opencl.available():
+        raise RuntimeError("NVIDIA OpenCL ICD or oracle/_ref/cl2.cl.gz not present")
+    T = len(s.tris)
+
+    def run(profile):
+        r = ref_opencl.RefCL(s.cfg, mode="shipped", profile=profile)
+        s.upload(r)
+        for i in range(2):
+            c_pos, c_rot = camera(s, i)
+            r.frame_shadows(1 if i == 0 else 0)
+            r.frame_draw(c_pos, c_rot, s.clear)
+            r.swap_buffers()
+        r.sync()
+        r.enter_steady_state()
+        return r
+    r = run(False)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        c_pos, c_rot = camera(s, 2 + i)
+        r.frame_shadows(0)
+        r.frame_draw(c_pos, c_rot, s.clear)
+        r.swap_buffers()
+    r.sync()
+    ms = 1e3 * (time.perf_counter() - t0) / steps
+    rp = run(True)
+    rp.kernel_ms.clear()
+    for i in range(3):
+        c_pos, c_rot = camera(s, 2 + i)
+        rp.frame_shadows(0)
+        rp.frame_draw(c_pos, c_rot, s.clear)
+        rp.swap_buffers()
+    kernels = {k: round(sum(v) / 3, 4) for k, v in rp.kernel_ms.items()}
+    return {"ms_per_step": round(ms, 4), "value": round(T / (ms * 1e-3) / 1e6, 3), "unit": UNIT, "fps": round(1e3 / ms, 2), "steps": steps,
+            "kernels_ms_per_frame": kernels, "kernel_sum_ms": round(sum(kernels.values()), 4), "build_options": r.options,
+            "what": "unmodified cl2.cl (prearrange, kernel1, kernel2, kernel3, *_realtime_shadowing) via NVIDIA OpenCL on the same GPU, "
+                    "launch sizes from the previous frame's counts as engine.cpp does; wall clock over clFinish"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -330,6 +373,11 @@ def run_ours(args):
             line["roofline_frame"] = {"B_frame_bytes": int(B_frame), "atomics": int(A_depth + A_shadow), "t_roof_ms": round(t_roof_ms, 4),
                                       "frac": round(t_roof_ms / ms, 4), "formula": "B_frame/BW_hbm + (A_depth+A_shadow)/R_atomic (SURVEY.md §8d)"}
             line["Mfrag_per_s"] = round((A_depth + A_shadow) / (ms * 1e-3) / 1e6, 1)
+    if world == 1 and not args.no_opencl_reference:
+        try:
+            line["reference_opencl_b200"] = opencl_reference(s, min(args.steps, 20))
+        except Exception as e:                         # informative only; never fails the bench
+            line["reference_opencl_b200"] = {"unavailable": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

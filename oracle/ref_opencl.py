@@ -195,6 +195,8 @@ class RefCL:
         self.kernel_ms = {}
         self.shadow_counts = []
         self.steady_count = None
+        self.steady = False
+        self.steady_shadow_counts = []
 
     # ---- helpers
     def _buf(self, arr=None, nbytes=None, flags=CL_MEM_READ_WRITE):
@@ -331,9 +333,13 @@ class RefCL:
         self._run("prearrange_realtime_shadowing", [self.g_tri_mem, self.g_tri_num, self._f4(light["pos"]), no_rot, self.g_tid_buf, self.g_tid_buf_max_len,
                                                     self.cnt_light, self.cut_num, self.g_cut_tri_mem, self.g_obj_desc, np.array([only_static], np.int32)],
                   (self.n_tris,), (256,))
-        cnt = self._read(self.cnt_light, np.zeros(1, np.uint32))
-        self.shadow_counts.append(int(cnt[0]))
-        fragments_number = int(cnt[0] * 1.1) + 256                                # engine.cpp:1682 (count is the current one: converged state)
+        idx = len(self.shadow_counts)
+        if self.steady and idx < len(self.steady_shadow_counts):
+            c0 = self.steady_shadow_counts[idx]          # engine.cpp:1680: non-blocking read, i.e. the previous frame's count
+        else:
+            c0 = int(self._read(self.cnt_light, np.zeros(1, np.uint32))[0])
+        self.shadow_counts.append(c0)
+        fragments_number = int(c0 * 1.1) + 256                                    # engine.cpp:1682
         self._run("kernel1_realtime_shadowing", [self.g_tri_mem, self.g_tid_buf, self._slab_scratch, self.cnt_light, self.g_cut_tri_mem], (fragments_number,), (256,))
         _chk(self.cl.clEnqueueCopyBuffer(self.q, self._slab_scratch, slab_buf, 0, slab_index * slab_bytes, slab_bytes, 0, None, None), "copy slab")
 
@@ -381,6 +387,13 @@ class RefCL:
                 u(1 if self.cfg.use_linear_rendering else 0)]
         self._run("kernel3", args, (self.W, self.H), (16, 16))
         self.frame_id += 1
+
+    def enter_steady_state(self):
+        """after a converged frame: launch sizes come from that frame's counts with no blocking reads, as the engine's
+        stale asynchronous reads do in steady state (engine.cpp:1680, 1836; object_context.cpp:8-15)."""
+        self.steady = True
+        self.steady_shadow_counts = list(self.shadow_counts)
+        self.steady_count = self.last_count
 
     def swap_buffers(self):
         self.cur ^= 1
