@@ -281,8 +281,7 @@ def run_ours(args):
     def frame_e2e(i):
         c_pos, c_rot = camera(s, i)
         if world == 1:
-            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_fb)
-            r.swap_buffers()
+            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_fb)        # swaps buffers itself
         else:
             r.scene_write_objs(s.objs)
             frame(i)

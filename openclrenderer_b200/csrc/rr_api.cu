@@ -98,6 +98,10 @@ struct rr_ctx {
     uint32_t* d_counters = nullptr;
     unsigned long long* d_lookback = nullptr;
     uint32_t lookback_blocks = 0;
+    uint32_t* d_fragcnt = nullptr;               // per-fragment pixel-slot counts
+    uint32_t *d_biglist = nullptr, *d_bigslot = nullptr;   // compacted big fragments + exclusive prefix of their slots (k_scan_big)
+    unsigned long long* d_scan_lookback = nullptr;
+    uint32_t scan_tiles = 0;
     uint32_t* h_counters = nullptr;      // pinned
     // e2e staging (pinned)
     rr_obj_desc* h_objs_pinned = nullptr;
@@ -132,6 +136,26 @@ int ensure_objlite(rr_ctx* c) {
     c->launches++;
     CU(cudaGetLastError());
     c->objlite_dirty = false;
+    return RR_OK;
+}
+
+// compact the big fragments of the list whose length is counters[n_index] and prefix-sum their slot counts
+int scan_big(rr_ctx* c, int n_index, uint32_t cap) {
+    CU(cudaMemsetAsync(c->d_counters + CTR_SLOTS, 0, 3 * 4, c->stream));                   // CTR_SLOTS, CTR_SCAN_TICKET, CTR_NBIG
+    CU(cudaMemsetAsync(c->d_scan_lookback, 0, (size_t)c->scan_tiles * 8, c->stream));
+    k_scan_big<<<grid_for(c, 2), SCAN_THREADS, 0, c->stream>>>(c->d_fragcnt, c->d_counters + n_index, cap, c->d_biglist, c->d_bigslot, c->d_counters,
+                                                                 c->d_scan_lookback);
+    c->launches++;
+    CU(cudaGetLastError());
+    return RR_OK;
+}
+
+template <int MODE>
+int raster(rr_ctx* c, const RasterParams& rp) {
+    k_raster_small<MODE><<<grid_for(c, 8), 256, 0, c->stream>>>(rp);
+    k_raster_big<MODE><<<grid_for(c, 4), RASTER_THREADS, 0, c->stream>>>(rp);
+    c->launches += 2;
+    CU(cudaGetLastError());
     return RR_OK;
 }
 
@@ -204,6 +228,11 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaMalloc((void**)&c->d_normals, P * 4) != cudaSuccess) return bail("normals");
     c->cap_frags = cfg->max_fragments ? cfg->max_fragments : (16u << 20);
     if (cudaMalloc((void**)&c->d_frags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("fragment buffer");
+    if (cudaMalloc((void**)&c->d_fragcnt, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("slot counts");
+    if (cudaMalloc((void**)&c->d_biglist, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("big list");
+    if (cudaMalloc((void**)&c->d_bigslot, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("big slots");
+    c->scan_tiles = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS / RR_SFRAG_WORDS + SCAN_TILE - 1) / SCAN_TILE) + 1;
+    if (cudaMalloc((void**)&c->d_scan_lookback, (size_t)c->scan_tiles * 8) != cudaSuccess) return bail("scan descriptors");
     if (cudaMalloc((void**)&c->d_counters, CTR_COUNT * 4) != cudaSuccess) return bail("counters");
     if (cudaMallocHost((void**)&c->h_counters, CTR_COUNT * 4) != cudaSuccess) return bail("pinned counters");
     cudaMemsetAsync(c->d_counters, 0, CTR_COUNT * 4, c->stream);
@@ -228,6 +257,7 @@ void rr_destroy(rr_ctx* c) {
     if (!c->ext_shadow_static) cudaFree(c->d_shadow_static);
     for (int i = 0; i < 2; i++) { cudaFree(c->d_depth[i]); cudaFree(c->d_ids[i]); }
     if (!c->ext_rgba8) cudaFree(c->d_rgba8);
+    cudaFree(c->d_fragcnt); cudaFree(c->d_scan_lookback); cudaFree(c->d_biglist); cudaFree(c->d_bigslot);
     cudaFree(c->d_normals); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
@@ -249,9 +279,9 @@ int rr_scene_alloc(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
     if ((r = dev_alloc(c->d_pc, n_tris))) return r;
     if ((r = dev_alloc(c->d_objs, n_objs))) return r;
     if ((r = dev_alloc(c->d_objlite, n_objs))) return r;
-    // projected triangles: main pass needs <= 2T; a shadow pass <= 12T in the worst case (reference allocates 12T,
-    // object_context.cpp:354). Default 4T + slack, overflow is detected and reported.
-    c->cap_cut = c->cfg.max_cutdown ? c->cfg.max_cutdown : (uint32_t)std::min<uint64_t>((uint64_t)n_tris * 4 + 1024, 0x7FFFFFFu);
+    // projected triangles: main pass needs <= 2T; a shadow pass (all lights at once) up to 12T per light in the worst
+    // case (the reference allocates 12T, object_context.cpp:354). Default 6T + slack ; overflow is detected and reported.
+    c->cap_cut = c->cfg.max_cutdown ? c->cfg.max_cutdown : (uint32_t)std::min<uint64_t>((uint64_t)n_tris * 6 + 1024, 0x7FFFFFFFu);
     if ((r = dev_alloc(c->d_cutdown, (size_t)c->cap_cut * 3))) return r;
     c->lookback_blocks = (n_tris + SETUP_THREADS - 1) / SETUP_THREADS;
     if ((r = dev_alloc(c->d_lookback, (size_t)c->lookback_blocks))) return r;
@@ -378,32 +408,53 @@ int rr_lights_write(rr_ctx* c, const rr_light* lights, uint32_t n_active) {
 }
 
 // ---- per frame -----------------------------------------------------------------------------------------------------
-static int shadow_pass(rr_ctx* c, const rr_light& l, int only_static, uint32_t* slab, uint32_t pair_base) {
-    // (light, face) pairs are owned in contiguous chunks of ceil(total / face_world) so that the owned part of the
-    // cubemap buffer is one contiguous range (in-place all-gather across contexts).
-    uint32_t mask = 0;
+// one pass = all shadow lights of one kind (dynamic: only_static 0 into g_shadow_light_buffer; static: only_static 1
+// into g_static_shadow_light_buffer), engine.cpp:1629-1784, in one setup launch + one scan + one raster pair
+static int shadow_pass(rr_ctx* c, int only_static) {
+    uint32_t* buffer = only_static ? c->d_shadow_static : c->d_shadow_dyn;
     const uint32_t total_pairs = 6u * (only_static ? c->n_static : c->n_shadow);
     const uint32_t chunk = c->cfg.face_world > 1 ? (total_pairs + c->cfg.face_world - 1) / c->cfg.face_world : total_pairs;
-    for (int kk = 0; kk < 6; kk++) {
-        bool mine = c->cfg.face_world <= 1 || ((pair_base + kk) / chunk) == (uint32_t)c->cfg.face_rank;
-        if (mine) mask |= 1u << kk;
+    std::vector<ShadowLight> sel;
+    uint32_t slab = 0;
+    for (size_t i = 0; i < c->lights.size(); i++) {
+        const rr_light& l = c->lights[i];
+        const bool in_pass = only_static ? (l.shadow && l.is_static) : (l.shadow == 1);
+        if (!in_pass) continue;
+        // (light, face) pairs are owned in contiguous chunks of ceil(total / face_world) so that the owned part of the
+        // cubemap buffer is one contiguous range (in-place all-gather across contexts)
+        uint32_t mask = 0;
+        for (uint32_t kk = 0; kk < 6; kk++)
+            if (c->cfg.face_world <= 1 || ((slab * 6 + kk) / chunk) == (uint32_t)c->cfg.face_rank) mask |= 1u << kk;
+        if (mask) sel.push_back(ShadowLight{l.pos[0], l.pos[1], l.pos[2], slab, mask});
+        slab++;
     }
-    if (!mask || c->n_tris == 0) return RR_OK;
-    ShadowSetupParams sp;
-    sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
-    sp.lpos = make_float3(l.pos[0], l.pos[1], l.pos[2]);
-    sp.faces = c->faces;
-    sp.L = (float)c->L; sp.icut = (float)c->cfg.depth_icutoff;
-    sp.only_static = only_static; sp.face_mask = mask;
-    sp.frags = c->d_frags; sp.cap_frags = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS) / RR_SFRAG_WORDS);
-    sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut; sp.counters = c->d_counters;
-    k_shadow_setup<<<(c->n_tris + 255) / 256, 256, 0, c->stream>>>(sp);
-    ShadowDepthParams dp;
-    dp.frags = c->d_frags; dp.cutdown = c->d_cutdown; dp.counters = c->d_counters; dp.cap_frags = sp.cap_frags;
-    dp.slab = slab; dp.L = (float)c->L; dp.Li = c->L;
-    k_shadow_depth<<<grid_for(c, 8), 256, 0, c->stream>>>(dp);
-    k_shadow_pass_end<<<1, 1, 0, c->stream>>>(c->d_counters);
-    c->launches += 3;
+    if (sel.empty() || c->n_tris == 0) return RR_OK;
+    int r;
+    for (size_t first = 0; first < sel.size(); first += SHADOW_MAX_LIGHTS) {
+        const int nl = (int)std::min<size_t>(SHADOW_MAX_LIGHTS, sel.size() - first);
+        CU(cudaMemsetAsync(c->d_counters + CTR_S_NFRAG, 0, 2 * 4, c->stream));
+        ShadowSetupParams sp;
+        sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
+        sp.n_lights = nl;
+        RasterParams dp;
+        for (int k = 0; k < nl; k++) { sp.lights[k] = sel[first + k]; dp.slab_of_light[k] = sel[first + k].slab; }
+        sp.faces = c->faces;
+        sp.L = (float)c->L; sp.icut = (float)c->cfg.depth_icutoff;
+        sp.only_static = only_static;
+        sp.frags = c->d_frags; sp.cap_frags = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS) / RR_SFRAG_WORDS);
+        sp.fragcnt = c->d_fragcnt;
+        sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut; sp.counters = c->d_counters;
+        sp.buffer = buffer;
+        k_shadow_setup<<<(c->n_tris + 255) / 256, 256, 0, c->stream>>>(sp);
+        c->launches++;
+        if ((r = scan_big(c, CTR_S_NFRAG, sp.cap_frags))) return r;
+        dp.frags = c->d_frags; dp.cutdown = c->d_cutdown; dp.fragcnt = c->d_fragcnt; dp.counters = c->d_counters; dp.cap_frags = sp.cap_frags;
+        dp.biglist = c->d_biglist; dp.bigslot = c->d_bigslot;
+        dp.n_index = CTR_S_NFRAG;
+        dp.depth = buffer; dp.ids = nullptr; dp.width = (float)c->L; dp.height = (float)c->L; dp.W = c->L;
+        dp.row_lo = 0; dp.row_hi = c->L;
+        if ((r = raster<RM_SHADOW>(c, dp))) return r;
+    }
     CU(cudaGetLastError());
     return RR_OK;
 }
@@ -415,24 +466,12 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     CU(cudaEventRecord(c->ev[EV_SH0], c->stream));
     const size_t slab = (size_t)6 * c->L * c->L;
     if (!c->lights.empty()) {                                                              // engine.cpp:1611-1626
-        // only the faces this context owns need clearing when faces are sharded, but a full clear keeps the slab
-        // contents defined for the all-gather that follows; it is one streaming fill.
+        // a full clear (not only the owned faces) keeps the buffer defined for the all-gather that follows
         if (c->n_shadow && (r = fill_u32(c, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
         if (static_lights_dirty && c->n_static && (r = fill_u32(c, c->d_shadow_static, slab * c->n_static, 0xFFFFFFFFu))) return r;
     }
-    CU(cudaMemsetAsync(c->d_counters + CTR_S_NCUT, 0, 3 * 4, c->stream));
-    uint32_t nn = 0, kk = 0;
-    for (size_t i = 0; i < c->lights.size(); i++) {                                        // engine.cpp:1629-1784
-        const rr_light& l = c->lights[i];
-        if (l.shadow == 1) {
-            if ((r = shadow_pass(c, l, 0, c->d_shadow_dyn + slab * nn, nn * 6))) return r;
-            nn++;
-        }
-        if (l.shadow && l.is_static && static_lights_dirty) {
-            if ((r = shadow_pass(c, l, 1, c->d_shadow_static + slab * kk, kk * 6))) return r;
-            kk++;
-        }
-    }
+    if (c->n_shadow && (r = shadow_pass(c, 0))) return r;                                  // engine.cpp:1629-1697
+    if (static_lights_dirty && c->n_static && (r = shadow_pass(c, 1))) return r;           // engine.cpp:1699-1784
     CU(cudaEventRecord(c->ev[EV_SH1], c->stream));
     c->have_shadow_ev = true;
     return RR_OK;
@@ -456,24 +495,28 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     SetupMainParams sp;
     sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
     sp.cam = cam; sp.width = (float)c->W; sp.height = (float)c->H; sp.fov = c->fov; sp.icut = (float)c->cfg.depth_icutoff;
-    sp.frags = c->d_frags; sp.cap_frags = c->cap_frags; sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut;
+    sp.frags = c->d_frags; sp.cap_frags = c->cap_frags; sp.fragcnt = c->d_fragcnt; sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut;
     sp.counters = c->d_counters; sp.lookback = c->d_lookback;
+    sp.depth = c->d_depth[c->cur]; sp.row_lo = row0; sp.row_hi = row1;
     k_setup_main<<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
     // kernel1 / kernel2
+    if ((r = scan_big(c, CTR_NFRAG, c->cap_frags))) return r;
     RasterParams rp;
-    rp.frags = c->d_frags; rp.cutdown = c->d_cutdown; rp.counters = c->d_counters; rp.cap_frags = c->cap_frags;
+    rp.frags = c->d_frags; rp.cutdown = c->d_cutdown; rp.fragcnt = c->d_fragcnt; rp.counters = c->d_counters; rp.cap_frags = c->cap_frags;
+    rp.biglist = c->d_biglist; rp.bigslot = c->d_bigslot;
+    rp.n_index = CTR_NFRAG;
     rp.depth = c->d_depth[c->cur]; rp.ids = c->d_ids[c->cur];
     rp.width = (float)c->W; rp.height = (float)c->H; rp.W = c->W;
     rp.row_lo = row0; rp.row_hi = row1;
-    k_depth<<<grid_for(c, 8), 256, 0, c->stream>>>(rp);
+    if ((r = raster<RM_DEPTH>(c, rp))) return r;
     CU(cudaEventRecord(c->ev[EV_DEPTH], c->stream));
     rp.row_lo = band0; rp.row_hi = band1;
-    k_ids<<<grid_for(c, 8), 256, 0, c->stream>>>(rp);
+    if ((r = raster<RM_IDS>(c, rp))) return r;
     CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
     // kernel3
     ShadeParams hp;
-    hp.tris = c->d_tris; hp.objs = c->d_objs; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown;
+    hp.tris = c->d_tris; hp.objs = c->d_objs; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
     hp.depth = c->d_depth[c->cur]; hp.ids = c->d_ids[c->cur];
     hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
     hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
@@ -493,7 +536,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     dim3 grid((c->W + 31) / 32, (row1 - row0 + 7) / 8);
     k_shade<<<grid, 256, 0, c->stream>>>(hp);
     CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
-    c->launches += 4;
+    c->launches += 2;
     c->have_frame_ev = true;
     CU(cudaGetLastError());
     return RR_OK;
@@ -567,7 +610,7 @@ int rr_get_timings(rr_ctx* c, rr_timings* t) {
     }
     t->n_cutdown = c->h_counters[CTR_NCUT];
     t->n_fragments = c->h_counters[CTR_NFRAG];
-    t->n_shadow_fragments = c->h_counters[CTR_S_TOTAL];
+    t->n_shadow_fragments = c->h_counters[CTR_S_NFRAG];    // of the last shadow pass
     t->overflow = c->h_counters[CTR_OVERFLOW];
     t->launches = c->launches;
     return RR_OK;

@@ -12,10 +12,13 @@ enum {
     CTR_NFRAG = 1,     // id_buffer_atomc of the main pass
     CTR_OVERFLOW = 2,  // bit0 fragments, bit1 cutdown, bit2 look-back watchdog
     CTR_TICKET = 3,    // block ticket of the single-pass scan
-    CTR_S_NCUT = 4,    // shadow pass counters (reset per pass)
-    CTR_S_NFRAG = 5,
+    CTR_S_NFRAG = 4,   // shadow pass allocation counter, one 64-bit word at [4..5]: (projected triangles << 32) | fragments,
+    CTR_S_NCUT = 5,    //   i.e. word 4 = fragment count, word 5 = projected-triangle count (little endian)
     CTR_S_TOTAL = 6,   // running total of shadow fragments in this frame (statistics)
-    CTR_COUNT = 8
+    CTR_SLOTS = 7,     // total pixel slots of the fragment list last scanned (k_scan_slots)
+    CTR_SCAN_TICKET = 8,
+    CTR_NBIG = 9,      // number of big fragments (more than RASTER_SMALL_MAX slots) in the list last scanned
+    CTR_COUNT = 12
 };
 
 struct CamParams {
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(128) k_objlite(const rr_obj_desc* __restrict__
 }
 
 // One clipped + projected triangle after culling. keep == false -> no storage written, no fragments.
-struct SubTri { float3 p0, p1, p2; float rconst; int n_frag; bool keep; };
+struct SubTri { float3 p0, p1, p2; float rconst; int n_frag; int box; bool keep; };
 
 // cull + bbox + fragment count, cl2.cl:4352-4377 (main) / 4571-4597 (shadow)
 __device__ __forceinline__ void classify(SubTri& s, bool two_sided, float ewidth, float eheight, float op_size) {
@@ -73,6 +76,7 @@ __device__ __forceinline__ void classify(SubTri& s, bool two_sided, float ewidth
                 (s.p0.y < 0 && s.p1.y < 0 && s.p2.y < 0) || (s.p0.y >= eheight && s.p1.y >= eheight && s.p2.y >= eheight);
     s.keep = valid && !cond;
     s.n_frag = 0;
+    s.box = 0;
     s.rconst = 0.f;
     if (!s.keep) return;
     float3 xr = make_float3(roundf(s.p0.x), roundf(s.p1.x), roundf(s.p2.x));
@@ -81,26 +85,99 @@ __device__ __forceinline__ void classify(SubTri& s, bool two_sided, float ewidth
     float4 mm = calc_min_max(xr, yr, ewidth, eheight);
     float area = (mm.y - mm.x) * (mm.w - mm.z);
     s.n_frag = (int)ceilf(area / op_size);
+    s.box = (int)area;                        // width * rows, exact (both are small integers)
 }
 
-// object -> world -> camera for the three vertices, then clip + project. cl2.cl:700-729. Returns num (0/1/2).
-__device__ __forceinline__ int transform_clip_project(float3 v0, float3 v1, float3 v2, const ObjLite& G, float3 cam_pos, const RotSC& cam_rot,
-                                                      float icut, float half_w, float half_h, float fovc, SubTri (&out)[2]) {
-    const float scale = G.pos_scale.w;
-    const float3 gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
-    float3 pr[3];
-    pr[0] = rot(rot_quat_n(v0 * scale, G.nquat) + gpos, cam_pos, cam_rot);
-    pr[1] = rot(rot_quat_n(v1 * scale, G.nquat) + gpos, cam_pos, cam_rot);
-    pr[2] = rot(rot_quat_n(v2 * scale, G.nquat) + gpos, cam_pos, cam_rot);
-    float3 cl[2][3];
-    int num = clip_near(pr, icut, cl);
-    for (int i = 0; i < num; i++) {
-        out[i].p0 = project(cl[i][0], half_w, half_h, fovc);
-        out[i].p1 = project(cl[i][1], half_w, half_h, fovc);
-        out[i].p2 = project(cl[i][2], half_w, half_h, fovc);
-    }
+// where the walk of a stored triangle ends: first k whose row counter reaches max_y (only needed for its slot counts)
+__device__ __forceinline__ int subtri_walk_end(const SubTri& s, float ewidth, float eheight) {
+    float3 xr = make_float3(roundf(s.p0.x), roundf(s.p1.x), roundf(s.p2.x));
+    float3 yr = make_float3(roundf(s.p0.y), roundf(s.p1.y), roundf(s.p2.y));
+    float4 mm = calc_min_max(xr, yr, ewidth, eheight);
+    const int width = (int)(mm.y - mm.x), rows = (int)(mm.w - mm.z);
+    return walk_end(width, rows, 1.f / (float)width, mm.z, mm.w);
+}
+
+// pixel slots chunk `a` of a triangle visits: k = a*op .. a*op+op, cut where the walk ends
+__device__ __forceinline__ uint32_t chunk_slots(int kend, int a, int op) { return (uint32_t)min(max(kend - a * op, 0), op + 1); }
+
+// camera-space triangle -> near-plane clip -> projection (cl2.cl:700-729 after the rotations). Returns num (0/1/2).
+__device__ __forceinline__ int clip_project(float3 q0, float3 q1, float3 q2, float icut, float half_w, float half_h, float fovc, SubTri& s0, SubTri& s1) {
+    float3 a0, a1, a2, b0, b1, b2;
+    const int num = clip_near(q0, q1, q2, icut, a0, a1, a2, b0, b1, b2);
+    if (num > 0) { s0.p0 = project(a0, half_w, half_h, fovc); s0.p1 = project(a1, half_w, half_h, fovc); s0.p2 = project(a2, half_w, half_h, fovc); }
+    if (num > 1) { s1.p0 = project(b0, half_w, half_h, fovc); s1.p1 = project(b1, half_w, half_h, fovc); s1.p2 = project(b2, half_w, half_h, fovc); }
     return num;
 }
+
+__device__ __forceinline__ void subtri_clear(SubTri& s) { s.keep = false; s.n_frag = 0; s.box = 0; s.rconst = 0.f; }
+
+// ---- inline rasterisation of a small single-chunk triangle from the setup kernels --------------------------------------
+// A triangle whose whole walk is one chunk of at most RASTER_SMALL_MAX slots is rasterised by the thread that set it up:
+// same frag_geom / scan_chunk / depth arithmetic as the raster kernels, but no trip through the record and
+// projected-triangle buffers and no second kernel. `target` is the depth buffer (or cubemap face) it lands in.
+#define RASTER_SMALL_MAX 48
+#define FRAGCNT_DEPTH_DONE 0x80000000u      // flag in the per-fragment slot count: depth already written inline
+
+__device__ __forceinline__ bool inline_candidate(const SubTri& s) { return s.keep && s.n_frag == 1 && s.box <= RASTER_SMALL_MAX; }
+
+__device__ __forceinline__ void raster_inline(float3 p0, float3 p1, float3 p2, float rconst, int op, float width, float height,
+                                              uint32_t* __restrict__ target, int row_lo, int row_hi) {
+    const FragGeom g = frag_geom(p0, p1, p2, rconst, width, height);
+    scan_chunk(g.mm, op, 0u, [&](float x, float y) {
+        if ((int)y < row_lo || (int)y >= row_hi) return;
+        if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
+            const float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
+            atomicMin(target + ((int)(y * width) + (int)x), sat_u32(RR_U32MAXF / fd));
+        }
+    });
+}
+
+// Per-warp queue in shared memory that compacts the small triangles of a warp (warp ballot + prefix) so that the walk is
+// always executed by 32 busy lanes: roughly half of a warp's triangles are culled and the survivors need different
+// numbers of steps, so rasterising them in place would leave most lanes idle.
+#define IQ_SLOTS 64
+#define IQ_FIELDS 11            // p0.xyz p1.xyz p2.xyz rconst target-index
+struct InlineQueue { float f[IQ_FIELDS][IQ_SLOTS]; };
+
+struct InlineRaster {
+    InlineQueue* q; int count;  // count is warp-uniform
+    int op; float width, height; uint32_t* base; size_t face_stride; int row_lo, row_hi;
+
+    __device__ __forceinline__ void run(int slot) const {
+        const float* f = &q->f[0][slot];
+        raster_inline(make_float3(f[0], f[IQ_SLOTS], f[2 * IQ_SLOTS]), make_float3(f[3 * IQ_SLOTS], f[4 * IQ_SLOTS], f[5 * IQ_SLOTS]),
+                      make_float3(f[6 * IQ_SLOTS], f[7 * IQ_SLOTS], f[8 * IQ_SLOTS]), f[9 * IQ_SLOTS], op, width, height,
+                      base + (size_t)__float_as_uint(f[10 * IQ_SLOTS]) * face_stride, row_lo, row_hi);
+    }
+    // called by all 32 lanes
+    __device__ __forceinline__ void push(bool has, const SubTri& s, uint32_t target_index) {
+        const int lane = threadIdx.x & 31;
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (!m) return;
+        if (has) {
+            const int at = count + __popc(m & ((1u << lane) - 1u));
+            float* f = &q->f[0][at];
+            f[0] = s.p0.x; f[IQ_SLOTS] = s.p0.y; f[2 * IQ_SLOTS] = s.p0.z;
+            f[3 * IQ_SLOTS] = s.p1.x; f[4 * IQ_SLOTS] = s.p1.y; f[5 * IQ_SLOTS] = s.p1.z;
+            f[6 * IQ_SLOTS] = s.p2.x; f[7 * IQ_SLOTS] = s.p2.y; f[8 * IQ_SLOTS] = s.p2.z;
+            f[9 * IQ_SLOTS] = s.rconst; f[10 * IQ_SLOTS] = __uint_as_float(target_index);
+        }
+        count += __popc(m);
+        __syncwarp();
+        if (count >= 32) {                      // drain a full warp's worth
+            count -= 32;
+            run(count + lane);
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        if (lane < count) run(lane);
+        count = 0;
+        __syncwarp();
+    }
+};
 
 // =====================================================================================================================
 // k_setup_main == prearrange (cl2.cl:4272-4409), single pass.
@@ -126,9 +203,11 @@ struct SetupMainParams {
     CamParams cam;
     float width, height, fov, icut;
     uint32_t* frags; uint32_t cap_frags;
+    uint32_t* fragcnt;                       // pixel slots per fragment (+ FRAGCNT_DEPTH_DONE)
     float4* cutdown; uint32_t cap_cut;
     uint32_t* counters;
     unsigned long long* lookback;
+    uint32_t* depth; int row_lo, row_hi;     // inline depth of small triangles
 };
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainParams P) {
@@ -138,7 +217,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     __shared__ uint32_t s_fexcl[2 * SETUP_THREADS];      // exclusive fragment offset of slot (2*thread + i) inside the block
     __shared__ uint32_t s_cid[2 * SETUP_THREADS];
     __shared__ float s_rconst[2 * SETUP_THREADS];
+    __shared__ int s_kend[2 * SETUP_THREADS];
     __shared__ uint32_t s_oid[SETUP_THREADS];
+    __shared__ InlineQueue s_iq[SETUP_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(&P.counters[CTR_TICKET], 1u);
@@ -146,10 +227,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     const uint32_t bid = s_bid;
     const uint32_t tri = bid * SETUP_THREADS + tid;
 
-    SubTri st[2];
+    SubTri st0, st1;
     int num = 0;
     uint32_t oid = 0;
-    st[0].keep = st[1].keep = false; st[0].n_frag = st[1].n_frag = 0; st[0].rconst = st[1].rconst = 0.f;
+    subtri_clear(st0); subtri_clear(st1);
     if (tri < P.n_tris) {
         const float4 a = __ldg(P.pa + tri), b = __ldg(P.pb + tri);
         const float2 c = __ldg(P.pc + tri);
@@ -157,15 +238,23 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
         const ObjLite G = P.objs[oid];
         const float3 gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
         if (!(length3(gpos - P.cam.pos) > RR_DEPTH_FAR)) {                      // cl2.cl:4321
-            num = transform_clip_project(make_float3(a.x, a.y, a.z), make_float3(a.w, b.x, b.y), make_float3(b.z, b.w, c.x), G, P.cam.pos,
-                                         P.cam.rot, P.icut, P.width / 2.f, P.height / 2.f, P.fov, st);
+            const float sc = G.pos_scale.w;
+            const float3 q0 = rot(rot_quat_n(make_float3(a.x, a.y, a.z) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);
+            const float3 q1 = rot(rot_quat_n(make_float3(a.w, b.x, b.y) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);
+            const float3 q2 = rot(rot_quat_n(make_float3(b.z, b.w, c.x) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);
+            num = clip_project(q0, q1, q2, P.icut, P.width / 2.f, P.height / 2.f, P.fov, st0, st1);
             const bool two_sided = (G.feature_flag & RR_FEATURE_TWO_SIDED) > 0;
-            for (int i = 0; i < num; i++) classify(st[i], two_sided, P.width, P.height, (float)RR_OP_SIZE);
+            if (num > 0) classify(st0, two_sided, P.width, P.height, (float)RR_OP_SIZE);
+            if (num > 1) classify(st1, two_sided, P.width, P.height, (float)RR_OP_SIZE);
         }
     }
+    const bool inl0 = num > 0 && inline_candidate(st0), inl1 = num > 1 && inline_candidate(st1);
+    // slot counts are only needed for what the raster kernels will walk: find the end of those walks now
+    const int kend0 = (st0.n_frag > 0) ? (inl0 ? st0.box : subtri_walk_end(st0, P.width, P.height)) : 0;
+    const int kend1 = (st1.n_frag > 0) ? (inl1 ? st1.box : subtri_walk_end(st1, P.width, P.height)) : 0;
     const uint32_t my_c = (uint32_t)num;                                        // slots are taken before culling (cl2.cl:4342)
-    const uint32_t my_f0 = (num > 0) ? (uint32_t)st[0].n_frag : 0u;
-    const uint32_t my_f1 = (num > 1) ? (uint32_t)st[1].n_frag : 0u;
+    const uint32_t my_f0 = (num > 0) ? (uint32_t)st0.n_frag : 0u;
+    const uint32_t my_f1 = (num > 1) ? (uint32_t)st1.n_frag : 0u;
     const uint32_t my_f = my_f0 + my_f1;
 
     // block exclusive scan of (my_c, my_f)
@@ -228,8 +317,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     const uint32_t cid0 = ex_c;    // block-relative; global added below
     s_fexcl[2 * tid] = ex_f;
     s_fexcl[2 * tid + 1] = ex_f + my_f0;
-    s_rconst[2 * tid] = st[0].rconst;
-    s_rconst[2 * tid + 1] = st[1].rconst;
+    s_rconst[2 * tid] = st0.rconst;
+    s_rconst[2 * tid + 1] = st1.rconst;
+    s_kend[2 * tid] = kend0 | (inl0 ? (int)FRAGCNT_DEPTH_DONE : 0);            // kend < 2^31 always
+    s_kend[2 * tid + 1] = kend1 | (inl1 ? (int)FRAGCNT_DEPTH_DONE : 0);
     s_oid[tid] = oid;
     __syncthreads();
     const uint32_t base_c = s_base_c, base_f = s_base_f;
@@ -240,22 +331,27 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     bool cut_ok = (base_c + tot_c) <= P.cap_cut;
     if (!cut_ok && tid == 0) atomicOr(&P.counters[CTR_OVERFLOW], 2u);
     if (cut_ok) {
-        for (int i = 0; i < num; i++) {
-            if (!st[i].keep) continue;
-            float4* dst = P.cutdown + (size_t)(base_c + cid0 + i) * 3;
-            dst[0] = make_float4(st[i].p0.x, st[i].p0.y, st[i].p0.z, 0.f);
-            dst[1] = make_float4(st[i].p1.x, st[i].p1.y, st[i].p1.z, 0.f);
-            dst[2] = make_float4(st[i].p2.x, st[i].p2.y, st[i].p2.z, 0.f);
+        if (num > 0 && st0.keep) {
+            float4* dst = P.cutdown + (size_t)(base_c + cid0) * 3;
+            dst[0] = make_float4(st0.p0.x, st0.p0.y, st0.p0.z, 0.f);
+            dst[1] = make_float4(st0.p1.x, st0.p1.y, st0.p1.z, 0.f);
+            dst[2] = make_float4(st0.p2.x, st0.p2.y, st0.p2.z, 0.f);
+        }
+        if (num > 1 && st1.keep) {
+            float4* dst = P.cutdown + (size_t)(base_c + cid0 + 1) * 3;
+            dst[0] = make_float4(st1.p0.x, st1.p0.y, st1.p0.z, 0.f);
+            dst[1] = make_float4(st1.p1.x, st1.p1.y, st1.p1.z, 0.f);
+            dst[2] = make_float4(st1.p2.x, st1.p2.y, st1.p2.z, 0.f);
         }
     }
     __syncthreads();
 
     // fragment records {tri id, chunk, c_id, bits(rconst), o_id}, cl2.cl:4394-4406 — block-cooperative, word-coalesced
     const uint32_t totf = s_tot_f;
-    if (totf == 0) return;
-    if ((unsigned long long)base_f + totf > (unsigned long long)P.cap_frags) { if (tid == 0) atomicOr(&P.counters[CTR_OVERFLOW], 1u); return; }
+    const bool frag_ok = (unsigned long long)base_f + totf <= (unsigned long long)P.cap_frags;
+    if (!frag_ok && tid == 0) atomicOr(&P.counters[CTR_OVERFLOW], 1u);
     uint32_t* out = P.frags + (size_t)base_f * RR_FRAG_WORDS;
-    const uint32_t nwords = totf * RR_FRAG_WORDS;
+    const uint32_t nwords = frag_ok ? totf * RR_FRAG_WORDS : 0u;
     for (uint32_t w = tid; w < nwords; w += SETUP_THREADS) {
         const uint32_t r = w / RR_FRAG_WORDS, field = w - r * RR_FRAG_WORDS;
         // last slot whose exclusive offset is <= r (slots with zero fragments share offsets; the last one owns r)
@@ -274,200 +370,399 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
             default: val = s_oid[slot >> 1]; break;
         }
         out[w] = val;
+        if (field == 1) {
+            const uint32_t ke = (uint32_t)s_kend[slot];
+            P.fragcnt[base_f + r] = chunk_slots((int)(ke & ~FRAGCNT_DEPTH_DONE), (int)val, RR_OP_SIZE) | (ke & FRAGCNT_DEPTH_DONE);
+        }
     }
+    // kernel1's work for the small single-chunk triangles, after everything other blocks wait for has been published
+    InlineRaster ir;
+    ir.q = &s_iq[warp]; ir.count = 0; ir.op = RR_OP_SIZE; ir.width = P.width; ir.height = P.height; ir.base = P.depth; ir.face_stride = 0;
+    ir.row_lo = P.row_lo; ir.row_hi = P.row_hi;
+    ir.push(inl0, st0, 0u);
+    ir.push(inl1, st1, 0u);
+    ir.flush();
 }
 
 // =====================================================================================================================
-// k_depth == kernel1 (cl2.cl:4986-5127) and k_ids == kernel2 (cl2.cl:5391-5546).
-// Persistent grid (multiple of the SM count), grid-stride over the fragment records whose count lives on the device,
-// so the host never reads the count back (the reference sizes the launch from a stale host copy, engine.cpp:1836,1899).
-// One thread replays one chunk's pixel walk; depth goes out as red.global.min.u32 on the L2-resident depth buffer.
+// Rasterisation: kernel1 (cl2.cl:4986-5127), kernel2 (5391-5546), kernel1_realtime_shadowing (5130-5246).
+//
+// The reference gives one work-item one <=501-pixel chunk and walks it sequentially, so a pass lasts as long as its
+// longest walk (measured: 82 us for a pass whose total work is ~10 us). Two paths here, split by the number of pixel
+// slots a fragment visits (known at setup time):
+//   small (<= RASTER_SMALL_MAX slots): k_raster_small — one thread replays the walk verbatim; the tail is bounded.
+//   big: k_scan_big compacts them into a list with a prefix sum of their slot counts; k_raster_big gives every CTA an
+//        equal range of SLOTS wherever they come from, stages the owning fragments' geometry in shared memory and
+//        resolves each slot with the closed form of the walk (rr_math.cuh walk_pixel).
+// Depth goes out as red.global.min.u32 on the L2-resident buffer; ids as red.global.max.u32 (canonical last writer).
 // =====================================================================================================================
+enum { RM_DEPTH = 0, RM_IDS = 1, RM_SHADOW = 2 };
+#define RASTER_THREADS 256
+#define RASTER_SLOTS 2048           // pixel slots per CTA work item (big path)
+#define RASTER_FRAGS 256            // fragments staged at a time (big path)
+
 struct RasterParams {
-    const uint32_t* frags; const float4* cutdown; const uint32_t* counters; uint32_t cap_frags;
-    uint32_t* depth; uint32_t* ids;
+    const uint32_t* frags; const float4* cutdown; const uint32_t* fragcnt; const uint32_t* counters; uint32_t cap_frags;
+    const uint32_t* biglist; const uint32_t* bigslot;
+    int n_index;                    // CTR_NFRAG or CTR_S_NFRAG
+    uint32_t* depth; uint32_t* ids; // RM_SHADOW: depth = base of the cubemap buffer of this pass
+    uint32_t slab_of_light[16];     // RM_SHADOW: record word 0 = light << 8 | face; slab index of each light of the pass
     float width, height; int W;
-    int row_lo, row_hi;     // rows this context needs rasterised (band +- halo); chunks entirely outside are skipped
+    int row_lo, row_hi;             // rows this context needs (band +- halo)
 };
 
+template <int MODE>
+__device__ __forceinline__ void emit_sample(const RasterParams& P, float x, float y, float A, float B, float C, uint32_t face, uint32_t f) {
+    const float fd = fmaf(A, x, fmaf(B, y, C));
+    const uint32_t d = sat_u32(RR_U32MAXF / fd);
+    if (MODE == RM_DEPTH) {
+        atomicMin(P.depth + ((int)(y * P.width) + (int)x), d);
+    } else if (MODE == RM_SHADOW) {
+        atomicMin(P.depth + ((size_t)P.slab_of_light[face >> 8] * 6 + (face & 0xFF)) * P.W * P.W + ((int)(y * P.width) + (int)x), d);
+    } else {
+        const int px = (int)y * P.W + (int)x;
+        const uint32_t val = P.depth[px];
+        // racing plain stores in the reference; canonical winner = highest fragment index (last writer in id order)
+        if (d > val - RR_BUF_ERROR && d < val + RR_BUF_ERROR) atomicMax(P.ids + px, f);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void load_fragment(const RasterParams& P, uint32_t f, uint32_t& face, uint32_t& distance, FragGeom& g) {
+    uint32_t ctri;
+    float rconst;
+    face = 0;
+    if (MODE == RM_SHADOW) {
+        const uint4 rec = __ldg(reinterpret_cast<const uint4*>(P.frags) + f);
+        face = rec.x; distance = rec.y; ctri = rec.z; rconst = __uint_as_float(rec.w);
+    } else {
+        const uint32_t* rec = P.frags + (size_t)f * RR_FRAG_WORDS;
+        distance = __ldg(rec + 1); ctri = __ldg(rec + 2); rconst = __uint_as_float(__ldg(rec + 3));
+    }
+    const float4 c0 = __ldg(P.cutdown + (size_t)ctri * 3), c1 = __ldg(P.cutdown + (size_t)ctri * 3 + 1), c2 = __ldg(P.cutdown + (size_t)ctri * 3 + 2);
+    g = frag_geom(xyz(c0), xyz(c1), xyz(c2), rconst, P.width, P.height);
+}
+
+// rows a chunk can touch, conservatively (for the sort-first band cull)
 __device__ __forceinline__ bool chunk_rows_outside(const float4 mm, int op_size, uint32_t distance, int row_lo, int row_hi) {
-    int width = (int)(mm.y - mm.x);
+    const int width = (int)(mm.y - mm.x);
     if (width <= 0) return true;
-    int k0 = op_size * (int)distance;
-    int y_lo = (int)mm.z + k0 / width - 2;
-    int y_hi = (int)mm.z + (k0 + op_size) / width + 2;
+    const int k0 = op_size * (int)distance;
+    const int y_lo = (int)mm.z + k0 / width - 2, y_hi = (int)mm.z + (k0 + op_size) / width + 2;
     return y_hi < row_lo || y_lo >= row_hi;
 }
 
-__global__ void __launch_bounds__(256) k_depth(const RasterParams P) {
-    const uint32_t n = min(P.counters[CTR_NFRAG], P.cap_frags);
+template <int MODE>
+__global__ void __launch_bounds__(256) k_raster_small(const RasterParams P) {
+    constexpr int OP = (MODE == RM_SHADOW) ? RR_OP_SIZE_LIGHT : RR_OP_SIZE;
+    const uint32_t n = min(P.counters[P.n_index], P.cap_frags);
     for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
-        const uint32_t* rec = P.frags + (size_t)f * RR_FRAG_WORDS;
-        const uint32_t distance = __ldg(rec + 1), ctri = __ldg(rec + 2);
-        const float rconst = __uint_as_float(__ldg(rec + 3));
-        const float4 c0 = __ldg(P.cutdown + (size_t)ctri * 3), c1 = __ldg(P.cutdown + (size_t)ctri * 3 + 1), c2 = __ldg(P.cutdown + (size_t)ctri * 3 + 2);
-        const FragGeom g = frag_geom(xyz(c0), xyz(c1), xyz(c2), rconst, P.width, P.height);
-        if (chunk_rows_outside(g.mm, RR_OP_SIZE, distance, P.row_lo, P.row_hi)) continue;
-        uint32_t* depth = P.depth;
-        const float ew = P.width;
-        scan_chunk(g.mm, RR_OP_SIZE, distance, [&](float x, float y) {
-            if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
-                float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
-                uint32_t d = sat_u32(RR_U32MAXF / fd);
-                atomicMin(depth + ((int)(y * ew) + (int)x), d);
-            }
+        const uint32_t raw = __ldg(P.fragcnt + f), cnt = raw & ~FRAGCNT_DEPTH_DONE;
+        if (cnt > RASTER_SMALL_MAX || cnt == 0) continue;
+        if (MODE == RM_DEPTH && (raw & FRAGCNT_DEPTH_DONE)) continue;        // written inline by k_setup_main
+        uint32_t face, distance;
+        FragGeom g;
+        load_fragment<MODE>(P, f, face, distance, g);
+        if (MODE != RM_SHADOW && chunk_rows_outside(g.mm, OP, distance, P.row_lo, P.row_hi)) continue;
+        scan_chunk(g.mm, OP, distance, [&](float x, float y) {
+            if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) emit_sample<MODE>(P, x, y, g.A, g.B, g.C, face, f);
         });
     }
 }
 
-__global__ void __launch_bounds__(256) k_ids(const RasterParams P) {
-    const uint32_t n = min(P.counters[CTR_NFRAG], P.cap_frags);
-    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
-        const uint32_t* rec = P.frags + (size_t)f * RR_FRAG_WORDS;
-        const uint32_t distance = __ldg(rec + 1), ctri = __ldg(rec + 2);
-        const float rconst = __uint_as_float(__ldg(rec + 3));
-        const float4 c0 = __ldg(P.cutdown + (size_t)ctri * 3), c1 = __ldg(P.cutdown + (size_t)ctri * 3 + 1), c2 = __ldg(P.cutdown + (size_t)ctri * 3 + 2);
-        const FragGeom g = frag_geom(xyz(c0), xyz(c1), xyz(c2), rconst, P.width, P.height);
-        if (chunk_rows_outside(g.mm, RR_OP_SIZE, distance, P.row_lo, P.row_hi)) continue;
-        const uint32_t* depth = P.depth;
-        uint32_t* ids = P.ids;
-        const int W = P.W;
-        scan_chunk(g.mm, RR_OP_SIZE, distance, [&](float x, float y) {
-            if (x < g.mm.x || y < g.mm.z) return;                                   // cl2.cl:5503
-            if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
-                float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
-                uint32_t d = sat_u32(RR_U32MAXF / fd);
-                const int px = (int)y * W + (int)x;
-                uint32_t val = depth[px];
-                // racing plain stores in the reference; canonical winner = highest fragment index (last writer in id order)
-                if (d > val - RR_BUF_ERROR && d < val + RR_BUF_ERROR) atomicMax(ids + px, f);
+// ---- k_scan_big: compact the big fragments and prefix-sum their slot counts (single pass, decoupled look-back) --------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+#define SCAN_SLOT_BITS 37
+#define SCAN_PAYLOAD_MASK ((1ull << 62) - 1)
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_big(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ n_ptr, uint32_t cap,
+                                                            uint32_t* __restrict__ biglist, uint32_t* __restrict__ bigslot,
+                                                            uint32_t* __restrict__ counters, unsigned long long* __restrict__ lookback) {
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = min(*n_ptr, cap);
+    const uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(&counters[CTR_SCAN_TICKET], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) break;                       // counters[CTR_SLOTS], [CTR_NBIG] were zeroed by the host
+        const uint32_t first = tile * SCAN_TILE + tid * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        unsigned long long mine = 0;                      // (number of big fragments << 37) | their slots
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            uint32_t c = (first + i < n) ? (__ldg(cnt + first + i) & ~FRAGCNT_DEPTH_DONE) : 0u;
+            v[i] = c > RASTER_SMALL_MAX ? c : 0u;
+            if (v[i]) mine += (1ull << SCAN_SLOT_BITS) | v[i];
+        }
+        unsigned long long inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; w++) { unsigned long long x = s_warp[w]; if (w < warp) woff += x; tot += x; }
+        if (warp == 0) {
+            volatile unsigned long long* desc = lookback;
+            unsigned long long base = 0;
+            if (tile == 0) { if (lane == 0) desc[0] = (2ull << 62) | tot; }
+            else {
+                if (lane == 0) desc[tile] = (1ull << 62) | tot;
+                int look = (int)tile - 1;
+                uint32_t watchdog = 0;
+                while (true) {
+                    int idx = look - lane;
+                    unsigned long long d = 2ull << 62;
+                    if (idx >= 0) {
+                        do {
+                            d = desc[idx];
+                            if (++watchdog > (1u << 26)) { atomicOr(&counters[CTR_OVERFLOW], 4u); d = 2ull << 62; break; }
+                        } while ((d >> 62) == 0);
+                    }
+                    const unsigned incl = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+                    const int first_incl = incl ? (__ffs(incl) - 1) : 32;
+                    unsigned long long val = (lane <= first_incl) ? (d & SCAN_PAYLOAD_MASK) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                    base += val;
+                    if (incl) break;
+                    look -= 32;
+                }
+                if (lane == 0) desc[tile] = (2ull << 62) | (base + tot);
             }
-        });
+            if (lane == 0) {
+                s_base = base;
+                if (tile == n_tiles - 1) {
+                    const unsigned long long all = base + tot, slots = all & ((1ull << SCAN_SLOT_BITS) - 1);
+                    if (slots > 0xFFFFFFFFull) atomicOr(&counters[CTR_OVERFLOW], 8u);
+                    counters[CTR_SLOTS] = (uint32_t)min(slots, 0xFFFFFFFFull);
+                    counters[CTR_NBIG] = (uint32_t)(all >> SCAN_SLOT_BITS);
+                }
+            }
+        }
+        __syncthreads();
+        unsigned long long run = s_base + woff + inc - mine;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (v[i]) {
+                const uint32_t at = (uint32_t)(run >> SCAN_SLOT_BITS);
+                biglist[at] = first + i;
+                bigslot[at] = (uint32_t)(run & ((1ull << SCAN_SLOT_BITS) - 1));
+                run += (1ull << SCAN_SLOT_BITS) | v[i];
+            }
+        }
+    }
+}
+
+// largest i in [0, n) with slot[i] <= s (slot[] is non-decreasing, slot[0] == 0); executed by one full warp
+__device__ __forceinline__ uint32_t warp_search_le(const uint32_t* __restrict__ slot, uint32_t n, uint32_t s) {
+    const int lane = threadIdx.x & 31;
+    uint32_t lo = 0, hi = n;                                 // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const uint32_t step = (hi - lo + 31) / 32;
+        const uint32_t idx = lo + lane * step;
+        const bool ok = idx < hi && __ldg(slot + idx) <= s;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);   // lane 0 is always ok (slot[lo] <= s)
+        const int last = 31 - __clz((int)m);
+        const uint32_t nlo = lo + (uint32_t)last * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
+    }
+    return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RASTER_THREADS) k_raster_big(const RasterParams P) {
+    constexpr int OP = (MODE == RM_SHADOW) ? RR_OP_SIZE_LIGHT : RR_OP_SIZE;
+    __shared__ float4 s_mm[RASTER_FRAGS];        // box
+    __shared__ float4 s_xa[RASTER_FRAGS];        // xr.xyz, A
+    __shared__ float4 s_yb[RASTER_FRAGS];        // yr.xyz, B
+    __shared__ float4 s_cw[RASTER_FRAGS];        // C, 1/width, k0 (int bits), width (int bits)
+    __shared__ uint32_t s_slot[RASTER_FRAGS];    // first slot of the fragment
+    __shared__ uint32_t s_face[RASTER_FRAGS];
+    __shared__ uint32_t s_frag[RASTER_FRAGS];    // fragment index (what kernel2 writes)
+    __shared__ uint32_t s_i0, s_i1;
+
+    const int tid = threadIdx.x;
+    const uint32_t n = P.counters[CTR_NBIG];
+    const uint32_t total = P.counters[CTR_SLOTS];
+    if (n == 0) return;
+    for (uint32_t item = blockIdx.x; (unsigned long long)item * RASTER_SLOTS < total; item += gridDim.x) {
+        const uint32_t s0 = item * RASTER_SLOTS;
+        const uint32_t s1 = (uint32_t)min((unsigned long long)total, (unsigned long long)s0 + RASTER_SLOTS);
+        __syncthreads();
+        if (tid < 32) { uint32_t i = warp_search_le(P.bigslot, n, s0); if (tid == 0) s_i0 = i; }
+        else if (tid < 64) { uint32_t i = warp_search_le(P.bigslot, n, s1 - 1); if (tid == 32) s_i1 = i; }
+        __syncthreads();
+        const uint32_t i0 = s_i0, i1 = s_i1;
+        for (uint32_t ib = i0; ib <= i1; ib += RASTER_FRAGS) {
+            const uint32_t nf = min((uint32_t)RASTER_FRAGS, i1 + 1 - ib);
+            __syncthreads();
+            if (tid < (int)nf) {
+                const uint32_t f = __ldg(P.biglist + ib + tid);
+                uint32_t face, distance;
+                FragGeom g;
+                load_fragment<MODE>(P, f, face, distance, g);
+                const int width = (int)(g.mm.y - g.mm.x);
+                s_mm[tid] = g.mm;
+                s_xa[tid] = make_float4(g.xr.x, g.xr.y, g.xr.z, g.A);
+                s_yb[tid] = make_float4(g.yr.x, g.yr.y, g.yr.z, g.B);
+                s_cw[tid] = make_float4(g.C, 1.f / (float)width, __int_as_float(OP * (int)distance), __int_as_float(width));
+                s_slot[tid] = __ldg(P.bigslot + ib + tid);
+                s_face[tid] = face;
+                s_frag[tid] = f;
+            }
+            __syncthreads();
+            // slots of this batch of fragments that fall in [s0, s1)
+            const uint32_t b0 = max(s0, s_slot[0]);
+            const uint32_t b1 = (ib + nf < n) ? min(s1, __ldg(P.bigslot + ib + nf)) : s1;
+            for (uint32_t s = b0 + tid; s < b1; s += RASTER_THREADS) {
+                int lo = 0, hi = (int)nf - 1;                 // last staged fragment whose first slot is <= s
+                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_slot[mid] <= s) lo = mid; else hi = mid - 1; }
+                const float4 mm = s_mm[lo], cw = s_cw[lo];
+                const int k0 = __float_as_int(cw.z), width = __float_as_int(cw.w);
+                const int k = k0 + (int)(s - s_slot[lo]);
+                float x, y;
+                if (!walk_pixel(k, k0, width, cw.y, mm, x, y)) continue;
+                const int iy = (int)y;
+                if (MODE != RM_SHADOW && (iy < P.row_lo || iy >= P.row_hi)) continue;
+                const float4 xa = s_xa[lo], yb = s_yb[lo];
+                if (!point_in_tri(x, y, xa.x, yb.x, xa.y, yb.y, xa.z, yb.z)) continue;
+                emit_sample<MODE>(P, x, y, xa.w, yb.w, cw.x, s_face[lo], s_frag[lo]);
+            }
+        }
     }
 }
 
 // =====================================================================================================================
-// shadow passes: k_shadow_setup == prearrange_realtime_shadowing (cl2.cl:4420-4636),
-//                k_shadow_depth == kernel1_realtime_shadowing (cl2.cl:5130-5246).
-// Slot numbers of a shadow pass are never observable (only the atomic_min result is), so allocation uses one
-// warp-aggregated atomicAdd per counter per warp instead of the scan. Faces not owned by this context are skipped.
+// shadow passes: k_shadow_setup == prearrange_realtime_shadowing (cl2.cl:4420-4636) for ALL lights of a pass in one launch.
+// The reference launches the kernel once per light and re-reads / re-transforms every triangle each time. Here a thread
+// loads its triangle once, brings it to world space once (bit-identical: that part of full_rotate_quat does not depend
+// on the light), and loops over the lights and their cube faces. Slot numbers of a shadow pass are never observable
+// (only the atomic_min result is), so allocation is ONE warp-aggregated 64-bit atomicAdd per (light, face) step that
+// reserves projected-triangle slots and fragment records together. Faces not owned by this context are skipped.
+// Records: {light << 8 | face, chunk, c_id, bits(rconst)} (cl2.cl:4626-4631 with the light folded into word 0).
 // =====================================================================================================================
+#define SHADOW_MAX_LIGHTS 16
+struct ShadowLight { float x, y, z; uint32_t slab; uint32_t face_mask; };
+
 struct ShadowSetupParams {
     const float4* pa; const float4* pb; const float2* pc;
     const ObjLite* objs;
     uint32_t n_tris;
-    float3 lpos;
+    int n_lights;
+    ShadowLight lights[SHADOW_MAX_LIGHTS];
     FaceTable faces;
     float L, icut;
     int only_static;
-    uint32_t face_mask;          // bit kk set -> this context renders face kk of this light
     uint32_t* frags; uint32_t cap_frags;
+    uint32_t* fragcnt;
     float4* cutdown; uint32_t cap_cut;
     uint32_t* counters;
+    uint32_t* buffer;                        // cubemap buffer of this pass (inline raster of small triangles)
 };
 
-__device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t mine) {
+// reserve `nc` projected-triangle slots and `nf` fragment records for this lane; one atomic per warp
+__device__ __forceinline__ void warp_alloc2(uint32_t* counters, uint32_t nc, uint32_t nf, uint32_t& cbase, uint32_t& fbase) {
     const int lane = threadIdx.x & 31;
-    uint32_t inc = mine;
+    const unsigned long long mine = ((unsigned long long)nc << 32) | nf;
+    unsigned long long inc = mine;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    uint32_t base = 0;
-    if (lane == 31 && total) base = atomicAdd(counter, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    return base + inc - mine;
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    const unsigned long long total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total) base = atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_S_NFRAG), total);
+    base = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
+    cbase = (uint32_t)(base >> 32);
+    fbase = (uint32_t)(base & 0xFFFFFFFFull);
 }
 
 __global__ void __launch_bounds__(256) k_shadow_setup(const ShadowSetupParams P) {
+    __shared__ InlineQueue s_iq[256 / 32];
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = tri < P.n_tris;
-    float3 v0, v1, v2;
-    ObjLite G;
-    uint32_t faces = 0;
+    float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0, gpos = w0;
+    bool two_sided = false;
+    InlineRaster ir;
+    ir.q = &s_iq[threadIdx.x >> 5]; ir.count = 0; ir.op = RR_OP_SIZE_LIGHT; ir.width = P.L; ir.height = P.L; ir.base = P.buffer;
+    ir.face_stride = (size_t)(P.L * P.L); ir.row_lo = 0; ir.row_hi = 0x7FFFFFFF;
     if (active) {
         const float4 a = __ldg(P.pa + tri), b = __ldg(P.pb + tri);
         const float2 c = __ldg(P.pc + tri);
-        G = P.objs[__float_as_uint(c.y)];
+        const ObjLite G = P.objs[__float_as_uint(c.y)];
         const bool is_static = (G.feature_flag & RR_FEATURE_IS_STATIC) > 0;
-        const float3 gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
         if ((!P.only_static && is_static) || (P.only_static && !is_static)) active = false;     // cl2.cl:4460-4464
-        else if (length3(gpos - P.lpos) > RR_DEPTH_FAR) active = false;                          // cl2.cl:4472
         else {
-            v0 = make_float3(a.x, a.y, a.z); v1 = make_float3(a.w, b.x, b.y); v2 = make_float3(b.z, b.w, c.x);
-            const float s = G.pos_scale.w;
-            faces |= 1u << ret_cubeface(rot_quat_n(v0 * s, G.nquat) + gpos, P.lpos);             // cl2.cl:4520-4539
-            faces |= 1u << ret_cubeface(rot_quat_n(v1 * s, G.nquat) + gpos, P.lpos);
-            faces |= 1u << ret_cubeface(rot_quat_n(v2 * s, G.nquat) + gpos, P.lpos);
-            faces &= P.face_mask;
+            gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
+            const float sc = G.pos_scale.w;
+            w0 = rot_quat_n(make_float3(a.x, a.y, a.z) * sc, G.nquat) + gpos;                  // cl2.cl:4524-4525 == 505-507
+            w1 = rot_quat_n(make_float3(a.w, b.x, b.y) * sc, G.nquat) + gpos;
+            w2 = rot_quat_n(make_float3(b.z, b.w, c.x) * sc, G.nquat) + gpos;
+            two_sided = (G.feature_flag & RR_FEATURE_TWO_SIDED) > 0;
         }
     }
-    if (!active) faces = 0;
-    const bool two_sided = active && (G.feature_flag & RR_FEATURE_TWO_SIDED) > 0;
-    // warp-uniform loop over the six faces so the warp-level allocation stays converged
-    for (int kk = 0; kk < 6; kk++) {
-        const bool mine = (faces >> kk) & 1u;
-        if (!__any_sync(0xffffffffu, mine)) continue;
-        SubTri st[2];
-        int num = 0;
-        st[0].keep = st[1].keep = false; st[0].n_frag = st[1].n_frag = 0; st[0].rconst = st[1].rconst = 0.f;
-        if (mine) {
-            num = transform_clip_project(v0, v1, v2, G, P.lpos, P.faces.r[kk], P.icut, P.L / 2.f, P.L / 2.f, P.L / 2.0f, st);
-            for (int i = 0; i < num; i++) classify(st[i], two_sided, P.L, P.L, (float)RR_OP_SIZE_LIGHT);
+    for (int li = 0; li < P.n_lights; li++) {
+        const float3 lpos = make_float3(P.lights[li].x, P.lights[li].y, P.lights[li].z);
+        uint32_t faces = 0;
+        if (active && !(length3(gpos - lpos) > RR_DEPTH_FAR)) {                                  // cl2.cl:4472
+            faces = (1u << ret_cubeface(w0, lpos)) | (1u << ret_cubeface(w1, lpos)) | (1u << ret_cubeface(w2, lpos));   // cl2.cl:4520-4539
+            faces &= P.lights[li].face_mask;
         }
-        const uint32_t nk = (st[0].keep ? 1u : 0u) + (st[1].keep ? 1u : 0u);
-        const uint32_t nf0 = st[0].keep ? (uint32_t)st[0].n_frag : 0u, nf1 = st[1].keep ? (uint32_t)st[1].n_frag : 0u;
-        uint32_t cbase = warp_alloc(&P.counters[CTR_S_NCUT], nk);
-        uint32_t fbase = warp_alloc(&P.counters[CTR_S_NFRAG], nf0 + nf1);
-        if (nk == 0) continue;
-        if (cbase + nk > P.cap_cut) { atomicOr(&P.counters[CTR_OVERFLOW], 2u); continue; }
-        if ((unsigned long long)fbase + nf0 + nf1 > (unsigned long long)P.cap_frags) { atomicOr(&P.counters[CTR_OVERFLOW], 1u); continue; }
-        uint32_t cid = cbase;
-        for (int i = 0; i < 2; i++) {
-            if (!st[i].keep) continue;
-            float4* dst = P.cutdown + (size_t)cid * 3;
-            dst[0] = make_float4(st[i].p0.x, st[i].p0.y, st[i].p0.z, 0.f);
-            dst[1] = make_float4(st[i].p1.x, st[i].p1.y, st[i].p1.z, 0.f);
-            dst[2] = make_float4(st[i].p2.x, st[i].p2.y, st[i].p2.z, 0.f);
-            uint4* rec = reinterpret_cast<uint4*>(P.frags) + fbase;                 // {face, chunk, c_id, bits(rconst)} cl2.cl:4626-4631
-            for (int a = 0; a < st[i].n_frag; a++) rec[a] = make_uint4((uint32_t)kk, (uint32_t)a, cid, __float_as_uint(st[i].rconst));
-            fbase += (uint32_t)st[i].n_frag;
-            cid++;
-        }
-    }
-}
-
-struct ShadowDepthParams {
-    const uint32_t* frags; const float4* cutdown; const uint32_t* counters; uint32_t cap_frags;
-    uint32_t* slab;      // this light's 6*L*L cubemap
-    float L; int Li;
-};
-
-__global__ void __launch_bounds__(256) k_shadow_depth(const ShadowDepthParams P) {
-    const uint32_t n = min(P.counters[CTR_S_NFRAG], P.cap_frags);
-    const uint4* recs = reinterpret_cast<const uint4*>(P.frags);
-    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
-        const uint4 rec = __ldg(recs + f);
-        const uint32_t face = rec.x, distance = rec.y, ctri = rec.z;
-        const float rconst = __uint_as_float(rec.w);
-        const float4 c0 = __ldg(P.cutdown + (size_t)ctri * 3), c1 = __ldg(P.cutdown + (size_t)ctri * 3 + 1), c2 = __ldg(P.cutdown + (size_t)ctri * 3 + 2);
-        const FragGeom g = frag_geom(xyz(c0), xyz(c1), xyz(c2), rconst, P.L, P.L);
-        uint32_t* depth = P.slab + (size_t)face * P.Li * P.Li;
-        const float ew = P.L;
-        scan_chunk(g.mm, RR_OP_SIZE_LIGHT, distance, [&](float x, float y) {
-            if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
-                float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
-                uint32_t d = sat_u32(RR_U32MAXF / fd);
-                atomicMin(depth + ((int)(y * ew) + (int)x), d);
+        // warp-uniform loop over the six faces so the warp-level allocation stays converged
+        for (int kk = 0; kk < 6; kk++) {
+            const bool mine = (faces >> kk) & 1u;
+            if (!__any_sync(0xffffffffu, mine)) continue;
+            SubTri st0, st1;
+            subtri_clear(st0); subtri_clear(st1);
+            if (mine) {
+                const RotSC& fr = P.faces.r[kk];
+                const int num = clip_project(rot(w0, lpos, fr), rot(w1, lpos, fr), rot(w2, lpos, fr), P.icut, P.L / 2.f, P.L / 2.f, P.L / 2.0f, st0, st1);
+                if (num > 0) classify(st0, two_sided, P.L, P.L, (float)RR_OP_SIZE_LIGHT);
+                if (num > 1) classify(st1, two_sided, P.L, P.L, (float)RR_OP_SIZE_LIGHT);
             }
-        });
+            // small triangles: queued for the warp to rasterise with all lanes busy; nothing is stored for them
+            const uint32_t face_index = P.lights[li].slab * 6 + (uint32_t)kk;
+            const bool small0 = inline_candidate(st0), small1 = inline_candidate(st1);
+            ir.push(small0, st0, face_index);
+            ir.push(small1, st1, face_index);
+            if (small0) st0.keep = false;
+            if (small1) st1.keep = false;
+            if (!__any_sync(0xffffffffu, st0.keep || st1.keep)) continue;
+            const uint32_t nk = (st0.keep ? 1u : 0u) + (st1.keep ? 1u : 0u);
+            const uint32_t nf0 = st0.keep ? (uint32_t)st0.n_frag : 0u, nf1 = st1.keep ? (uint32_t)st1.n_frag : 0u;
+            uint32_t cid, fbase;
+            warp_alloc2(P.counters, nk, nf0 + nf1, cid, fbase);
+            if (nk == 0) continue;
+            if (cid + nk > P.cap_cut) { atomicOr(&P.counters[CTR_OVERFLOW], 2u); continue; }
+            if ((unsigned long long)fbase + nf0 + nf1 > (unsigned long long)P.cap_frags) { atomicOr(&P.counters[CTR_OVERFLOW], 1u); continue; }
+            const uint32_t word0 = ((uint32_t)li << 8) | (uint32_t)kk;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const SubTri& st = i ? st1 : st0;
+                if (!st.keep) continue;
+                float4* dst = P.cutdown + (size_t)cid * 3;
+                dst[0] = make_float4(st.p0.x, st.p0.y, st.p0.z, 0.f);
+                dst[1] = make_float4(st.p1.x, st.p1.y, st.p1.z, 0.f);
+                dst[2] = make_float4(st.p2.x, st.p2.y, st.p2.z, 0.f);
+                const int kend = subtri_walk_end(st, P.L, P.L);
+                uint4* rec = reinterpret_cast<uint4*>(P.frags) + fbase;
+                for (int a = 0; a < st.n_frag; a++) {
+                    rec[a] = make_uint4(word0, (uint32_t)a, cid, __float_as_uint(st.rconst));
+                    P.fragcnt[fbase + a] = chunk_slots(kend, a, RR_OP_SIZE_LIGHT);
+                }
+                fbase += (uint32_t)st.n_frag;
+                cid++;
+            }
+        }
     }
-}
-
-// accumulate statistics of a finished shadow pass and reset its counters for the next one
-__global__ void k_shadow_pass_end(uint32_t* counters) {
-    counters[CTR_S_TOTAL] += counters[CTR_S_NFRAG];
-    counters[CTR_S_NCUT] = 0;
-    counters[CTR_S_NFRAG] = 0;
+    ir.flush();
 }
 
 // =====================================================================================================================
@@ -574,7 +869,7 @@ __global__ void __launch_bounds__(256) k_atlas_mip(uint32_t src_id, uint32_t dst
 // =====================================================================================================================
 struct ShadeParams {
     const rr_triangle* tris; const rr_obj_desc* objs;
-    const uint32_t* frags; const float4* cutdown;
+    const uint32_t* frags; const float4* cutdown; const uint32_t* n_frags;
     const uint32_t* depth; const uint32_t* ids;
     uint32_t* depth_next; uint32_t* ids_next;        // cleared for the next frame (to_clear, cl2.cl:5820)
     uchar4* rgba8; ushort2* normals;
@@ -643,8 +938,8 @@ __device__ __forceinline__ float4 texture_filter_diff(float2 vt, float2 vtdiff, 
 __device__ __forceinline__ float generate_ssao(int sx, int sy, const uint32_t* __restrict__ depth_buffer, int W, int H, float fov, float ssao_rad, float ssao_div) {
     uint32_t seed1 = wang_hash((uint32_t)sx + (uint32_t)W * (uint32_t)H * (uint32_t)sy);
     uint32_t seed2 = rand_xorshift(seed1);
-    float foffset = (float)seed2 / RR_U32MAXF;
-    float depth = ((float)__ldg(depth_buffer + sy * W + sx) / RR_U32MAXF) * RR_DEPTH_FAR;
+    float foffset = (float)seed2 * RR_INV_U32MAXF;
+    float depth = ((float)__ldg(depth_buffer + sy * W + sx) * RR_INV_U32MAXF) * RR_DEPTH_FAR;
     float rad = ssao_rad + foffset / 2.f;
     float world_rad = rad * fov / depth;
     float acc = 0.f;
@@ -652,7 +947,7 @@ __device__ __forceinline__ float generate_ssao(int sx, int sy, const uint32_t* _
         for (int x = -2; x <= 2; x++) {
             float ox = roundf((float)x * world_rad), oy = roundf((float)y * world_rad);
             float wx = clampf((float)sx + ox, 1.f, (float)W - 2.f), wy = clampf((float)sy + oy, 1.f, (float)H - 2.f);
-            float d2 = ((float)__ldg(depth_buffer + ((int)wy) * W + (int)wx) / RR_U32MAXF) * RR_DEPTH_FAR;
+            float d2 = ((float)__ldg(depth_buffer + ((int)wy) * W + (int)wx) * RR_INV_U32MAXF) * RR_DEPTH_FAR;
 #pragma unroll
             for (int z = -2; z <= 2; z++)
                 if (d2 > depth + (float)z) acc += 1.f;
@@ -682,7 +977,7 @@ __device__ __forceinline__ float hard_occlusion(float3 lpos, float3 normal, floa
     for (int y = -1; y <= 2; y++)
 #pragma unroll
         for (int x = -1; x <= 2; x++) {
-            float ldp1 = ((float)__ldg(ldepth_map + (ipy + y) * L + ipx + x) / RR_U32MAXF) * RR_DEPTH_FAR;
+            float ldp1 = ((float)__ldg(ldepth_map + (ipy + y) * L + ipx + x) * RR_INV_U32MAXF) * RR_DEPTH_FAR;
             cnd[(y + 1) * 4 + x + 1] = dpth > ldp1 + bias ? 1.f : 0.f;
         }
     float shadow = 0.f;
@@ -722,6 +1017,10 @@ __global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
         return;
     }
     const uint32_t idv = P.ids[px];
+    if (idv >= P.n_frags[0]) {          // stale id (buffers not swapped since an earlier frame): never index past this frame's records (q7)
+        P.rgba8[px] = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
+        return;
+    }
     const uint32_t* rec = P.frags + (size_t)idv * RR_FRAG_WORDS;
     const uint32_t tri_global = __ldg(rec + 0), ctri = __ldg(rec + 2);
     const float rconst = __uint_as_float(__ldg(rec + 3));
@@ -748,7 +1047,7 @@ __global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
     const float fov = P.fov;
     const float3 zero3 = make_float3(0, 0, 0);
 
-    const float ldepth = ((float)d / RR_U32MAXF) * RR_DEPTH_FAR;      // cl2.cl:5897
+    const float ldepth = ((float)d * RR_INV_U32MAXF) * RR_DEPTH_FAR;  // cl2.cl:5897 (x / 2^32 == x * 2^-32 exactly)
     float3 local_position = make_float3((((float)x - W / 2.0f) * ldepth / fov), (((float)y - H / 2.0f) * ldepth / fov), ldepth);
     float3 global_position = back_rot(local_position, zero3, P.cam.rot);
     global_position = global_position + P.cam.pos;
@@ -792,7 +1091,7 @@ __global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
 
     const uint32_t seed1 = wang_hash((uint32_t)x + (uint32_t)y * (uint32_t)W * (uint32_t)H);    // cl2.cl:5965 (wraps mod 2^32)
     const uint32_t seed2 = rand_xorshift(seed1), seed3 = rand_xorshift(seed2), seed4 = rand_xorshift(seed3);
-    float3 rseed = make_float3((float)seed2 / RR_U32MAXF, (float)seed3 / RR_U32MAXF, (float)seed4 / RR_U32MAXF);
+    float3 rseed = make_float3((float)seed2 * RR_INV_U32MAXF, (float)seed3 * RR_INV_U32MAXF, (float)seed4 * RR_INV_U32MAXF);
     rseed = make_float3((rseed.x - 0.5f) * 2, (rseed.y - 0.5f) * 2, (rseed.z - 0.5f) * 2);
 
     float3 diffuse_sum = zero3, specular_sum = zero3;
@@ -824,7 +1123,8 @@ __global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
             static_num++;
         }
         float distance = length3(point_to_light);
-        float illumination = __ldg(&l->brightness) / powf((distance / __ldg(&l->radius)) + 1.f, 2.f);
+        const float dr1 = (distance / __ldg(&l->radius)) + 1.f;
+        float illumination = __ldg(&l->brightness) / (dr1 * dr1);                             // pow(x, 2)
         const float cutoff = 0.1f;
         illumination -= cutoff;
         illumination *= 1.f / (1.f - cutoff);
@@ -850,7 +1150,8 @@ __global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
         float vdh = fmaxf(0.f, dot3(l2p, Hh));
         float ndl = fmaxf(0.f, dot3(normal, point_to_light));
         const float F0 = 0.4f;
-        float fresnel = F0 + (1 - F0) * powf((1.f - vdh), 5.f);
+        const float omv = 1.f - vdh, omv2 = omv * omv;
+        float fresnel = F0 + (1 - F0) * (omv2 * omv2 * omv);                                  // native_powr(x, 5)
         float rough = clampf(1.f - Gspecular, 0.001f, 10.f);
         float alpha = rational_acos(ndh);
         float microfacet = 0.8346f * expf(-alpha * alpha / (rough * rough));

@@ -12,6 +12,7 @@ namespace rr {
 
 #define RR_DEPTH_FAR 350000.0f       /* cl2.cl:17 */
 #define RR_U32MAXF 4294967296.0f     /* (float)UINT_MAX, cl2.cl:19 */
+#define RR_INV_U32MAXF 2.3283064365386963e-10f   /* 2^-32: x / 2^32 == x * 2^-32 bit for bit */
 #define RR_PI_F 3.1415927f           /* cl2.cl:14 */
 #define RR_OP_SIZE 500               /* cl2.cl:4247 */
 #define RR_OP_SIZE_LIGHT 300         /* cl2.cl:4249 */
@@ -132,35 +133,38 @@ __device__ __forceinline__ float3 project(float3 r, float half_w, float half_h, 
     return make_float3(fmaf(r.x, k, half_w), fmaf(r.y, k, half_h), r.z);
 }
 
-// cl2.cl:577-663 — near-plane clip of one camera-space triangle into 0/1/2 triangles
-__device__ __forceinline__ int clip_near(const float3 (&pt)[3], float icut, float3 (&out)[2][3]) {
-    int id_valid = 0, n_behind = 0;
-    int ids_behind[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        if (pt[i].z <= icut || pt[i].z > RR_DEPTH_FAR) { ids_behind[n_behind] = i; n_behind++; }
-        else id_valid = i;
-    }
+// cl2.cl:577-663 — near-plane clip of one camera-space triangle into 0/1/2 triangles (register-only formulation:
+// the reference's index arrays become selects so nothing is spilled to local memory)
+__device__ __forceinline__ float3 sel3(int k, float3 a, float3 b, float3 c) { return k == 0 ? a : (k == 1 ? b : c); }
+
+__device__ __forceinline__ int clip_near(float3 q0, float3 q1, float3 q2, float icut, float3& a0, float3& a1, float3& a2, float3& b0, float3& b1, float3& b2) {
+    const bool h0 = q0.z <= icut || q0.z > RR_DEPTH_FAR, h1 = q1.z <= icut || q1.z > RR_DEPTH_FAR, h2 = q2.z <= icut || q2.z > RR_DEPTH_FAR;
+    const int n_behind = (int)h0 + (int)h1 + (int)h2;
+    if (n_behind == 0) { a0 = q0; a1 = q1; a2 = q2; return 1; }
     if (n_behind > 2) return 0;
-    if (n_behind == 0) { out[0][0] = pt[0]; out[0][1] = pt[1]; out[0][2] = pt[2]; return 1; }
     int g1, g2, g3;
     if (n_behind == 1) {
-        int id = ids_behind[0];
+        const int id = h0 ? 0 : (h1 ? 1 : 2);                     // ids_behind[0]
         g1 = id;
         g2 = (id + 1) >= 3 ? id - 2 : id + 1;
         g3 = (id + 2) >= 3 ? id - 1 : id + 2;
-    } else { g2 = ids_behind[0]; g3 = ids_behind[1]; g1 = id_valid; }
-    float3 P1 = pt[g1], P2 = pt[g2], P3 = pt[g3];
-    float3 p1 = P2 + ((icut - P2.z) * (P1 - P2)) / (P1.z - P2.z);
-    float3 p2 = P3 + ((icut - P3.z) * (P1 - P3)) / (P1.z - P3.z);
+    } else {
+        g2 = h0 ? 0 : 1;                                          // ids_behind[0]
+        g3 = h2 ? 2 : 1;                                          // ids_behind[1]
+        g1 = !h0 ? 0 : (!h1 ? 1 : 2);                             // id_valid
+    }
+    const float3 P1 = sel3(g1, q0, q1, q2), P2 = sel3(g2, q0, q1, q2), P3 = sel3(g3, q0, q1, q2);
+    const float3 p1 = P2 + ((icut - P2.z) * (P1 - P2)) / (P1.z - P2.z);
+    const float3 p2 = P3 + ((icut - P3.z) * (P1 - P3)) / (P1.z - P3.z);
     if (n_behind == 1) {
-        out[0][0] = p1; out[0][1] = P2; out[0][2] = P3;
-        out[1][0] = p1; out[1][1] = P3; out[1][2] = p2;
+        a0 = p1; a1 = P2; a2 = P3;
+        b0 = p1; b1 = P3; b2 = p2;
         return 2;
     }
-    // two behind: slots ids_behind[0] <- p1, ids_behind[1] <- p2, id_valid <- the valid vertex
-#pragma unroll
-    for (int k = 0; k < 3; k++) out[0][k] = (k == g2) ? p1 : ((k == g3) ? p2 : P1);
+    // two behind: slot ids_behind[0] <- p1, slot ids_behind[1] <- p2, slot id_valid <- the valid vertex
+    a0 = (0 == g2) ? p1 : ((0 == g3) ? p2 : P1);
+    a1 = (1 == g2) ? p1 : ((1 == g3) ? p2 : P1);
+    a2 = (2 == g2) ? p1 : ((2 == g3) ? p2 : P1);
     return 1;
 }
 
@@ -197,7 +201,8 @@ __device__ __forceinline__ uint32_t rand_xorshift(uint32_t s) { s ^= (s << 13); 
 // cl2.cl:2469-2477
 __device__ __forceinline__ float rational_acos(float x) {
     const float a = -0.939115566365855f, b = 0.9217841528914573f, c = -1.2845906244690837f, d = 0.295624144969963174f;
-    return RR_PI_F / 2.f + (a * x + b * x * x * x) / (1.f + c * x * x + d * powf(x, 4.f));
+    const float x2 = x * x;
+    return RR_PI_F / 2.f + (a * x + b * x * x * x) / (1.f + c * x * x + d * (x2 * x2));      // pow(x, 4)
 }
 
 // cl2.cl:5372-5384
@@ -262,8 +267,8 @@ __device__ __forceinline__ FragGeom frag_geom(float3 p0, float3 p1, float3 p2, f
 }
 
 // The reference's pixel walk (cl2.cl:5042-5095 == 5184-5227 == 5447-5508), replayed verbatim for ONE chunk.
-// f(x, y) is called for every pixel the state machine tests. Kept sequential on purpose: the walk has float quirks
-// (a lagging / leading row counter skips the first column of some rows) that define the covered-pixel set.
+// f(x, y) is called for every pixel the state machine tests. Used for small chunks (few slots: one thread each);
+// large chunks go through the closed form below so their slots can be spread over many threads.
 template <class F>
 __device__ __forceinline__ void scan_chunk(const float4 mm, int op_size, uint32_t distance, F&& f) {
     int width = (int)(mm.y - mm.x);
@@ -287,6 +292,35 @@ __device__ __forceinline__ void scan_chunk(const float4 mm, int op_size, uint32_
         if (x >= mm.y) continue;
         f(x, y);
     }
+}
+
+// ---- closed form of the walk ------------------------------------------------------------------------------------------
+// The walk visits linear indices k = k0 .. k0+op of the row-major box, with a float row counter
+//     y_k = floor(fma((float)k, 1.f/width, min_y))                  (cl2.cl:5076)
+// that can lag or lead the true row by a step at exact row boundaries, and a column that restarts only when y_k changes.
+// Because y_k is monotone in k, the walk has a closed form (property-tested against the literal state machine in
+// tests/test_oracle_units.py::test_scan_closed_form_equals_literal_walk):
+//     x_k = min_x + (j mod width) + (k - j),   j = max(k0, first index whose row counter equals y_k)
+// and the walk of a triangle ends at k_end = first k with y_k >= max_y. This is what lets pixel slots be spread evenly
+// over threads instead of being replayed sequentially per fragment.
+__device__ __forceinline__ float walk_row(int k, float iw, float min_y) { return floorf(fmaf((float)k, iw, min_y)); }
+
+__device__ __forceinline__ int walk_end(int width, int rows, float iw, float min_y, float max_y) {
+    int k = width * rows;
+    while (k > 0 && walk_row(k - 1, iw, min_y) >= max_y) k--;
+    while (walk_row(k, iw, min_y) < max_y) k++;
+    return k;
+}
+
+// pixel of slot k in the chunk starting at k0; returns false when the walk skips it (x beyond the box)
+__device__ __forceinline__ bool walk_pixel(int k, int k0, int width, float iw, const float4 mm, float& x, float& y) {
+    y = walk_row(k, iw, mm.z);
+    int c = (int)(y - mm.z) * width;
+    while (c > k0 && walk_row(c - 1, iw, mm.z) == y) c--;
+    while (walk_row(c, iw, mm.z) < y) c++;
+    const int j = max(c, k0);
+    x = mm.x + (float)(j % width) + (float)(k - j);
+    return x < mm.y;
 }
 
 }  // namespace rr
