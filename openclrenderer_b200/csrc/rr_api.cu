@@ -79,6 +79,7 @@ struct rr_ctx {
     // lights
     std::vector<rr_light> lights;
     rr_light* d_lights = nullptr;
+    LightLite* d_lightlite = nullptr;
     uint32_t n_shadow = 0, n_static = 0;
     uint32_t *d_shadow_dyn = nullptr, *d_shadow_static = nullptr;
     bool ext_shadow_dyn = false, ext_shadow_static = false;
@@ -90,6 +91,7 @@ struct rr_ctx {
     uchar4* d_rgba8 = nullptr;
     bool ext_rgba8 = false;
     ushort2* d_normals = nullptr;
+    uint32_t* d_shade_list = nullptr;            // compacted covered pixels
     // raster storage
     uint32_t* d_frags = nullptr;
     uint32_t cap_frags = 0;
@@ -226,6 +228,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     }
     if (cudaMalloc((void**)&c->d_rgba8, P * 4) != cudaSuccess) return bail("rgba8");
     if (cudaMalloc((void**)&c->d_normals, P * 4) != cudaSuccess) return bail("normals");
+    if (cudaMalloc((void**)&c->d_shade_list, P * 4) != cudaSuccess) return bail("shade list");
     c->cap_frags = cfg->max_fragments ? cfg->max_fragments : (16u << 20);
     if (cudaMalloc((void**)&c->d_frags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("fragment buffer");
     if (cudaMalloc((void**)&c->d_fragcnt, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("slot counts");
@@ -252,13 +255,13 @@ void rr_destroy(rr_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite);
     cudaFree(c->d_atlas); cudaFree(c->d_nums); cudaFree(c->d_sizes); cudaFree(c->d_upload);
-    cudaFree(c->d_lights);
+    cudaFree(c->d_lights); cudaFree(c->d_lightlite);
     if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
     if (!c->ext_shadow_static) cudaFree(c->d_shadow_static);
     for (int i = 0; i < 2; i++) { cudaFree(c->d_depth[i]); cudaFree(c->d_ids[i]); }
     if (!c->ext_rgba8) cudaFree(c->d_rgba8);
     cudaFree(c->d_fragcnt); cudaFree(c->d_scan_lookback); cudaFree(c->d_biglist); cudaFree(c->d_bigslot);
-    cudaFree(c->d_normals); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
+    cudaFree(c->d_normals); cudaFree(c->d_shade_list); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
     for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -388,7 +391,12 @@ int rr_lights_write(rr_ctx* c, const rr_light* lights, uint32_t n_active) {
     }
     int r;
     if ((r = dev_alloc(c->d_lights, std::max(n_active, 1u)))) return r;   // clamped_num, light.cpp:172
-    if (n_active) CU(cudaMemcpyAsync(c->d_lights, lights, (size_t)n_active * sizeof(rr_light), cudaMemcpyHostToDevice, c->stream));
+    if ((r = dev_alloc(c->d_lightlite, std::max(n_active, 1u)))) return r;
+    if (n_active) {
+        CU(cudaMemcpyAsync(c->d_lights, lights, (size_t)n_active * sizeof(rr_light), cudaMemcpyHostToDevice, c->stream));
+        k_lightlite<<<(n_active + 63) / 64, 64, 0, c->stream>>>(c->d_lights, n_active, c->d_lightlite);
+        c->launches++;
+    }
     const size_t slab = (size_t)6 * c->L * c->L;
     if (!c->ext_shadow_dyn && (ns != c->n_shadow || !c->d_shadow_dyn)) {
         c->shadow_dyn_words = std::max<size_t>(slab * ns, 4);
@@ -516,7 +524,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
     // kernel3
     ShadeParams hp;
-    hp.tris = c->d_tris; hp.objs = c->d_objs; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
+    hp.tris = c->d_tris; hp.objs = c->d_objs; hp.objlite = c->d_objlite; hp.lightlite = c->d_lightlite; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
     hp.depth = c->d_depth[c->cur]; hp.ids = c->d_ids[c->cur];
     hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
     hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
@@ -533,10 +541,13 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     hp.no_ssao = c->cfg.no_ssao;
     hp.row0 = row0; hp.row1 = row1; hp.band_y0 = band0; hp.band_y1 = band1;
     if (hp.n_lights > 0 && (!c->d_lights)) return fail(RR_ERR_INVALID, "lights not written");
+    hp.shade_list = c->d_shade_list; hp.shade_count = c->d_counters + CTR_NSHADE;
+    CU(cudaMemsetAsync(c->d_counters + CTR_NSHADE, 0, 4, c->stream));
     dim3 grid((c->W + 31) / 32, (row1 - row0 + 7) / 8);
-    k_shade<<<grid, 256, 0, c->stream>>>(hp);
+    k_shade_pre<<<grid, 256, 0, c->stream>>>(hp);
+    k_shade<<<grid_for(c, 12), 128, 0, c->stream>>>(hp);
     CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
-    c->launches += 2;
+    c->launches += 3;
     c->have_frame_ev = true;
     CU(cudaGetLastError());
     return RR_OK;

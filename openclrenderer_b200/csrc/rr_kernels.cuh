@@ -18,6 +18,7 @@ enum {
     CTR_SLOTS = 7,     // total pixel slots of the fragment list last scanned (k_scan_slots)
     CTR_SCAN_TICKET = 8,
     CTR_NBIG = 9,      // number of big fragments (more than RASTER_SMALL_MAX slots) in the list last scanned
+    CTR_NSHADE = 10,   // covered pixels in the shading list
     CTR_COUNT = 12
 };
 
@@ -50,9 +51,16 @@ __global__ void __launch_bounds__(256) k_repack(const rr_triangle* __restrict__ 
 struct ObjLite {
     float4 pos_scale;     // world_pos.xyz, scale
     float4 nquat;         // fast_normalize(world_rot_quat)  (rot_quat() normalises on every call, cl2.cl:352)
+    float4 bquat;         // the normalised conjugate back_rot_quat() ends up rotating with (cl2.cl:359-370)
     int32_t feature_flag;
     int32_t _pad[3];
 };
+
+// Per-light constants of kernel3's light loop: the light colour after gamma_transform_approx (cl2.cl:6150-6153), which the
+// reference recomputes per pixel per light.
+struct LightLite { float4 col_linear; };
+
+__global__ void k_lightlite(const rr_light* __restrict__ lights, uint32_t n, LightLite* __restrict__ out);
 
 __global__ void __launch_bounds__(128) k_objlite(const rr_obj_desc* __restrict__ objs, uint32_t n, ObjLite* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +68,9 @@ __global__ void __launch_bounds__(128) k_objlite(const rr_obj_desc* __restrict__
     const rr_obj_desc& G = objs[i];
     ObjLite o;
     o.pos_scale = make_float4(G.world_pos[0], G.world_pos[1], G.world_pos[2], G.scale);
-    o.nquat = normalize4(make_float4(G.world_rot_quat[0], G.world_rot_quat[1], G.world_rot_quat[2], G.world_rot_quat[3]));
+    const float4 q = make_float4(G.world_rot_quat[0], G.world_rot_quat[1], G.world_rot_quat[2], G.world_rot_quat[3]);
+    o.nquat = normalize4(q);
+    o.bquat = back_quat(q);
     o.feature_flag = G.feature_flag;
     o._pad[0] = o._pad[1] = o._pad[2] = 0;
     out[i] = o;
@@ -868,8 +878,9 @@ __global__ void __launch_bounds__(256) k_atlas_mip(uint32_t src_id, uint32_t dst
 // depth / id loads and the RGBA8 / normal / clear stores are full 128-byte lines).
 // =====================================================================================================================
 struct ShadeParams {
-    const rr_triangle* tris; const rr_obj_desc* objs;
+    const rr_triangle* tris; const rr_obj_desc* objs; const ObjLite* objlite; const LightLite* lightlite;
     const uint32_t* frags; const float4* cutdown; const uint32_t* n_frags;
+    uint32_t* shade_list; uint32_t* shade_count;     // covered pixels of this frame (k_shade_pre -> k_shade)
     const uint32_t* depth; const uint32_t* ids;
     uint32_t* depth_next; uint32_t* ids_next;        // cleared for the next frame (to_clear, cl2.cl:5820)
     uchar4* rgba8; ushort2* normals;
@@ -942,16 +953,22 @@ __device__ __forceinline__ float generate_ssao(int sx, int sy, const uint32_t* _
     float depth = ((float)__ldg(depth_buffer + sy * W + sx) * RR_INV_U32MAXF) * RR_DEPTH_FAR;
     float rad = ssao_rad + foffset / 2.f;
     float world_rad = rad * fov / depth;
-    float acc = 0.f;
-    for (int y = -2; y <= 2; y++)
-        for (int x = -2; x <= 2; x++) {
-            float ox = roundf((float)x * world_rad), oy = roundf((float)y * world_rad);
-            float wx = clampf((float)sx + ox, 1.f, (float)W - 2.f), wy = clampf((float)sy + oy, 1.f, (float)H - 2.f);
-            float d2 = ((float)__ldg(depth_buffer + ((int)wy) * W + (int)wx) * RR_INV_U32MAXF) * RR_DEPTH_FAR;
+    // the five thresholds depth + z are per-pixel constants; acc only ever adds 1.f, so an integer count is the same value
+    const float t0 = depth + -2.f, t1 = depth + -1.f, t2 = depth + 0.f, t3 = depth + 1.f, t4 = depth + 2.f;
+    int cnt = 0;
+    for (int y = -2; y <= 2; y++) {
+        const float oy = roundf((float)y * world_rad);
+        const float wy = clampf((float)sy + oy, 1.f, (float)H - 2.f);
+        const uint32_t* row = depth_buffer + ((int)wy) * W;
 #pragma unroll
-            for (int z = -2; z <= 2; z++)
-                if (d2 > depth + (float)z) acc += 1.f;
+        for (int x = -2; x <= 2; x++) {
+            const float ox = roundf((float)x * world_rad);
+            const float wx = clampf((float)sx + ox, 1.f, (float)W - 2.f);
+            const float d2 = ((float)__ldg(row + (int)wx) * RR_INV_U32MAXF) * RR_DEPTH_FAR;
+            cnt += (int)(d2 > t0) + (int)(d2 > t1) + (int)(d2 > t2) + (int)(d2 > t3) + (int)(d2 > t4);
         }
+    }
+    float acc = (float)cnt;
     acc /= 125.f;                       // pow(samples*2+1, 3)
     return 1.f - (1.f - acc) / ssao_div;
 }
@@ -1002,25 +1019,12 @@ __device__ __forceinline__ float4 vertex_col_f(uint32_t c) {        // cl2.cl:56
 
 __device__ __forceinline__ unsigned char quant8(float c) { return (unsigned char)(clampf(c, 0.f, 1.f) * 255.f + 0.5f); }
 
-__global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = P.row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= P.W || y >= P.row1) return;
+// Shading of one covered pixel (everything of kernel3 after the depth == UINT_MAX early-out, cl2.cl:5864-6390).
+__device__ __forceinline__ void shade_pixel(const ShadeParams& P, const int x, const int y) {
     const int W = P.W, H = P.H;
     const size_t px = (size_t)y * W + x;
     const uint32_t d = P.depth[px];
-    P.depth_next[px] = 0xFFFFFFFFu;                                    // to_clear, cl2.cl:5820
-    P.ids_next[px] = 0u;                                               // id image of the next frame (atomicMax needs a clean slate)
-    if (y < P.band_y0 || y >= P.band_y1) return;
-    if (d == 0xFFFFFFFFu) {                                            // cl2.cl:5835-5862
-        P.rgba8[px] = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
-        return;
-    }
     const uint32_t idv = P.ids[px];
-    if (idv >= P.n_frags[0]) {          // stale id (buffers not swapped since an earlier frame): never index past this frame's records (q7)
-        P.rgba8[px] = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
-        return;
-    }
     const uint32_t* rec = P.frags + (size_t)idv * RR_FRAG_WORDS;
     const uint32_t tri_global = __ldg(rec + 0), ctri = __ldg(rec + 2);
     const float rconst = __uint_as_float(__ldg(rec + 3));
@@ -1039,10 +1043,9 @@ __global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
     const float2 vt1 = make_float2(t0.x, t0.y), vt2 = make_float2(t1.x, t1.y), vt3 = make_float2(t2.x, t2.y);
     const uint32_t vc0 = __float_as_uint(t0.w), vc1 = __float_as_uint(t1.w), vc2 = __float_as_uint(t2.w);
     const float4 Gpos4 = __ldg(reinterpret_cast<const float4*>(G->world_pos));
-    const float4 Gq = __ldg(reinterpret_cast<const float4*>(G->world_rot_quat));
     const float Gscale = __ldg(&G->scale);
     const float3 Gpos = xyz(Gpos4);
-    const float4 Gqn = normalize4(Gq), Gqb = back_quat(Gq);
+    const float4 Gqn = __ldg(&P.objlite[o_id].nquat), Gqb = __ldg(&P.objlite[o_id].bquat);     // per-object constants, hoisted (k_objlite)
     const float3 p1 = xyz(pv0) * Gscale, p2 = xyz(pv1) * Gscale, p3 = xyz(pv2) * Gscale;
     const float fov = P.fov;
     const float3 zero3 = make_float3(0, 0, 0);
@@ -1129,8 +1132,7 @@ __global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
         illumination -= cutoff;
         illumination *= 1.f / (1.f - cutoff);
         if (illumination <= 0) continue;
-        float3 light_col = xyz(lc4);
-        if (P.linear) light_col = make_float3(gamma_fwd(light_col.x), gamma_fwd(light_col.y), gamma_fwd(light_col.z));
+        const float3 light_col = P.linear ? xyz(__ldg(&P.lightlite[i].col_linear)) : xyz(lc4);   // gamma of the light colour hoisted (k_lightlite)
         if (lshadow && receives_dynamic_shadows) {
             int face = ret_cubeface(global_position, lpos);
             float dyn = 1.f - hard_occlusion(lpos, normal, point_to_light, P.shadow_dyn, face, global_position, shnum, P);
@@ -1179,6 +1181,58 @@ __global__ void __launch_bounds__(256) k_shade(const ShadeParams P) {
     float k = sqrtf(fmaxf(nn.z * 0.5f + 0.5f, 0.f));
     float rx = (nn.x / ln) * k, ry = (nn.y / ln) * k;
     P.normals[px] = make_ushort2(to_ushort_sat(((rx + 1) / 2) * 65536 - 1), to_ushort_sat(((ry + 1) / 2) * 65536 - 1));
+}
+
+// k_shade_pre: the streaming part of kernel3 for every pixel of the 32x8 tile (clear the next frame's depth and id,
+// cl2.cl:5820; write the clear colour where nothing was drawn, 5835-5862) and a device-wide list of the covered pixels:
+// warp ballot + block prefix in shared memory, ONE atomicAdd per tile to reserve its range, coalesced index stores.
+__global__ void __launch_bounds__(256) k_shade_pre(const ShadeParams P) {
+    __shared__ int s_warp[8];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x = blockIdx.x * 32 + lane;
+    const int y = P.row0 + blockIdx.y * 8 + warp;
+    bool covered = false;
+    uint32_t px = 0;
+    if (x < P.W && y < P.row1) {
+        px = (uint32_t)y * (uint32_t)P.W + (uint32_t)x;
+        const uint32_t d = P.depth[px];
+        const uint32_t idv = (d != 0xFFFFFFFFu) ? P.ids[px] : 0u;
+        P.depth_next[px] = 0xFFFFFFFFu;
+        P.ids_next[px] = 0u;                                               // id image of the next frame (atomicMax needs a clean slate)
+        if (y >= P.band_y0 && y < P.band_y1) {
+            // idv >= n_frags: stale id (buffers not swapped since an earlier frame) - never index past this frame's records (q7)
+            covered = d != 0xFFFFFFFFu && idv < P.n_frags[0];
+            if (!covered) P.rgba8[px] = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, covered);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const int c = s_warp[w]; if (w < warp) off += c; total += c; }
+    if (total == 0) return;
+    if (tid == 0) s_base = atomicAdd(P.shade_count, (uint32_t)total);
+    __syncthreads();
+    if (covered) P.shade_list[s_base + off + __popc(m & ((1u << lane) - 1u))] = px;
+}
+
+// k_shade: the expensive part of kernel3 (~6000 instructions per covered pixel) over the compacted list — every warp
+// is dense whatever the screen coverage looks like. Persistent grid, stride over the list.
+__global__ void __launch_bounds__(128) k_shade(const ShadeParams P) {
+    const uint32_t n = *P.shade_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t px = __ldg(P.shade_list + i);
+        const int y = (int)(px / (uint32_t)P.W);
+        shade_pixel(P, (int)(px - (uint32_t)y * (uint32_t)P.W), y);
+    }
+}
+
+__global__ void k_lightlite(const rr_light* __restrict__ lights, uint32_t n, LightLite* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i].col_linear = make_float4(gamma_fwd(lights[i].col[0]), gamma_fwd(lights[i].col[1]), gamma_fwd(lights[i].col[2]), lights[i].col[3]);
 }
 
 // =====================================================================================================================
