@@ -104,7 +104,15 @@ struct rr_ctx {
     uint32_t *d_biglist = nullptr, *d_bigslot = nullptr;   // compacted big fragments + exclusive prefix of their slots (k_scan_big)
     unsigned long long* d_scan_lookback = nullptr;
     uint32_t scan_tiles = 0;
-    uint32_t* h_counters = nullptr;      // pinned
+    uint32_t* h_counters = nullptr;      // pinned (main counters, then shadow counters)
+    // second raster workspace + stream: the shadow passes of a frame run concurrently with the main view's setup / depth /
+    // id kernels (they only meet at shading). The reference shares g_tid_buf / g_cut_tri_mem between them and serialises.
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_shadow_done = nullptr;
+    bool shadow_pending = false;
+    uint32_t *d_sfrags = nullptr, *d_sfragcnt = nullptr, *d_sbiglist = nullptr, *d_sbigslot = nullptr, *d_scounters = nullptr;
+    float4* d_scutdown = nullptr;
+    unsigned long long* d_sscan_lookback = nullptr;
     // e2e staging (pinned)
     rr_obj_desc* h_objs_pinned = nullptr;
     // stats
@@ -124,9 +132,9 @@ int dev_alloc(T*& p, size_t count) {
 
 inline int grid_for(const rr_ctx* c, int per_sm) { return c->sm_count * per_sm; }
 
-int fill_u32(rr_ctx* c, uint32_t* p, size_t n, uint32_t v) {
+int fill_u32(rr_ctx* c, cudaStream_t st, uint32_t* p, size_t n, uint32_t v) {
     if (n == 0) return RR_OK;
-    k_fill_u32<<<grid_for(c, 8), 256, 0, c->stream>>>(p, n, v);
+    k_fill_u32<<<grid_for(c, 8), 256, 0, st>>>(p, n, v);
     c->launches++;
     CU(cudaGetLastError());
     return RR_OK;
@@ -142,20 +150,20 @@ int ensure_objlite(rr_ctx* c) {
 }
 
 // compact the big fragments of the list whose length is counters[n_index] and prefix-sum their slot counts
-int scan_big(rr_ctx* c, int n_index, uint32_t cap) {
-    CU(cudaMemsetAsync(c->d_counters + CTR_SLOTS, 0, 3 * 4, c->stream));                   // CTR_SLOTS, CTR_SCAN_TICKET, CTR_NBIG
-    CU(cudaMemsetAsync(c->d_scan_lookback, 0, (size_t)c->scan_tiles * 8, c->stream));
-    k_scan_big<<<grid_for(c, 2), SCAN_THREADS, 0, c->stream>>>(c->d_fragcnt, c->d_counters + n_index, cap, c->d_biglist, c->d_bigslot, c->d_counters,
-                                                                 c->d_scan_lookback);
+int scan_big(rr_ctx* c, cudaStream_t st, uint32_t* counters, const uint32_t* fragcnt, uint32_t* biglist, uint32_t* bigslot,
+             unsigned long long* lookback, int n_index, uint32_t cap) {
+    CU(cudaMemsetAsync(counters + CTR_SLOTS, 0, 3 * 4, st));                               // CTR_SLOTS, CTR_SCAN_TICKET, CTR_NBIG
+    CU(cudaMemsetAsync(lookback, 0, (size_t)c->scan_tiles * 8, st));
+    k_scan_big<<<grid_for(c, 2), SCAN_THREADS, 0, st>>>(fragcnt, counters + n_index, cap, biglist, bigslot, counters, lookback);
     c->launches++;
     CU(cudaGetLastError());
     return RR_OK;
 }
 
 template <int MODE>
-int raster(rr_ctx* c, const RasterParams& rp) {
-    k_raster_small<MODE><<<grid_for(c, 8), 256, 0, c->stream>>>(rp);
-    k_raster_big<MODE><<<grid_for(c, 4), RASTER_THREADS, 0, c->stream>>>(rp);
+int raster(rr_ctx* c, cudaStream_t st, const RasterParams& rp) {
+    k_raster_small<MODE><<<grid_for(c, 8), 256, 0, st>>>(rp);
+    k_raster_big<MODE><<<grid_for(c, 4), RASTER_THREADS, 0, st>>>(rp);
     c->launches += 2;
     CU(cudaGetLastError());
     return RR_OK;
@@ -237,7 +245,20 @@ rr_ctx* rr_create(const rr_config* cfg) {
     c->scan_tiles = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS / RR_SFRAG_WORDS + SCAN_TILE - 1) / SCAN_TILE) + 1;
     if (cudaMalloc((void**)&c->d_scan_lookback, (size_t)c->scan_tiles * 8) != cudaSuccess) return bail("scan descriptors");
     if (cudaMalloc((void**)&c->d_counters, CTR_COUNT * 4) != cudaSuccess) return bail("counters");
-    if (cudaMallocHost((void**)&c->h_counters, CTR_COUNT * 4) != cudaSuccess) return bail("pinned counters");
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail("stream2");
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    if (cudaEventCreateWithFlags(&c->ev_shadow_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    {
+        const size_t srec = (size_t)c->cap_frags * RR_FRAG_WORDS / RR_SFRAG_WORDS;     // shadow records are 4 words
+        if (cudaMalloc((void**)&c->d_sfrags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("shadow fragment buffer");
+        if (cudaMalloc((void**)&c->d_sfragcnt, srec * 4 + 16) != cudaSuccess) return bail("shadow slot counts");
+        if (cudaMalloc((void**)&c->d_sbiglist, srec * 4 + 16) != cudaSuccess) return bail("shadow big list");
+        if (cudaMalloc((void**)&c->d_sbigslot, srec * 4 + 16) != cudaSuccess) return bail("shadow big slots");
+        if (cudaMalloc((void**)&c->d_sscan_lookback, (size_t)c->scan_tiles * 8) != cudaSuccess) return bail("shadow scan descriptors");
+        if (cudaMalloc((void**)&c->d_scounters, CTR_COUNT * 4) != cudaSuccess) return bail("shadow counters");
+        cudaMemsetAsync(c->d_scounters, 0, CTR_COUNT * 4, c->stream);
+    }
+    if (cudaMallocHost((void**)&c->h_counters, 2 * CTR_COUNT * 4) != cudaSuccess) return bail("pinned counters");
     cudaMemsetAsync(c->d_counters, 0, CTR_COUNT * 4, c->stream);
     // depth_buffer[0..1] start at UINT_MAX (object_context.cpp:43-52); the id image starts at 0
     for (int i = 0; i < 2; i++) {
@@ -253,6 +274,12 @@ rr_ctx* rr_create(const rr_config* cfg) {
 void rr_destroy(rr_ctx* c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    cudaFree(c->d_sfrags); cudaFree(c->d_sfragcnt); cudaFree(c->d_sbiglist); cudaFree(c->d_sbigslot); cudaFree(c->d_scounters);
+    cudaFree(c->d_scutdown); cudaFree(c->d_sscan_lookback);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_shadow_done) cudaEventDestroy(c->ev_shadow_done);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite);
     cudaFree(c->d_atlas); cudaFree(c->d_nums); cudaFree(c->d_sizes); cudaFree(c->d_upload);
     cudaFree(c->d_lights); cudaFree(c->d_lightlite);
@@ -286,6 +313,8 @@ int rr_scene_alloc(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
     // case (the reference allocates 12T, object_context.cpp:354). Default 6T + slack ; overflow is detected and reported.
     c->cap_cut = c->cfg.max_cutdown ? c->cfg.max_cutdown : (uint32_t)std::min<uint64_t>((uint64_t)n_tris * 6 + 1024, 0x7FFFFFFFu);
     if ((r = dev_alloc(c->d_cutdown, (size_t)c->cap_cut * 3))) return r;
+    CU(cudaStreamSynchronize(c->stream2));
+    if ((r = dev_alloc(c->d_scutdown, (size_t)c->cap_cut * 3))) return r;
     c->lookback_blocks = (n_tris + SETUP_THREADS - 1) / SETUP_THREADS;
     if ((r = dev_alloc(c->d_lookback, (size_t)c->lookback_blocks))) return r;
     if (c->h_objs_pinned) { cudaFreeHost(c->h_objs_pinned); c->h_objs_pinned = nullptr; }
@@ -383,6 +412,7 @@ int rr_atlas_read_raw(rr_ctx* c, uint8_t* dst, size_t nbytes) {
 int rr_lights_write(rr_ctx* c, const rr_light* lights, uint32_t n_active) {
     if (!c || (!lights && n_active)) return fail(RR_ERR_INVALID, "null argument");
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream2));
     c->lights.assign(lights, lights + n_active);
     uint32_t ns = 0, nst = 0;
     for (uint32_t i = 0; i < n_active; i++) {
@@ -401,12 +431,12 @@ int rr_lights_write(rr_ctx* c, const rr_light* lights, uint32_t n_active) {
     if (!c->ext_shadow_dyn && (ns != c->n_shadow || !c->d_shadow_dyn)) {
         c->shadow_dyn_words = std::max<size_t>(slab * ns, 4);
         if ((r = dev_alloc(c->d_shadow_dyn, c->shadow_dyn_words))) return r;
-        if ((r = fill_u32(c, c->d_shadow_dyn, c->shadow_dyn_words, 0xFFFFFFFFu))) return r;
+        if ((r = fill_u32(c, c->stream, c->d_shadow_dyn, c->shadow_dyn_words, 0xFFFFFFFFu))) return r;
     }
     if (!c->ext_shadow_static && (nst != c->n_static || !c->d_shadow_static)) {
         c->shadow_static_words = std::max<size_t>(slab * nst, 4);
         if ((r = dev_alloc(c->d_shadow_static, c->shadow_static_words))) return r;
-        if ((r = fill_u32(c, c->d_shadow_static, c->shadow_static_words, 0xFFFFFFFFu))) return r;
+        if ((r = fill_u32(c, c->stream, c->d_shadow_static, c->shadow_static_words, 0xFFFFFFFFu))) return r;
     }
     if (c->ext_shadow_dyn && slab * ns > c->shadow_dyn_words) return fail(RR_ERR_INVALID, "bound dynamic shadow buffer too small");
     if (c->ext_shadow_static && slab * nst > c->shadow_static_words) return fail(RR_ERR_INVALID, "bound static shadow buffer too small");
@@ -440,7 +470,8 @@ static int shadow_pass(rr_ctx* c, int only_static) {
     int r;
     for (size_t first = 0; first < sel.size(); first += SHADOW_MAX_LIGHTS) {
         const int nl = (int)std::min<size_t>(SHADOW_MAX_LIGHTS, sel.size() - first);
-        CU(cudaMemsetAsync(c->d_counters + CTR_S_NFRAG, 0, 2 * 4, c->stream));
+        cudaStream_t st = c->stream2;
+        CU(cudaMemsetAsync(c->d_scounters + CTR_S_NFRAG, 0, 2 * 4, st));
         ShadowSetupParams sp;
         sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
         sp.n_lights = nl;
@@ -449,19 +480,19 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         sp.faces = c->faces;
         sp.L = (float)c->L; sp.icut = (float)c->cfg.depth_icutoff;
         sp.only_static = only_static;
-        sp.frags = c->d_frags; sp.cap_frags = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS) / RR_SFRAG_WORDS);
-        sp.fragcnt = c->d_fragcnt;
-        sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut; sp.counters = c->d_counters;
+        sp.frags = c->d_sfrags; sp.cap_frags = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS) / RR_SFRAG_WORDS);
+        sp.fragcnt = c->d_sfragcnt;
+        sp.cutdown = c->d_scutdown; sp.cap_cut = c->cap_cut; sp.counters = c->d_scounters;
         sp.buffer = buffer;
-        k_shadow_setup<<<(c->n_tris + 255) / 256, 256, 0, c->stream>>>(sp);
+        k_shadow_setup<<<(c->n_tris + 127) / 128, 128, 0, st>>>(sp);
         c->launches++;
-        if ((r = scan_big(c, CTR_S_NFRAG, sp.cap_frags))) return r;
-        dp.frags = c->d_frags; dp.cutdown = c->d_cutdown; dp.fragcnt = c->d_fragcnt; dp.counters = c->d_counters; dp.cap_frags = sp.cap_frags;
-        dp.biglist = c->d_biglist; dp.bigslot = c->d_bigslot;
+        if ((r = scan_big(c, st, c->d_scounters, c->d_sfragcnt, c->d_sbiglist, c->d_sbigslot, c->d_sscan_lookback, CTR_S_NFRAG, sp.cap_frags))) return r;
+        dp.frags = c->d_sfrags; dp.cutdown = c->d_scutdown; dp.fragcnt = c->d_sfragcnt; dp.counters = c->d_scounters; dp.cap_frags = sp.cap_frags;
+        dp.biglist = c->d_sbiglist; dp.bigslot = c->d_sbigslot;
         dp.n_index = CTR_S_NFRAG;
         dp.depth = buffer; dp.ids = nullptr; dp.width = (float)c->L; dp.height = (float)c->L; dp.W = c->L;
         dp.row_lo = 0; dp.row_hi = c->L;
-        if ((r = raster<RM_SHADOW>(c, dp))) return r;
+        if ((r = raster<RM_SHADOW>(c, st, dp))) return r;
     }
     CU(cudaGetLastError());
     return RR_OK;
@@ -471,17 +502,38 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     if (!c) return fail(RR_ERR_INVALID, "null ctx");
     int r;
     if ((r = ensure_objlite(c))) return r;
-    CU(cudaEventRecord(c->ev[EV_SH0], c->stream));
+    // fork: the shadow work is ordered after everything already enqueued on the main stream (previous frame's shading
+    // reads the cubemaps, uploads, k_objlite) and then runs on its own stream, concurrently with rr_frame_draw's
+    // setup / depth / id kernels; rr_frame_draw joins right before shading
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    CU(cudaEventRecord(c->ev[EV_SH0], c->stream2));
     const size_t slab = (size_t)6 * c->L * c->L;
     if (!c->lights.empty()) {                                                              // engine.cpp:1611-1626
         // a full clear (not only the owned faces) keeps the buffer defined for the all-gather that follows
-        if (c->n_shadow && (r = fill_u32(c, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
-        if (static_lights_dirty && c->n_static && (r = fill_u32(c, c->d_shadow_static, slab * c->n_static, 0xFFFFFFFFu))) return r;
+        if (c->n_shadow && (r = fill_u32(c, c->stream2, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
+        if (static_lights_dirty && c->n_static && (r = fill_u32(c, c->stream2, c->d_shadow_static, slab * c->n_static, 0xFFFFFFFFu))) return r;
     }
     if (c->n_shadow && (r = shadow_pass(c, 0))) return r;                                  // engine.cpp:1629-1697
     if (static_lights_dirty && c->n_static && (r = shadow_pass(c, 1))) return r;           // engine.cpp:1699-1784
-    CU(cudaEventRecord(c->ev[EV_SH1], c->stream));
+    CU(cudaEventRecord(c->ev[EV_SH1], c->stream2));
+    CU(cudaEventRecord(c->ev_shadow_done, c->stream2));
     c->have_shadow_ev = true;
+    if (c->cfg.face_world > 1) {
+        // faces are exchanged by the caller on the main stream right after this call: join now
+        CU(cudaStreamWaitEvent(c->stream, c->ev_shadow_done, 0));
+        c->shadow_pending = false;
+    } else {
+        c->shadow_pending = true;
+    }
+    return RR_OK;
+}
+
+static int join_shadows(rr_ctx* c) {
+    if (c->shadow_pending) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_shadow_done, 0));
+        c->shadow_pending = false;
+    }
     return RR_OK;
 }
 
@@ -509,7 +561,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     k_setup_main<<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
     // kernel1 / kernel2
-    if ((r = scan_big(c, CTR_NFRAG, c->cap_frags))) return r;
+    if ((r = scan_big(c, c->stream, c->d_counters, c->d_fragcnt, c->d_biglist, c->d_bigslot, c->d_scan_lookback, CTR_NFRAG, c->cap_frags))) return r;
     RasterParams rp;
     rp.frags = c->d_frags; rp.cutdown = c->d_cutdown; rp.fragcnt = c->d_fragcnt; rp.counters = c->d_counters; rp.cap_frags = c->cap_frags;
     rp.biglist = c->d_biglist; rp.bigslot = c->d_bigslot;
@@ -517,10 +569,10 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     rp.depth = c->d_depth[c->cur]; rp.ids = c->d_ids[c->cur];
     rp.width = (float)c->W; rp.height = (float)c->H; rp.W = c->W;
     rp.row_lo = row0; rp.row_hi = row1;
-    if ((r = raster<RM_DEPTH>(c, rp))) return r;
+    if ((r = raster<RM_DEPTH>(c, c->stream, rp))) return r;
     CU(cudaEventRecord(c->ev[EV_DEPTH], c->stream));
     rp.row_lo = band0; rp.row_hi = band1;
-    if ((r = raster<RM_IDS>(c, rp))) return r;
+    if ((r = raster<RM_IDS>(c, c->stream, rp))) return r;
     CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
     // kernel3
     ShadeParams hp;
@@ -545,6 +597,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     CU(cudaMemsetAsync(c->d_counters + CTR_NSHADE, 0, 4, c->stream));
     dim3 grid((c->W + 31) / 32, (row1 - row0 + 7) / 8);
     k_shade_pre<<<grid, 256, 0, c->stream>>>(hp);
+    if ((r = join_shadows(c))) return r;                                                   // the cubemaps must be complete before shading
     k_shade<<<grid_for(c, 12), 128, 0, c->stream>>>(hp);
     CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
     c->launches += 3;
@@ -561,10 +614,15 @@ int rr_swap_buffers(rr_ctx* c) {
 
 int rr_sync(rr_ctx* c) {
     if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    int r;
+    if ((r = join_shadows(c))) return r;
     CU(cudaMemcpyAsync(c->h_counters, c->d_counters, CTR_COUNT * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_counters + CTR_COUNT, c->d_scounters, CTR_COUNT * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->h_counters[CTR_OVERFLOW])
-        return fail(RR_ERR_OVERFLOW, "raster storage exhausted (flags %u): fragments cap %u, projected-triangle cap %u", c->h_counters[CTR_OVERFLOW], c->cap_frags, c->cap_cut);
+    CU(cudaStreamSynchronize(c->stream2));
+    const uint32_t ovf = c->h_counters[CTR_OVERFLOW] | c->h_counters[CTR_COUNT + CTR_OVERFLOW];
+    if (ovf)
+        return fail(RR_ERR_OVERFLOW, "raster storage exhausted (flags %u): fragments cap %u, projected-triangle cap %u", ovf, c->cap_frags, c->cap_cut);
     return RR_OK;
 }
 
@@ -583,6 +641,7 @@ int rr_read_shadow(rr_ctx* c, int is_static, uint32_t slab_idx, uint32_t* dst) {
     if (!c) return fail(RR_ERR_INVALID, "null ctx");
     const size_t slab = (size_t)6 * c->L * c->L;
     if (slab_idx >= (is_static ? c->n_static : c->n_shadow)) return fail(RR_ERR_INVALID, "rr_read_shadow: slab %u out of range", slab_idx);
+    { int jr = join_shadows(c); if (jr) return jr; }
     return read_back(c, dst, (is_static ? c->d_shadow_static : c->d_shadow_dyn) + slab * slab_idx, slab * 4);
 }
 int rr_read_fragments(rr_ctx* c, uint32_t* dst, uint32_t max_records, uint32_t* n_records) {
@@ -621,8 +680,8 @@ int rr_get_timings(rr_ctx* c, rr_timings* t) {
     }
     t->n_cutdown = c->h_counters[CTR_NCUT];
     t->n_fragments = c->h_counters[CTR_NFRAG];
-    t->n_shadow_fragments = c->h_counters[CTR_S_NFRAG];    // of the last shadow pass
-    t->overflow = c->h_counters[CTR_OVERFLOW];
+    t->n_shadow_fragments = c->h_counters[CTR_COUNT + CTR_S_NFRAG];    // stored (non-inlined) fragments of the last shadow pass
+    t->overflow = c->h_counters[CTR_OVERFLOW] | c->h_counters[CTR_COUNT + CTR_OVERFLOW];
     t->launches = c->launches;
     return RR_OK;
 }
@@ -631,6 +690,7 @@ int rr_get_timings(rr_ctx* c, rr_timings* t) {
 int rr_bind_external(rr_ctx* c, int which, void* p, size_t nbytes) {
     if (!c || !p) return fail(RR_ERR_INVALID, "null argument");
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream2));
     const size_t P = (size_t)c->W * c->H;
     switch (which) {
         case RR_BUF_RGBA8:

@@ -694,8 +694,8 @@ __device__ __forceinline__ void warp_alloc2(uint32_t* counters, uint32_t nc, uin
     fbase = (uint32_t)(base & 0xFFFFFFFFull);
 }
 
-__global__ void __launch_bounds__(256) k_shadow_setup(const ShadowSetupParams P) {
-    __shared__ InlineQueue s_iq[256 / 32];
+__global__ void __launch_bounds__(128) k_shadow_setup(const ShadowSetupParams P) {
+    __shared__ InlineQueue s_iq[128 / 32];
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = tri < P.n_tris;
     float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0, gpos = w0;
