@@ -214,8 +214,9 @@ def run_ours(args):
         cfg = rrd.band_config(cfg, world, rank, args.halo)
     r = Renderer(cfg)
     # colour target and cubemap slab live in torch tensors so torch.distributed (NCCL) can move them
-    fb = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
-    r.bind_external(RR_BUF_RGBA8, fb.data_ptr(), fb.numel())
+    fb = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
+    if world > 1:
+        r.bind_external(RR_BUF_RGBA8, fb.data_ptr(), fb.numel())
     chunk = rrd.face_chunk(n_shadow, world)
     shadow = torch.full((chunk * world * L * L,), -1, dtype=torch.int32, device=dev)
     r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
@@ -276,12 +277,13 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers: H2D of the per-frame inputs (object descriptors from
     # pinned memory, as object_context::flush_locations does) and D2H of the finished frame, inside the timed region
     host_fb = rr.host_alloc((H, W, 4), np.uint8) if rank == 0 else None
+    host_fb2 = rr.host_alloc((H, W, 4), np.uint8) if (rank == 0 and world == 1) else None
     pinned_t = torch.from_numpy(host_fb) if rank == 0 else None
 
     def frame_e2e(i):
         c_pos, c_rot = camera(s, i)
         if world == 1:
-            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_fb)        # swaps buffers itself
+            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_fb if i % 2 == 0 else host_fb2)   # pipelined read-back; swaps buffers itself
         else:
             r.scene_write_objs(s.objs)
             frame(i)

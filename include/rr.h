@@ -167,7 +167,10 @@ void* rr_stream(rr_ctx*);                                                       
 void* rr_host_alloc(size_t nbytes);            /* page-locked host memory for read-backs (CL_MEM_ALLOC_HOST_PTR role; async_read.hpp:30-60 host buffers) */
 void  rr_host_free(void* p);
 
-/* ---- host-to-host frame for e2e timing: upload camera, draw, read RGBA8 back into pinned host memory ------------ */
+/* ---- host-to-host frame: upload the per-frame inputs (object descriptors), draw, read RGBA8 back ------------------
+ * Pipelined like the reference's read-back ring (async_read.hpp:30-144): the call returns once the PREVIOUS call's
+ * host buffer is complete; this call's buffer is complete after the next rr_frame_e2e or rr_sync. Alternate between
+ * two host buffers (page-locked ones from rr_host_alloc make the copy a direct DMA). Swaps buffers itself. */
 int rr_frame_e2e(rr_ctx*, const float c_pos[4], const float c_rot[4], const float clear_rgba[4],
                  int with_shadows, uint8_t* host_rgba8);
 

@@ -88,8 +88,13 @@ struct rr_ctx {
     uint32_t* d_depth[2] = {nullptr, nullptr};
     uint32_t* d_ids[2] = {nullptr, nullptr};
     int cur = 0;
-    uchar4* d_rgba8 = nullptr;
+    uchar4* d_rgba8 = nullptr;          // colour target of the frame being / last drawn
+    uchar4* d_rgba8_alt = nullptr;      // second target for pipelined read-back (rr_frame_e2e), like async_read.hpp's host ring
     bool ext_rgba8 = false;
+    cudaStream_t stream3 = nullptr;     // copy stream
+    cudaEvent_t ev_draw_done = nullptr, ev_copy_done[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    int fb_parity = 0;
     ushort2* d_normals = nullptr;
     uint32_t* d_shade_list = nullptr;            // compacted covered pixels
     // raster storage
@@ -246,6 +251,9 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaMalloc((void**)&c->d_scan_lookback, (size_t)c->scan_tiles * 8) != cudaSuccess) return bail("scan descriptors");
     if (cudaMalloc((void**)&c->d_counters, CTR_COUNT * 4) != cudaSuccess) return bail("counters");
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail("stream2");
+    if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail("stream3");
+    if (cudaEventCreateWithFlags(&c->ev_draw_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (cudaEventCreateWithFlags(&c->ev_shadow_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     {
@@ -275,6 +283,11 @@ void rr_destroy(rr_ctx* c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
+    if (c->stream3) cudaStreamSynchronize(c->stream3);
+    if (c->d_rgba8_alt) cudaFree(c->d_rgba8_alt);
+    if (c->ev_draw_done) cudaEventDestroy(c->ev_draw_done);
+    for (int i = 0; i < 2; i++) if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
+    if (c->stream3) cudaStreamDestroy(c->stream3);
     cudaFree(c->d_sfrags); cudaFree(c->d_sfragcnt); cudaFree(c->d_sbiglist); cudaFree(c->d_sbigslot); cudaFree(c->d_scounters);
     cudaFree(c->d_scutdown); cudaFree(c->d_sscan_lookback);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -620,6 +633,8 @@ int rr_sync(rr_ctx* c) {
     CU(cudaMemcpyAsync(c->h_counters + CTR_COUNT, c->d_scounters, CTR_COUNT * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->stream2));
+    CU(cudaStreamSynchronize(c->stream3));
+    c->copy_pending[0] = c->copy_pending[1] = false;
     const uint32_t ovf = c->h_counters[CTR_OVERFLOW] | c->h_counters[CTR_COUNT + CTR_OVERFLOW];
     if (ovf)
         return fail(RR_ERR_OVERFLOW, "raster storage exhausted (flags %u): fragments cap %u, projected-triangle cap %u", ovf, c->cap_frags, c->cap_cut);
@@ -735,13 +750,33 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
         CU(cudaMemcpyAsync(c->d_objs, c->h_objs_pinned, (size_t)c->n_objs * sizeof(rr_obj_desc), cudaMemcpyHostToDevice, c->stream));
         c->objlite_dirty = true;
     }
+    // Pipelined read-back (the reference keeps a ring of host buffers for the same reason, async_read.hpp:30-144): this
+    // frame is drawn into one of two colour targets while the copy stream is still moving the previous frame out of the
+    // other. On return the PREVIOUS call's host buffer is complete; rr_sync() completes this one.
+    const int k = c->fb_parity;
+    if (!c->ext_rgba8) {
+        if (!c->d_rgba8_alt) CU(cudaMalloc((void**)&c->d_rgba8_alt, (size_t)c->W * c->H * 4));
+        std::swap(c->d_rgba8, c->d_rgba8_alt);
+        if (c->copy_pending[k]) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy_done[k], 0)); }   // target k is free again
+    }
     if (with_shadows && (r = rr_frame_shadows(c, 0))) return r;
     if ((r = rr_frame_draw(c, c_pos, c_rot, clear_rgba))) return r;
     int band0, band1, row0, row1;
     band_rows(c, band0, band1, row0, row1);
     const size_t off = (size_t)band0 * c->W * 4, len = (size_t)(band1 - band0) * c->W * 4;
-    CU(cudaMemcpyAsync(host_rgba8 + off, (uint8_t*)c->d_rgba8 + off, len, cudaMemcpyDeviceToHost, c->stream));   // direct DMA when host_rgba8 is pinned (rr_host_alloc)
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(c->ev_draw_done, c->stream));
+    CU(cudaStreamWaitEvent(c->stream3, c->ev_draw_done, 0));
+    CU(cudaMemcpyAsync(host_rgba8 + off, (uint8_t*)c->d_rgba8 + off, len, cudaMemcpyDeviceToHost, c->stream3));   // direct DMA when host_rgba8 is pinned (rr_host_alloc)
+    CU(cudaEventRecord(c->ev_copy_done[k], c->stream3));
+    c->copy_pending[k] = true;
+    if (c->ext_rgba8) {                                   // one caller-owned target: no pipelining possible
+        CU(cudaEventSynchronize(c->ev_copy_done[k]));
+        c->copy_pending[k] = false;
+    } else if (c->copy_pending[k ^ 1]) {                  // at most one frame in flight
+        CU(cudaEventSynchronize(c->ev_copy_done[k ^ 1]));
+        c->copy_pending[k ^ 1] = false;
+    }
+    c->fb_parity ^= 1;
     if ((r = rr_swap_buffers(c))) return r;
     return RR_OK;
 }
