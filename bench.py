@@ -222,13 +222,15 @@ def run_ours(args):
     r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
     s.upload(r)
     stream = torch.cuda.ExternalStream(r.stream(), device=dev)
+    sh_stream = torch.cuda.ExternalStream(r.shadow_stream(), device=dev)
 
     def frame(i):
         c_pos, c_rot = camera(s, i)
         r.frame_shadows(0)
         if world > 1:
-            with torch.cuda.stream(stream):
+            with torch.cuda.stream(sh_stream):                                   # on the shadow stream: overlaps the main view's setup/depth/ids
                 rrd.all_gather_faces(shadow, chunk * L * L, rank)                # faces rendered elsewhere arrive in place
+            r.shadows_done()
         r.frame_draw(c_pos, c_rot, s.clear)
         if world > 1:
             with torch.cuda.stream(stream):

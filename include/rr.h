@@ -163,6 +163,9 @@ int rr_get_timings(rr_ctx*, rr_timings* out);
 int   rr_bind_external(rr_ctx*, int which /*enum rr_buffer*/, void* device_ptr, size_t nbytes); /* render straight into caller-owned (e.g. torch / peer-mapped) memory */
 void* rr_device_ptr(rr_ctx*, int which /*enum rr_buffer*/);
 void* rr_stream(rr_ctx*);                                                                       /* cudaStream_t the context launches on */
+void* rr_shadow_stream(rr_ctx*);   /* cudaStream_t of the shadow passes: rr_frame_shadows runs there, concurrently with rr_frame_draw's
+                                      setup/depth/id kernels; rr_frame_draw waits for it right before shading */
+int   rr_shadows_done(rr_ctx*);    /* call after enqueueing extra work on the shadow stream (the cubemap-face all-gather): shading waits for it too */
 
 void* rr_host_alloc(size_t nbytes);            /* page-locked host memory for read-backs (CL_MEM_ALLOC_HOST_PTR role; async_read.hpp:30-60 host buffers) */
 void  rr_host_free(void* p);

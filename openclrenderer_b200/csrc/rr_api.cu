@@ -532,13 +532,7 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     CU(cudaEventRecord(c->ev[EV_SH1], c->stream2));
     CU(cudaEventRecord(c->ev_shadow_done, c->stream2));
     c->have_shadow_ev = true;
-    if (c->cfg.face_world > 1) {
-        // faces are exchanged by the caller on the main stream right after this call: join now
-        CU(cudaStreamWaitEvent(c->stream, c->ev_shadow_done, 0));
-        c->shadow_pending = false;
-    } else {
-        c->shadow_pending = true;
-    }
+    c->shadow_pending = true;
     return RR_OK;
 }
 
@@ -733,6 +727,13 @@ void* rr_device_ptr(rr_ctx* c, int which) {
     }
 }
 void* rr_stream(rr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+void* rr_shadow_stream(rr_ctx* c) { return c ? (void*)c->stream2 : nullptr; }
+int rr_shadows_done(rr_ctx* c) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    CU(cudaEventRecord(c->ev_shadow_done, c->stream2));      // everything enqueued on the shadow stream so far (e.g. the face all-gather)
+    c->shadow_pending = true;
+    return RR_OK;
+}
 
 void* rr_host_alloc(size_t nbytes) {
     void* p = nullptr;

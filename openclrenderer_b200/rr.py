@@ -33,6 +33,10 @@ def load_library():
         _LIB.rr_device_ptr.argtypes = [_P, C.c_int]
         _LIB.rr_stream.restype = _P
         _LIB.rr_stream.argtypes = [_P]
+        _LIB.rr_shadow_stream.restype = _P
+        _LIB.rr_shadow_stream.argtypes = [_P]
+        _LIB.rr_shadows_done.restype = C.c_int
+        _LIB.rr_shadows_done.argtypes = [_P]
         _LIB.rr_frame_e2e.restype = C.c_int
         _LIB.rr_frame_e2e.argtypes = [_P, _F4, _F4, _F4, C.c_int, _P]
         _LIB.rr_host_alloc.restype = _P
@@ -81,6 +85,14 @@ class Renderer(CApi):
 
     def stream(self):
         return self._lib.rr_stream(self._ctx)
+
+    def shadow_stream(self):
+        return self._lib.rr_shadow_stream(self._ctx)
+
+    def shadows_done(self):
+        r = self._lib.rr_shadows_done(self._ctx)
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
 
     def frame_e2e(self, c_pos, c_rot, clear, with_shadows, host_rgba8):
         def f4(v):
