@@ -97,6 +97,9 @@ struct rr_ctx {
     int fb_parity = 0;
     ushort2* d_normals = nullptr;
     uint32_t* d_shade_list = nullptr;            // compacted covered pixels
+    uint2* d_samples = nullptr;                  // covered samples of inline-rasterised triangles (pixel, depth)
+    uint4* d_sample_desc = nullptr;              // {first sample, count, fragment index}
+    uint32_t cap_samples = 0;
     // raster storage
     uint32_t* d_frags = nullptr;
     uint32_t cap_frags = 0;
@@ -242,8 +245,11 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaMalloc((void**)&c->d_rgba8, P * 4) != cudaSuccess) return bail("rgba8");
     if (cudaMalloc((void**)&c->d_normals, P * 4) != cudaSuccess) return bail("normals");
     if (cudaMalloc((void**)&c->d_shade_list, P * 4) != cudaSuccess) return bail("shade list");
+    c->cap_samples = (uint32_t)std::min<size_t>(4 * P + (1u << 20), 0x7FFFFFFFu);
+    if (cudaMalloc((void**)&c->d_samples, (size_t)c->cap_samples * 8) != cudaSuccess) return bail("sample list");
     c->cap_frags = cfg->max_fragments ? cfg->max_fragments : (16u << 20);
     if (cudaMalloc((void**)&c->d_frags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("fragment buffer");
+    if (cudaMalloc((void**)&c->d_sample_desc, (size_t)c->cap_frags * 16) != cudaSuccess) return bail("sample descriptors");
     if (cudaMalloc((void**)&c->d_fragcnt, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("slot counts");
     if (cudaMalloc((void**)&c->d_biglist, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("big list");
     if (cudaMalloc((void**)&c->d_bigslot, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("big slots");
@@ -301,7 +307,7 @@ void rr_destroy(rr_ctx* c) {
     for (int i = 0; i < 2; i++) { cudaFree(c->d_depth[i]); cudaFree(c->d_ids[i]); }
     if (!c->ext_rgba8) cudaFree(c->d_rgba8);
     cudaFree(c->d_fragcnt); cudaFree(c->d_scan_lookback); cudaFree(c->d_biglist); cudaFree(c->d_bigslot);
-    cudaFree(c->d_normals); cudaFree(c->d_shade_list); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
+    cudaFree(c->d_normals); cudaFree(c->d_shade_list); cudaFree(c->d_samples); cudaFree(c->d_sample_desc); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
     for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -558,6 +564,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     CU(cudaEventRecord(c->ev[EV_F0], c->stream));
     // prearrange
     CU(cudaMemsetAsync(c->d_counters, 0, 4 * 4, c->stream));                               // n_cut, n_frag, overflow, ticket
+    CU(cudaMemsetAsync(c->d_counters + CTR_NSAMPLES, 0, 2 * 4, c->stream));                // sample list
     CU(cudaMemsetAsync(c->d_lookback, 0, (size_t)c->lookback_blocks * 8, c->stream));
     SetupMainParams sp;
     sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
@@ -565,6 +572,8 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     sp.frags = c->d_frags; sp.cap_frags = c->cap_frags; sp.fragcnt = c->d_fragcnt; sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut;
     sp.counters = c->d_counters; sp.lookback = c->d_lookback;
     sp.depth = c->d_depth[c->cur]; sp.row_lo = row0; sp.row_hi = row1;
+    sp.sl.samples = c->d_samples; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
+    sp.sl.desc = c->d_sample_desc; sp.sl.cap_desc = c->cap_frags; sp.sl.desc_count = c->d_counters + CTR_NDESC; sp.sl.fragcnt = c->d_fragcnt;
     k_setup_main<<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
     // kernel1 / kernel2
@@ -579,6 +588,8 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     if ((r = raster<RM_DEPTH>(c, c->stream, rp))) return r;
     CU(cudaEventRecord(c->ev[EV_DEPTH], c->stream));
     rp.row_lo = band0; rp.row_hi = band1;
+    k_ids_list<<<grid_for(c, 8), 256, 0, c->stream>>>(sp.sl, c->d_depth[c->cur], c->d_ids[c->cur], c->W, band0, band1);
+    c->launches++;
     if ((r = raster<RM_IDS>(c, c->stream, rp))) return r;
     CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
     // kernel3
@@ -602,8 +613,13 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     if (hp.n_lights > 0 && (!c->d_lights)) return fail(RR_ERR_INVALID, "lights not written");
     hp.shade_list = c->d_shade_list; hp.shade_count = c->d_counters + CTR_NSHADE;
     CU(cudaMemsetAsync(c->d_counters + CTR_NSHADE, 0, 4, c->stream));
-    dim3 grid((c->W + 31) / 32, (row1 - row0 + 7) / 8);
-    k_shade_pre<<<grid, 256, 0, c->stream>>>(hp);
+    if (c->W % 4 == 0) {
+        dim3 grid4((c->W + 127) / 128, (row1 - row0 + 7) / 8);
+        k_shade_pre4<<<grid4, 256, 0, c->stream>>>(hp);
+    } else {
+        dim3 grid((c->W + 31) / 32, (row1 - row0 + 7) / 8);
+        k_shade_pre<<<grid, 256, 0, c->stream>>>(hp);
+    }
     if ((r = join_shadows(c))) return r;                                                   // the cubemaps must be complete before shading
     k_shade<<<grid_for(c, 12), 128, 0, c->stream>>>(hp);
     CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));

@@ -19,7 +19,9 @@ enum {
     CTR_SCAN_TICKET = 8,
     CTR_NBIG = 9,      // number of big fragments (more than RASTER_SMALL_MAX slots) in the list last scanned
     CTR_NSHADE = 10,   // covered pixels in the shading list
-    CTR_COUNT = 12
+    CTR_NSAMPLES = 11, // entries reserved in the sample list (inline-rasterised triangles)
+    CTR_NDESC = 12,    // descriptors in the sample list
+    CTR_COUNT = 16
 };
 
 struct CamParams {
@@ -127,40 +129,92 @@ __device__ __forceinline__ void subtri_clear(SubTri& s) { s.keep = false; s.n_fr
 // projected-triangle buffers and no second kernel. `target` is the depth buffer (or cubemap face) it lands in.
 #define RASTER_SMALL_MAX 48
 #define FRAGCNT_DEPTH_DONE 0x80000000u      // flag in the per-fragment slot count: depth already written inline
+#define FRAGCNT_IDS_LISTED 0x40000000u      // ... and its covered samples are in the sample list (k_ids_list resolves its ids)
+#define FRAGCNT_MASK 0x3FFFFFFFu
 
 __device__ __forceinline__ bool inline_candidate(const SubTri& s) { return s.keep && s.n_frag == 1 && s.box <= RASTER_SMALL_MAX; }
-
-__device__ __forceinline__ void raster_inline(float3 p0, float3 p1, float3 p2, float rconst, int op, float width, float height,
-                                              uint32_t* __restrict__ target, int row_lo, int row_hi) {
-    const FragGeom g = frag_geom(p0, p1, p2, rconst, width, height);
-    scan_chunk(g.mm, op, 0u, [&](float x, float y) {
-        if ((int)y < row_lo || (int)y >= row_hi) return;
-        if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
-            const float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
-            atomicMin(target + ((int)(y * width) + (int)x), sat_u32(RR_U32MAXF / fd));
-        }
-    });
-}
 
 // Per-warp queue in shared memory that compacts the small triangles of a warp (warp ballot + prefix) so that the walk is
 // always executed by 32 busy lanes: roughly half of a warp's triangles are culled and the survivors need different
 // numbers of steps, so rasterising them in place would leave most lanes idle.
+// REC (main view only): the covered samples (pixel, depth) of every triangle are appended to a sample list with one
+// descriptor {first sample, count, fragment index} per triangle, so that kernel2's work for these triangles is a
+// stream over that list (k_ids_list) instead of a second walk. Space is reserved per drain with one warp-aggregated
+// atomicAdd (box-many entries per triangle); if the list is full the triangle is simply left to the re-walk path.
 #define IQ_SLOTS 64
-#define IQ_FIELDS 11            // p0.xyz p1.xyz p2.xyz rconst target-index
+#define IQ_FIELDS 12            // p0.xyz p1.xyz p2.xyz rconst target-index fragment-index
 struct InlineQueue { float f[IQ_FIELDS][IQ_SLOTS]; };
 
+struct SampleList { uint2* samples; uint32_t cap; uint32_t* count; uint4* desc; uint32_t cap_desc; uint32_t* desc_count; uint32_t* fragcnt; };
+
+template <bool REC>
 struct InlineRaster {
     InlineQueue* q; int count;  // count is warp-uniform
     int op; float width, height; uint32_t* base; size_t face_stride; int row_lo, row_hi;
+    SampleList sl;
 
-    __device__ __forceinline__ void run(int slot) const {
-        const float* f = &q->f[0][slot];
-        raster_inline(make_float3(f[0], f[IQ_SLOTS], f[2 * IQ_SLOTS]), make_float3(f[3 * IQ_SLOTS], f[4 * IQ_SLOTS], f[5 * IQ_SLOTS]),
-                      make_float3(f[6 * IQ_SLOTS], f[7 * IQ_SLOTS], f[8 * IQ_SLOTS]), f[9 * IQ_SLOTS], op, width, height,
-                      base + (size_t)__float_as_uint(f[10 * IQ_SLOTS]) * face_stride, row_lo, row_hi);
+    // executed by all 32 lanes; lanes with !valid only take part in the warp collectives
+    __device__ __forceinline__ void run(int slot, bool valid) const {
+        const int lane = threadIdx.x & 31;
+        const float* f = &q->f[0][valid ? slot : 0];
+        FragGeom g;
+        uint32_t* target = base;
+        uint32_t fidx = 0;
+        int need = 0;
+        if (valid) {
+            g = frag_geom(make_float3(f[0], f[IQ_SLOTS], f[2 * IQ_SLOTS]), make_float3(f[3 * IQ_SLOTS], f[4 * IQ_SLOTS], f[5 * IQ_SLOTS]),
+                          make_float3(f[6 * IQ_SLOTS], f[7 * IQ_SLOTS], f[8 * IQ_SLOTS]), f[9 * IQ_SLOTS], width, height);
+            target = base + (size_t)__float_as_uint(f[10 * IQ_SLOTS]) * face_stride;
+            fidx = __float_as_uint(f[11 * IQ_SLOTS]);
+            need = (int)((g.mm.y - g.mm.x) * (g.mm.w - g.mm.z));
+        }
+        uint32_t first = 0;
+        bool rec = false;
+        if (REC) {              // reserve `need` sample entries per lane with one atomic per warp
+            int inc = need;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            uint32_t b0 = 0;
+            if (lane == 31 && total) b0 = atomicAdd(sl.count, (uint32_t)total);
+            b0 = __shfl_sync(0xffffffffu, b0, 31);
+            first = b0 + (uint32_t)(inc - need);
+            rec = valid && ((unsigned long long)b0 + (unsigned long long)total <= (unsigned long long)sl.cap);
+        }
+        uint32_t n = 0;
+        if (valid) {
+            const float w = width;
+            const int rlo = row_lo, rhi = row_hi;
+            scan_chunk(g.mm, op, 0u, [&](float x, float y) {
+                if ((int)y < rlo || (int)y >= rhi) return;
+                if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
+                    const float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
+                    const uint32_t d = sat_u32(RR_U32MAXF / fd);
+                    const uint32_t px = (uint32_t)((int)(y * w) + (int)x);
+                    atomicMin(target + px, d);
+                    if (REC && rec) sl.samples[first + n++] = make_uint2(px, d);
+                }
+            });
+        }
+        if (REC) {              // one descriptor per recorded triangle
+            const unsigned m = __ballot_sync(0xffffffffu, rec);
+            if (m) {
+                uint32_t d0 = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) d0 = atomicAdd(sl.desc_count, (uint32_t)__popc(m));
+                d0 = __shfl_sync(0xffffffffu, d0, leader);
+                if (rec) {
+                    const uint32_t at = d0 + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    if (at < sl.cap_desc) {
+                        sl.desc[at] = make_uint4(first, n, fidx, 0u);
+                        sl.fragcnt[fidx] |= FRAGCNT_IDS_LISTED;      // only this lane touches fragcnt[fidx] now (the block synchronised after the record phase)
+                    }
+                }
+            }
+        }
     }
     // called by all 32 lanes
-    __device__ __forceinline__ void push(bool has, const SubTri& s, uint32_t target_index) {
+    __device__ __forceinline__ void push(bool has, const SubTri& s, uint32_t target_index, uint32_t fidx) {
         const int lane = threadIdx.x & 31;
         const unsigned m = __ballot_sync(0xffffffffu, has);
         if (!m) return;
@@ -170,20 +224,20 @@ struct InlineRaster {
             f[0] = s.p0.x; f[IQ_SLOTS] = s.p0.y; f[2 * IQ_SLOTS] = s.p0.z;
             f[3 * IQ_SLOTS] = s.p1.x; f[4 * IQ_SLOTS] = s.p1.y; f[5 * IQ_SLOTS] = s.p1.z;
             f[6 * IQ_SLOTS] = s.p2.x; f[7 * IQ_SLOTS] = s.p2.y; f[8 * IQ_SLOTS] = s.p2.z;
-            f[9 * IQ_SLOTS] = s.rconst; f[10 * IQ_SLOTS] = __uint_as_float(target_index);
+            f[9 * IQ_SLOTS] = s.rconst; f[10 * IQ_SLOTS] = __uint_as_float(target_index); f[11 * IQ_SLOTS] = __uint_as_float(fidx);
         }
         count += __popc(m);
         __syncwarp();
         if (count >= 32) {                      // drain a full warp's worth
             count -= 32;
-            run(count + lane);
+            run(count + lane, true);
             __syncwarp();
         }
     }
     __device__ __forceinline__ void flush() {
         const int lane = threadIdx.x & 31;
         __syncwarp();
-        if (lane < count) run(lane);
+        if (count > 0) run(lane, lane < count);
         count = 0;
         __syncwarp();
     }
@@ -218,6 +272,7 @@ struct SetupMainParams {
     uint32_t* counters;
     unsigned long long* lookback;
     uint32_t* depth; int row_lo, row_hi;     // inline depth of small triangles
+    SampleList sl;                           // their covered samples, for k_ids_list
 };
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainParams P) {
@@ -386,11 +441,12 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
         }
     }
     // kernel1's work for the small single-chunk triangles, after everything other blocks wait for has been published
-    InlineRaster ir;
+    __syncthreads();            // every fragcnt word of this block is written: the rasterising lane may now update its flags
+    InlineRaster<true> ir;
     ir.q = &s_iq[warp]; ir.count = 0; ir.op = RR_OP_SIZE; ir.width = P.width; ir.height = P.height; ir.base = P.depth; ir.face_stride = 0;
-    ir.row_lo = P.row_lo; ir.row_hi = P.row_hi;
-    ir.push(inl0, st0, 0u);
-    ir.push(inl1, st1, 0u);
+    ir.row_lo = P.row_lo; ir.row_hi = P.row_hi; ir.sl = P.sl;
+    ir.push(inl0 && frag_ok, st0, 0u, base_f + ex_f);                 // single-chunk triangles: their one fragment's index
+    ir.push(inl1 && frag_ok, st1, 0u, base_f + ex_f + my_f0);
     ir.flush();
 }
 
@@ -467,9 +523,10 @@ __global__ void __launch_bounds__(256) k_raster_small(const RasterParams P) {
     constexpr int OP = (MODE == RM_SHADOW) ? RR_OP_SIZE_LIGHT : RR_OP_SIZE;
     const uint32_t n = min(P.counters[P.n_index], P.cap_frags);
     for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
-        const uint32_t raw = __ldg(P.fragcnt + f), cnt = raw & ~FRAGCNT_DEPTH_DONE;
+        const uint32_t raw = __ldg(P.fragcnt + f), cnt = raw & FRAGCNT_MASK;
         if (cnt > RASTER_SMALL_MAX || cnt == 0) continue;
         if (MODE == RM_DEPTH && (raw & FRAGCNT_DEPTH_DONE)) continue;        // written inline by k_setup_main
+        if (MODE == RM_IDS && (raw & FRAGCNT_IDS_LISTED)) continue;          // resolved from the sample list by k_ids_list
         uint32_t face, distance;
         FragGeom g;
         load_fragment<MODE>(P, f, face, distance, g);
@@ -477,6 +534,21 @@ __global__ void __launch_bounds__(256) k_raster_small(const RasterParams P) {
         scan_chunk(g.mm, OP, distance, [&](float x, float y) {
             if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) emit_sample<MODE>(P, x, y, g.A, g.B, g.C, face, f);
         });
+    }
+}
+
+// kernel2 for the triangles the setup kernel rasterised inline: stream their recorded samples instead of walking again.
+__global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const uint32_t* __restrict__ depth, uint32_t* __restrict__ ids, int W, int row_lo, int row_hi) {
+    const uint32_t n = min(*sl.desc_count, sl.cap_desc);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 de = sl.desc[i];
+        for (uint32_t j = 0; j < de.y; j++) {
+            const uint2 sm = sl.samples[de.x + j];
+            const int row = (int)(sm.x / (uint32_t)W);
+            if (row < row_lo || row >= row_hi) continue;
+            const uint32_t val = depth[sm.x];
+            if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) atomicMax(ids + sm.x, de.z);
+        }
     }
 }
 
@@ -507,7 +579,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_big(const uint32_t* __res
         unsigned long long mine = 0;                      // (number of big fragments << 37) | their slots
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; i++) {
-            uint32_t c = (first + i < n) ? (__ldg(cnt + first + i) & ~FRAGCNT_DEPTH_DONE) : 0u;
+            uint32_t c = (first + i < n) ? (__ldg(cnt + first + i) & FRAGCNT_MASK) : 0u;
             v[i] = c > RASTER_SMALL_MAX ? c : 0u;
             if (v[i]) mine += (1ull << SCAN_SLOT_BITS) | v[i];
         }
@@ -700,7 +772,7 @@ __global__ void __launch_bounds__(128) k_shadow_setup(const ShadowSetupParams P)
     bool active = tri < P.n_tris;
     float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0, gpos = w0;
     bool two_sided = false;
-    InlineRaster ir;
+    InlineRaster<false> ir;
     ir.q = &s_iq[threadIdx.x >> 5]; ir.count = 0; ir.op = RR_OP_SIZE_LIGHT; ir.width = P.L; ir.height = P.L; ir.base = P.buffer;
     ir.face_stride = (size_t)(P.L * P.L); ir.row_lo = 0; ir.row_hi = 0x7FFFFFFF;
     if (active) {
@@ -740,8 +812,8 @@ __global__ void __launch_bounds__(128) k_shadow_setup(const ShadowSetupParams P)
             // small triangles: queued for the warp to rasterise with all lanes busy; nothing is stored for them
             const uint32_t face_index = P.lights[li].slab * 6 + (uint32_t)kk;
             const bool small0 = inline_candidate(st0), small1 = inline_candidate(st1);
-            ir.push(small0, st0, face_index);
-            ir.push(small1, st1, face_index);
+            ir.push(small0, st0, face_index, 0u);
+            ir.push(small1, st1, face_index, 0u);
             if (small0) st0.keep = false;
             if (small1) st1.keep = false;
             if (!__any_sync(0xffffffffu, st0.keep || st1.keep)) continue;
@@ -969,7 +1041,7 @@ __device__ __forceinline__ float generate_ssao(int sx, int sy, const uint32_t* _
         }
     }
     float acc = (float)cnt;
-    acc /= 125.f;                       // pow(samples*2+1, 3)
+    acc = div_pos(acc, 125.f);          // pow(samples*2+1, 3)
     return 1.f - (1.f - acc) / ssao_div;
 }
 
@@ -1004,7 +1076,7 @@ __device__ __forceinline__ float hard_occlusion(float3 lpos, float3 normal, floa
         for (int x = -1; x <= 1; x++)
             shadow += bilinear_interpolate(pp.x + 0.5f + (float)x, pp.y + 0.5f + (float)y, cnd[(y + 1) * 4 + x + 1], cnd[(y + 1) * 4 + x + 2],
                                            cnd[(y + 2) * 4 + x + 1], cnd[(y + 2) * 4 + x + 2]);
-    return shadow / 9.f;
+    return div_pos(shadow, 9.f);
 }
 
 __device__ __forceinline__ unsigned short to_ushort_sat(float v) {
@@ -1160,7 +1232,8 @@ __device__ __forceinline__ void shade_pixel(const ShadeParams& P, const int x, c
         float sv = 2 * ndh / vdh;
         float c1 = sv * ndv, c2 = sv * ndl;
         float geometric = fminf(fminf(1.f, c1), c2);
-        float spec = (fresnel * microfacet * geometric) / (RR_PI_F * ndv);
+        const float spec_num = fresnel * microfacet * geometric, spec_den = RR_PI_F * ndv;
+        float spec = (spec_num == 0.f && spec_den > 0.f) ? spec_num : spec_num / spec_den;   // 0 / positive == 0 without the division's slow path
         specular_sum = specular_sum + light_col * (spec * kS * illumination) * Gspec_mult;
         specular_sum = make_float3(fmaxf(specular_sum.x, 0.f), fmaxf(specular_sum.y, 0.f), fmaxf(specular_sum.z, 0.f));
         specular_sum = specular_sum * occlusion;
@@ -1216,6 +1289,51 @@ __global__ void __launch_bounds__(256) k_shade_pre(const ShadeParams P) {
     if (tid == 0) s_base = atomicAdd(P.shade_count, (uint32_t)total);
     __syncthreads();
     if (covered) P.shade_list[s_base + off + __popc(m & ((1u << lane) - 1u))] = px;
+}
+
+// k_shade_pre4: same, four consecutive pixels per thread with 128-bit loads and stores (W % 4 == 0). Tile = 128 x 8.
+__global__ void __launch_bounds__(256) k_shade_pre4(const ShadeParams P) {
+    __shared__ int s_warp[8];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x = blockIdx.x * 128 + lane * 4;
+    const int y = P.row0 + blockIdx.y * 8 + warp;
+    unsigned cov = 0;                   // bit i: pixel x+i is covered
+    uint32_t px = 0;
+    if (x < P.W && y < P.row1) {
+        px = (uint32_t)y * (uint32_t)P.W + (uint32_t)x;
+        const uint4 d = *reinterpret_cast<const uint4*>(P.depth + px);
+        const bool any = (d.x & d.y & d.z & d.w) != 0xFFFFFFFFu;
+        uint4 idv = make_uint4(0, 0, 0, 0);
+        if (any) idv = *reinterpret_cast<const uint4*>(P.ids + px);
+        *reinterpret_cast<uint4*>(P.depth_next + px) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        *reinterpret_cast<uint4*>(P.ids_next + px) = make_uint4(0, 0, 0, 0);
+        if (y >= P.band_y0 && y < P.band_y1) {
+            const uint32_t nfr = P.n_frags[0];
+            cov = (unsigned)(d.x != 0xFFFFFFFFu && idv.x < nfr) | ((unsigned)(d.y != 0xFFFFFFFFu && idv.y < nfr) << 1) |
+                  ((unsigned)(d.z != 0xFFFFFFFFu && idv.z < nfr) << 2) | ((unsigned)(d.w != 0xFFFFFFFFu && idv.w < nfr) << 3);
+            if (cov != 0xFu) {          // covered pixels are overwritten by k_shade afterwards
+                const uchar4 c = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
+                const uint32_t cw = *reinterpret_cast<const uint32_t*>(&c);
+                *reinterpret_cast<uint4*>(P.rgba8 + px) = make_uint4(cw, cw, cw, cw);
+            }
+        }
+    }
+    const int mine = __popc(cov);
+    int inc = mine;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const int c = s_warp[w]; if (w < warp) off += c; total += c; }
+    if (total == 0) return;
+    if (tid == 0) s_base = atomicAdd(P.shade_count, (uint32_t)total);
+    __syncthreads();
+    uint32_t at = s_base + off + inc - mine;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (cov & (1u << i)) P.shade_list[at++] = px + i;
 }
 
 // k_shade: the expensive part of kernel3 (~6000 instructions per covered pixel) over the compacted list — every warp

@@ -40,6 +40,9 @@ __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_fl
 __device__ __forceinline__ float2 operator*(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// a / b for b > 0 where a is often exactly zero: +-0 / b == +-0, and skipping the division avoids the IEEE slow path that
+// a zero numerator triggers (bit-identical result)
+__device__ __forceinline__ float div_pos(float a, float b) { return a == 0.f ? a : a / b; }
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
