@@ -34,10 +34,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c3_small", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c3_small", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-opencl-reference", action="store_true")
-    ap.add_argument("--halo", type=int, default=-1, help="band halo rows at N>1 (-1 = rasterise depth for every row: exact SSAO)")
+    ap.add_argument("--halo", type=int, default=None, help="band halo rows at N>1 (default: the SSAO reach bound of the scene, exact; -1 = every row)")
     return ap.parse_args()
 
 
@@ -46,6 +46,8 @@ def make_scene(name):
         return scn.scene_c3()
     if name == "c5":
         return scn.scene_c5()
+    if name == "c4":
+        return scn.scene_c4()
     return scn.scene_spheres(1920, 1080, 60, (10, 6), 20260, 4, 512, name="c3_small_spheres_120ktri_1920x1080_4lights")
 
 
@@ -211,6 +213,8 @@ def run_ours(args):
     rows = H // world
     cfg = s.cfg.copy(device=local)
     if world > 1:
+        if args.halo is None:
+            args.halo = rrd.ssao_halo(s, [camera(s, i) for i in range(7)])
         cfg = rrd.band_config(cfg, world, rank, args.halo)
     r = Renderer(cfg)
     # colour target and cubemap slab live in torch tensors so torch.distributed (NCCL) can move them

@@ -68,6 +68,8 @@ struct rr_ctx {
     float2* d_pc = nullptr;
     rr_obj_desc* d_objs = nullptr;
     ObjLite* d_objlite = nullptr;
+    uint32_t* d_obj_r2 = nullptr;                // per-object bounding radius^2 (float bits), object space
+    int2* d_obj_rows = nullptr;                  // per-object screen rows of this frame (band mode)
     bool objlite_dirty = true;
     // atlas
     uchar4* d_atlas = nullptr;
@@ -299,7 +301,7 @@ void rr_destroy(rr_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_shadow_done) cudaEventDestroy(c->ev_shadow_done);
     if (c->stream2) cudaStreamDestroy(c->stream2);
-    cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite);
+    cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite); cudaFree(c->d_obj_r2); cudaFree(c->d_obj_rows);
     cudaFree(c->d_atlas); cudaFree(c->d_nums); cudaFree(c->d_sizes); cudaFree(c->d_upload);
     cudaFree(c->d_lights); cudaFree(c->d_lightlite);
     if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
@@ -328,6 +330,9 @@ int rr_scene_alloc(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
     if ((r = dev_alloc(c->d_pc, n_tris))) return r;
     if ((r = dev_alloc(c->d_objs, n_objs))) return r;
     if ((r = dev_alloc(c->d_objlite, n_objs))) return r;
+    if ((r = dev_alloc(c->d_obj_r2, n_objs))) return r;
+    if ((r = dev_alloc(c->d_obj_rows, n_objs))) return r;
+    CU(cudaMemsetAsync(c->d_obj_r2, 0, std::max<size_t>(1, n_objs) * 4, c->stream));
     // projected triangles: main pass needs <= 2T; a shadow pass (all lights at once) up to 12T per light in the worst
     // case (the reference allocates 12T, object_context.cpp:354). Default 6T + slack ; overflow is detected and reported.
     c->cap_cut = c->cfg.max_cutdown ? c->cfg.max_cutdown : (uint32_t)std::min<uint64_t>((uint64_t)n_tris * 6 + 1024, 0x7FFFFFFFu);
@@ -347,7 +352,7 @@ int rr_scene_write_tris(rr_ctx* c, uint32_t first, uint32_t count, const rr_tria
     if ((uint64_t)first + count > c->n_tris) return fail(RR_ERR_INVALID, "rr_scene_write_tris: range [%u,+%u) outside %u", first, count, c->n_tris);
     if (count == 0) return RR_OK;
     CU(cudaMemcpyAsync(c->d_tris + first, tris, (size_t)count * sizeof(rr_triangle), cudaMemcpyHostToDevice, c->stream));
-    k_repack<<<(count + 255) / 256, 256, 0, c->stream>>>(c->d_tris, first, count, c->d_pa, c->d_pb, c->d_pc);
+    k_repack<<<(count + 255) / 256, 256, 0, c->stream>>>(c->d_tris, first, count, c->d_pa, c->d_pb, c->d_pc, c->d_obj_r2, c->n_objs);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));      // caller may free `tris` on return (the reference keeps staging alive instead, object.cpp:729)
@@ -572,6 +577,13 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     sp.frags = c->d_frags; sp.cap_frags = c->cap_frags; sp.fragcnt = c->d_fragcnt; sp.cutdown = c->d_cutdown; sp.cap_cut = c->cap_cut;
     sp.counters = c->d_counters; sp.lookback = c->d_lookback;
     sp.depth = c->d_depth[c->cur]; sp.row_lo = row0; sp.row_hi = row1;
+    sp.obj_rows = nullptr;
+    if ((row0 > 0 || row1 < c->H) && c->n_objs) {      // sort-first band: objects that cannot touch the rasterised rows are not set up here
+        k_obj_rows<<<(c->n_objs + 127) / 128, 128, 0, c->stream>>>(c->d_objlite, c->d_obj_r2, c->n_objs, cam, (float)c->H, c->fov,
+                                                                    (float)c->cfg.depth_icutoff, c->d_obj_rows);
+        c->launches++;
+        sp.obj_rows = c->d_obj_rows;
+    }
     sp.sl.samples = c->d_samples; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
     sp.sl.desc = c->d_sample_desc; sp.sl.cap_desc = c->cap_frags; sp.sl.desc_count = c->d_counters + CTR_NDESC; sp.sl.fragcnt = c->d_fragcnt;
     k_setup_main<<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);

@@ -36,7 +36,8 @@ struct FaceTable { RotSC r[6]; };
 // Runs once per rr_scene_write_tris (the reference's fill_ids kernel, cl2.cl:4231, ran at the same point).
 // =====================================================================================================================
 __global__ void __launch_bounds__(256) k_repack(const rr_triangle* __restrict__ tris, uint32_t first, uint32_t count,
-                                                float4* __restrict__ pa, float4* __restrict__ pb, float2* __restrict__ pc) {
+                                                float4* __restrict__ pa, float4* __restrict__ pb, float2* __restrict__ pc,
+                                                uint32_t* __restrict__ obj_r2_bits, uint32_t n_objs) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const rr_triangle* t = tris + first + i;
@@ -47,6 +48,9 @@ __global__ void __launch_bounds__(256) k_repack(const rr_triangle* __restrict__ 
     pa[first + i] = make_float4(v0.x, v0.y, v0.z, v1.x);
     pb[first + i] = make_float4(v1.y, v1.z, v2.x, v2.y);
     pc[first + i] = make_float2(v2.z, __uint_as_float(oid));
+    // bounding-sphere radius^2 of the object in object space (non-negative floats order like their bit patterns)
+    const float r2 = fmaxf(fmaxf(v0.x * v0.x + v0.y * v0.y + v0.z * v0.z, v1.x * v1.x + v1.y * v1.y + v1.z * v1.z), v2.x * v2.x + v2.y * v2.y + v2.z * v2.z);
+    if (oid < n_objs) atomicMax(obj_r2_bits + oid, __float_as_uint(r2));
 }
 
 // Per-object data the setup kernels need, 48 B instead of the 144 B descriptor: rebuilt when descriptors change.
@@ -76,6 +80,26 @@ __global__ void __launch_bounds__(128) k_objlite(const rr_obj_desc* __restrict__
     o.feature_flag = G.feature_flag;
     o._pad[0] = o._pad[1] = o._pad[2] = 0;
     out[i] = o;
+}
+
+// Sort-first object culling (multi-GPU band mode only): conservative screen-row range of every object's bounding sphere
+// for this frame's camera. A triangle of an object whose rows cannot touch [row_lo, row_hi) is not set up at all on this
+// context — it cannot produce a fragment there. rows = (first, last) inclusive; (INT_MIN, INT_MAX) when in doubt.
+__global__ void __launch_bounds__(128) k_obj_rows(const ObjLite* __restrict__ objs, const uint32_t* __restrict__ obj_r2_bits, uint32_t n,
+                                                  CamParams cam, float height, float fov, float icut, int2* __restrict__ rows) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ObjLite G = objs[i];
+    const float R = sqrtf(__uint_as_float(obj_r2_bits[i])) * fabsf(G.pos_scale.w) * 1.001f + 1e-3f;
+    const float3 c = rot(make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z), cam.pos, cam.rot);
+    int2 r = make_int2(INT_MIN, INT_MAX);
+    const float zn = c.z - R, zf = c.z + R;
+    if (zn > icut + 1.f && isfinite(R) && isfinite(c.y) && isfinite(c.z)) {      // entirely in front of the near plane: no clipping involved
+        const float a = (c.y - R) * fov, b = (c.y + R) * fov;
+        const float lo = fminf(a / zn, a / zf) + height * 0.5f, hi = fmaxf(b / zn, b / zf) + height * 0.5f;
+        r = make_int2((int)fmaxf(floorf(lo) - 4.f, -1e9f), (int)fminf(ceilf(hi) + 4.f, 1e9f));
+    }
+    rows[i] = r;
 }
 
 // One clipped + projected triangle after culling. keep == false -> no storage written, no fragments.
@@ -273,6 +297,7 @@ struct SetupMainParams {
     unsigned long long* lookback;
     uint32_t* depth; int row_lo, row_hi;     // inline depth of small triangles
     SampleList sl;                           // their covered samples, for k_ids_list
+    const int2* obj_rows;                    // band mode: per-object row range (k_obj_rows); nullptr = no object culling
 };
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainParams P) {
@@ -302,7 +327,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
         oid = __float_as_uint(c.y);
         const ObjLite G = P.objs[oid];
         const float3 gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
-        if (!(length3(gpos - P.cam.pos) > RR_DEPTH_FAR)) {                      // cl2.cl:4321
+        bool in_band = true;
+        if (P.obj_rows) { const int2 rw = __ldg(P.obj_rows + oid); in_band = !(rw.y < P.row_lo || rw.x >= P.row_hi); }
+        if (in_band && !(length3(gpos - P.cam.pos) > RR_DEPTH_FAR)) {           // cl2.cl:4321
             const float sc = G.pos_scale.w;
             const float3 q0 = rot(rot_quat_n(make_float3(a.x, a.y, a.z) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);
             const float3 q1 = rot(rot_quat_n(make_float3(a.w, b.x, b.y) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);

@@ -46,3 +46,31 @@ def gather_bands(fb, rows, rank, world, dst=0, group=None):
                 fb[k * rows:(k + 1) * rows].copy_(lst[k])
     else:
         dist.gather(band, [fb[k * rows:(k + 1) * rows] for k in range(world)] if rank == dst else None, dst=dst, group=group)
+
+
+def ssao_halo(scene, cameras=None, margin=8):
+    """Rows of depth a band needs beyond its own for exact SSAO (cl2.cl:2194-2260): the taps reach round(2 * world_rad)
+    pixels with world_rad = (SSAO_RAD + 0.5) * FOV_CONST / depth, so the nearest geometry bounds it. Computed from the
+    objects' bounding spheres for the given cameras; -1 (rasterise every row) when geometry can reach the near plane."""
+    import numpy as np
+    from .scene import fov_for
+    if scene.cfg.no_ssao:
+        return margin
+    tris, objs = scene.tris, scene.objs
+    oid = tris["vertices"]["object_id"][:, 0]
+    r_obj = np.zeros(len(objs))
+    np.maximum.at(r_obj, oid, np.linalg.norm(tris["vertices"]["pos"][:, :, :3].astype(np.float64), axis=-1).max(axis=1))
+    R = r_obj * np.abs(objs["scale"].astype(np.float64)) * 1.001
+    z_near = np.inf
+    for c_pos, c_rot in (cameras or [(scene.c_pos, scene.c_rot)]):
+        cr, sr = np.cos(np.asarray(c_rot, np.float64)), np.sin(np.asarray(c_rot, np.float64))
+        rel = objs["world_pos"][:, :3].astype(np.float64) - np.asarray(c_pos, np.float64)[:3]
+        t = sr[2] * rel[:, 1] + cr[2] * rel[:, 0]
+        u = cr[1] * rel[:, 2] + sr[1] * t
+        v = cr[2] * rel[:, 1] - sr[2] * rel[:, 0]
+        z = cr[0] * u - sr[0] * v                                   # rot(), cl2.cl:236
+        z_near = min(z_near, float(np.where(z + R > scene.cfg.depth_icutoff, np.maximum(z - R, 0.0), np.inf).min()))
+    if not np.isfinite(z_near) or z_near <= scene.cfg.depth_icutoff + 1:
+        return -1
+    reach = 2.0 * (scene.cfg.ssao_rad + 0.5) * fov_for(scene.cfg) / z_near
+    return int(np.ceil(reach)) + margin

@@ -100,24 +100,39 @@ def test_odd_resolution_and_empty_scene():
     assert (g2.read_depth() == 0xFFFFFFFF).all()
 
 
-def test_band_split_equals_full_frame():
-    """sort-first bands: compositing the bands of 4 contexts == the single-context frame, bit for bit."""
+def _tri_of(r):
+    ids, fr, d = r.read_ids(), r.read_fragments(), r.read_depth()
+    t = np.full(ids.shape, -1, np.int64)
+    ok = (d != 0xFFFFFFFF) & (ids < len(fr))
+    t[ok] = fr[ids[ok], 0]
+    return t
+
+
+@pytest.mark.parametrize("halo", [-1, 24])
+def test_band_split_equals_full_frame(halo):
+    """sort-first bands: compositing the bands of 4 contexts == the single-context frame, bit for bit in
+    depth and colour; ids compared as triangle ids (each context numbers only the fragments of the objects it set up).
+    halo -1 rasterises every row on every context; halo 24 (>= this scene's SSAO reach) culls objects outside band+halo."""
     s = scene.scene_spheres(640, 384, n_spheres=12, grid=(4, 3), seed=11, n_lights=2, light_dim=128, tex_sizes=(128, 64))
     full = Renderer(s.cfg)
     s.upload(full)
     s.render(full, frames=2)
-    fd, fi, fc = full.read_depth(), full.read_ids(), full.read_rgba8()
+    fd, ft, fc = full.read_depth(), _tri_of(full), full.read_rgba8()
+    n_full = len(full.read_fragments())
     n = 4
+    culled = 0
     for k in range(n):
         y0, y1 = k * 96, (k + 1) * 96
-        cfg = s.cfg.copy(band_y0=y0, band_y1=y1, band_halo=-1, face_rank=0, face_world=0)
+        cfg = s.cfg.copy(band_y0=y0, band_y1=y1, band_halo=halo, face_rank=0, face_world=0)
         b = Renderer(cfg)
         s.upload(b)
         s.render(b, frames=2)
         assert np.array_equal(b.read_depth()[y0:y1], fd[y0:y1])
-        cov = fd[y0:y1] != 0xFFFFFFFF
-        assert np.array_equal(b.read_ids()[y0:y1][cov], fi[y0:y1][cov])
+        assert np.array_equal(_tri_of(b)[y0:y1], ft[y0:y1])
         assert np.array_equal(b.read_rgba8()[y0:y1], fc[y0:y1])
+        culled += int(len(b.read_fragments()) < n_full)
+    if halo >= 0:
+        assert culled >= 2, "object culling never kicked in"
 
 
 def test_face_sharding_union_equals_full_cubemap():
