@@ -276,6 +276,9 @@ def run_ours(args):
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_total, launches = float(tmax[0]), int(tsum[1])
+    if os.environ.get("RR_BENCH_RANK_TIMINGS"):
+        tm = r.timings()
+        sys.stderr.write("rank %d: %s\n" % (rank, json.dumps({k: round(v, 4) if isinstance(v, float) else v for k, v in tm.items()})))
     ms = ms_total / args.steps
     T = len(s.tris)
     val = T / (ms * 1e-3) / 1e6
