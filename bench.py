@@ -38,6 +38,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-opencl-reference", action="store_true")
     ap.add_argument("--halo", type=int, default=None, help="band halo rows at N>1 (default: the SSAO reach bound of the scene, exact; -1 = every row)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = interleaved row tiles, faces pushed and rows composited by the kernels over peer memory (product); "
+                         "nccl = contiguous bands, all_gather + gather collectives per frame (baseline)")
+    ap.add_argument("--tile", type=int, default=0, help="rows per tile of the interleaved split (p2p; 0 = choose)")
+    ap.add_argument("--verify", action="store_true", help="N>1: rank 0 also renders the frame alone and checks the composite bit for bit")
     return ap.parse_args()
 
 
@@ -212,25 +217,38 @@ def run_ours(args):
     from openclrenderer_b200 import distributed as rrd
     rows = H // world
     cfg = s.cfg.copy(device=local)
+    p2p = world > 1 and args.exchange == "p2p"
     if world > 1:
         if args.halo is None:
             args.halo = rrd.ssao_halo(s, [camera(s, i) for i in range(7)])
-        cfg = rrd.band_config(cfg, world, rank, args.halo)
+        if p2p:
+            if not args.tile:
+                args.tile = rrd.choose_tile(H, world, args.halo)
+            cfg = rrd.tile_config(cfg, world, rank, args.tile, args.halo)
+        else:
+            cfg = rrd.band_config(cfg, world, rank, args.halo)
     r = Renderer(cfg)
-    # colour target and cubemap slab live in torch tensors so torch.distributed (NCCL) can move them
-    fb = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
-    if world > 1:
+    # nccl baseline: colour target and cubemap slab live in torch tensors so torch.distributed (NCCL) can move them
+    fb = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) if (world > 1 and not p2p) else None
+    if fb is not None:
         r.bind_external(RR_BUF_RGBA8, fb.data_ptr(), fb.numel())
     chunk = rrd.face_chunk(n_shadow, world)
-    shadow = torch.full((chunk * world * L * L,), -1, dtype=torch.int32, device=dev)
-    r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
+    if not p2p:
+        shadow = torch.full((chunk * world * L * L,), -1, dtype=torch.int32, device=dev)
+        r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
     s.upload(r)
+    if p2p:
+        rrd.connect_peers(r, rank, world, device=dev)     # after this the kernels exchange faces and rows themselves
     stream = torch.cuda.ExternalStream(r.stream(), device=dev)
     sh_stream = torch.cuda.ExternalStream(r.shadow_stream(), device=dev)
 
     def frame(i):
         c_pos, c_rot = camera(s, i)
         r.frame_shadows(0)
+        if p2p:
+            r.frame_draw(c_pos, c_rot, s.clear)
+            r.swap_buffers()
+            return
         if world > 1:
             with torch.cuda.stream(sh_stream):                                   # on the shadow stream: overlaps the main view's setup/depth/ids
                 rrd.all_gather_faces(shadow, chunk * L * L, rank)                # faces rendered elsewhere arrive in place
@@ -286,13 +304,17 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers: H2D of the per-frame inputs (object descriptors from
     # pinned memory, as object_context::flush_locations does) and D2H of the finished frame, inside the timed region
     host_fb = rr.host_alloc((H, W, 4), np.uint8) if rank == 0 else None
-    host_fb2 = rr.host_alloc((H, W, 4), np.uint8) if (rank == 0 and world == 1) else None
+    host_fb2 = rr.host_alloc((H, W, 4), np.uint8) if (rank == 0 and (world == 1 or p2p)) else None
     pinned_t = torch.from_numpy(host_fb) if rank == 0 else None
+    dummy = np.zeros(4, np.uint8)
 
     def frame_e2e(i):
         c_pos, c_rot = camera(s, i)
         if world == 1:
             r.frame_e2e(c_pos, c_rot, s.clear, 1, host_fb if i % 2 == 0 else host_fb2)   # pipelined read-back; swaps buffers itself
+        elif p2p:
+            # every rank uploads its descriptors and renders its rows into rank 0's target; rank 0 reads the composite back
+            r.frame_e2e(c_pos, c_rot, s.clear, 1, (host_fb if i % 2 == 0 else host_fb2) if rank == 0 else dummy)
         else:
             r.scene_write_objs(s.objs)
             frame(i)
@@ -320,7 +342,8 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u32",
-                "data": "synthetic", "config": config_dict(s, {"parallelism": f"bands{world}+faces{world}" if world > 1 else "single",
+                "data": "synthetic", "config": config_dict(s, {"parallelism": (f"tiles{world}x{args.tile}rows+faces{world} peer-memory (in-kernel push/composite over NVLink)" if p2p
+                                                                                else f"bands{world}+faces{world} nccl") if world > 1 else "single",
                                                                 "band_halo": args.halo if world > 1 else None}),
                 "fps": round(1e3 / ms, 2), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
 
@@ -393,6 +416,33 @@ def run_ours(args):
             line["reference_opencl_b200"] = opencl_reference(s, min(args.steps, 20))
         except Exception as e:                         # informative only; never fails the bench
             line["reference_opencl_b200"] = {"unavailable": str(e)[:200]}
+    if world > 1 and args.verify:
+        # the composite on rank 0 must equal the frame one context renders alone, bit for bit
+        c_pos, c_rot = camera(s, 12345)
+        r.frame_shadows(0)
+        if p2p:
+            r.frame_draw(c_pos, c_rot, s.clear)
+        else:
+            with torch.cuda.stream(sh_stream):
+                rrd.all_gather_faces(shadow, chunk * L * L, rank)
+            r.shadows_done()
+            r.frame_draw(c_pos, c_rot, s.clear)
+            with torch.cuda.stream(stream):
+                rrd.gather_bands(fb, rows, rank, world, dst=0)
+        barrier()
+        if rank == 0:
+            got = r.read_rgba8()
+            solo = Renderer(s.cfg.copy(device=local))
+            s.upload(solo)
+            solo.frame_shadows(0)
+            solo.frame_draw(c_pos, c_rot, s.clear)
+            solo.sync()
+            want = solo.read_rgba8()
+            bad = int((got != want).any(axis=-1).sum())
+            line["verify"] = {"pixels_differing_from_single_gpu_frame": bad, "pixels": int(W * H)}
+            solo.close()
+        r.swap_buffers()
+        barrier()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -26,6 +26,7 @@ extern "C" {
 #define RR_ERR_CUDA     (-2)   /* CUDA runtime failure (text in rr_last_error) */
 #define RR_ERR_OOM      (-3)
 #define RR_ERR_OVERFLOW (-4)   /* fragment / projected-triangle storage exhausted (reference: silent corruption, cl2.cl:4392) */
+#define RR_ERR_PEER     (-5)   /* multi-GPU: a peer context did not deliver its part of the frame in time */
 
 /* ---- device-visible PODs: byte-identical to the reference's host/device structs ------------------------------- */
 
@@ -98,6 +99,10 @@ typedef struct rr_config {
     int32_t face_rank, face_world; /* shadow (light,face) pair p = 6*slab+face is rendered here iff p / ceil(6S/face_world) == face_rank; 0,0 = all */
     uint32_t max_fragments;        /* fragment-record capacity; 0 = 16 Mi (reference: 2 Mi, engine.cpp:601) */
     uint32_t max_cutdown;          /* projected-triangle capacity; 0 = derived from the triangle count */
+    /* interleaved sort-first split (load balance when the geometry sits in a few screen rows): */
+    int32_t band_tile;             /* > 0: row y belongs to this context iff (y / band_tile) % band_world == band_rank; band_y0/y1 ignored */
+    int32_t band_rank, band_world;
+    int32_t face_interleave;       /* 1: pair p is rendered here iff p % face_world == face_rank (peer-memory exchange); 0: contiguous chunks */
 } rr_config;
 
 typedef struct rr_timings {      /* CUDA-event milliseconds of the last rr_frame_* calls (reference: -DPROFILING, engine.hpp:625-640) */
@@ -166,6 +171,25 @@ void* rr_stream(rr_ctx*);                                                       
 void* rr_shadow_stream(rr_ctx*);   /* cudaStream_t of the shadow passes: rr_frame_shadows runs there, concurrently with rr_frame_draw's
                                       setup/depth/id kernels; rr_frame_draw waits for it right before shading */
 int   rr_shadows_done(rr_ctx*);    /* call after enqueueing extra work on the shadow stream (the cubemap-face all-gather): shading waits for it too */
+
+/* ---- multi-GPU exchange over peer memory (NVLink P2P), one context per GPU --------------------------------------------
+ * Replaces nothing in the reference (single device); it is the north star's "bands composited to GPU 0 over NVLink, cubemap
+ * faces sharded" step done inside the producing kernels instead of with collectives afterwards:
+ *   - every context renders the cubemap faces it owns and pushes them into all peers' cubemap buffers (k_push_faces);
+ *   - every context's shading kernel stores its rows straight into rank 0's colour target;
+ *   - frame-counter flags in a small control block order producers and consumers (no host synchronisation per frame).
+ * Call order: rr_lights_write -> rr_mgpu_export on every context -> exchange the handles (any transport; the Python harness
+ * uses torch.distributed) -> rr_mgpu_connect with all handles in rank order -> frames, called in lock-step on all contexts.
+ * rr_mgpu_connect_local wires contexts living in ONE process (same device or peer-accessible devices) without IPC. */
+typedef struct rr_mgpu_handle {
+    uint8_t  shadow[64], fb[64], ctrl[64];   /* cudaIpcMemHandle_t of the cubemap pair, the colour-target pair, the control block */
+    uint64_t shadow_bytes, fb_bytes;
+    int32_t  device, n_shadow, width, height, light_dim, _pad;
+} rr_mgpu_handle;
+int rr_mgpu_export(rr_ctx*, rr_mgpu_handle* out);
+int rr_mgpu_connect(rr_ctx*, int rank, int world, const rr_mgpu_handle* handles /* [world], rank order */);
+int rr_mgpu_connect_local(rr_ctx* const* ctxs, int world);   /* ctxs[k] becomes rank k */
+int rr_mgpu_disconnect(rr_ctx*);
 
 void* rr_host_alloc(size_t nbytes);            /* page-locked host memory for read-backs (CL_MEM_ALLOC_HOST_PTR role; async_read.hpp:30-60 host buffers) */
 void  rr_host_free(void* p);

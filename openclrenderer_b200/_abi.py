@@ -25,7 +25,7 @@ assert VERTEX.itemsize == 48 and TRIANGLE.itemsize == 144 and OBJ_DESC.itemsize 
 
 FEATURE_SS_REFLECTIVE, FEATURE_TWO_SIDED, FEATURE_OUTLINE, FEATURE_IS_STATIC, FEATURE_NO_DYNAMIC_SHADOWS = 1, 2, 4, 8, 16
 
-RR_OK, RR_ERR_INVALID, RR_ERR_CUDA, RR_ERR_OOM, RR_ERR_OVERFLOW = 0, -1, -2, -3, -4
+RR_OK, RR_ERR_INVALID, RR_ERR_CUDA, RR_ERR_OOM, RR_ERR_OVERFLOW, RR_ERR_PEER = 0, -1, -2, -3, -4, -5
 RR_BUF_RGBA8, RR_BUF_SHADOW_DYNAMIC, RR_BUF_SHADOW_STATIC, RR_BUF_DEPTH, RR_BUF_IDS = range(5)
 
 
@@ -34,14 +34,16 @@ class Config(C.Structure):
                 ("depth_icutoff", C.c_int32), ("ambient", C.c_float), ("ssao_rad", C.c_float), ("ssao_div", C.c_float), ("mip_bias", C.c_float),
                 ("shadow_bias", C.c_float), ("shadow_exp", C.c_float), ("test_linear", C.c_int32), ("use_linear_rendering", C.c_int32),
                 ("no_ssao", C.c_int32), ("device", C.c_int32), ("band_y0", C.c_int32), ("band_y1", C.c_int32), ("band_halo", C.c_int32),
-                ("face_rank", C.c_int32), ("face_world", C.c_int32), ("max_fragments", C.c_uint32), ("max_cutdown", C.c_uint32)]
+                ("face_rank", C.c_int32), ("face_world", C.c_int32), ("max_fragments", C.c_uint32), ("max_cutdown", C.c_uint32),
+                ("band_tile", C.c_int32), ("band_rank", C.c_int32), ("band_world", C.c_int32), ("face_interleave", C.c_int32)]
 
     @staticmethod
     def default(width=800, height=600, **kw):
         """Reference defaults: SSAO_RAD 5, no TEST_LINEAR ("profile B")."""
         c = Config(width=width, height=height, light_dim=1024, fov_const=0.0, hfov_deg=120.0, depth_icutoff=20, ambient=0.2, ssao_rad=5.0,
                    ssao_div=2.5, mip_bias=1.1, shadow_bias=50.0, shadow_exp=1.0, test_linear=0, use_linear_rendering=1, no_ssao=0, device=0,
-                   band_y0=0, band_y1=0, band_halo=-1, face_rank=0, face_world=0, max_fragments=0, max_cutdown=0)
+                   band_y0=0, band_y1=0, band_halo=-1, face_rank=0, face_world=0, max_fragments=0, max_cutdown=0,
+                   band_tile=0, band_rank=0, band_world=0, face_interleave=0)
         for k, v in kw.items():
             if not hasattr(c, k):
                 raise AttributeError(k)
@@ -59,6 +61,12 @@ class Config(C.Structure):
         for k, v in kw.items():
             setattr(c, k, v)
         return c
+
+
+class MgpuHandle(C.Structure):
+    """rr_mgpu_handle (include/rr.h): the IPC handles one context exports for the peer-memory exchange."""
+    _fields_ = [("shadow", C.c_uint8 * 64), ("fb", C.c_uint8 * 64), ("ctrl", C.c_uint8 * 64), ("shadow_bytes", C.c_uint64), ("fb_bytes", C.c_uint64),
+                ("device", C.c_int32), ("n_shadow", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("light_dim", C.c_int32), ("_pad", C.c_int32)]
 
 
 class Timings(C.Structure):

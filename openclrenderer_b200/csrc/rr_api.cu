@@ -125,6 +125,35 @@ struct rr_ctx {
     unsigned long long* d_sscan_lookback = nullptr;
     // e2e staging (pinned)
     rr_obj_desc* h_objs_pinned = nullptr;
+    // sort-first rows (rr_config.band_*): bounding ranges, and per-row tables in interleaved mode
+    int own_lo = 0, own_hi = 0, need_lo = 0, need_hi = 0;
+    bool banded = false;
+    uint8_t* d_rowmask = nullptr;                // ROW_NEEDED | ROW_OWNED per row (interleaved mode only)
+    int* d_rowpfx = nullptr;                     // [H + 1] prefix count of ROW_NEEDED rows
+    // clusters of CLUSTER_TRIS consecutive triangles (k_cluster_bounds): per-frame culling units of the setup kernels
+    uint32_t n_clusters = 0;
+    ClusterBox* d_clusters = nullptr;
+    uint8_t* d_cluster_vis = nullptr;            // main view: 0 = culled this frame (k_cluster_vis)
+    uint4* d_cluster_faces = nullptr;            // face sharding: per-cluster cube-face reach of the lights of the pass
+    // multi-GPU exchange over peer memory (rr_mgpu_*)
+    struct Mg {
+        bool exported = false, connected = false, ipc = false;
+        int rank = 0, world = 1;
+        uint32_t* shadow[2] = {nullptr, nullptr};            // local double-buffered dynamic cubemaps (one allocation)
+        uchar4* fb[2] = {nullptr, nullptr};                  // local colour-target pair (rank 0's are the composite targets)
+        MgCtrl* ctrl = nullptr;
+        size_t shadow_words = 0;                             // per buffer
+        uint32_t* peer_shadow[MG_MAX_WORLD][2] = {};
+        uchar4* fb0[2] = {nullptr, nullptr};                 // rank 0's colour targets as seen from here
+        MgCtrl* peer_ctrl[MG_MAX_WORLD] = {};
+        void* opened[MG_MAX_WORLD][3] = {};                  // cudaIpcOpenMemHandle results to close
+        uint8_t* prev_dirty[2] = {nullptr, nullptr};
+        uint32_t shadow_epoch = 0, draw_epoch = 0;
+        uint32_t* saved_shadow_dyn = nullptr; bool saved_ext_shadow = false; size_t saved_shadow_words = 0;
+        uchar4* saved_rgba8 = nullptr; bool saved_ext_rgba8 = false;
+    } mg;
+    int mg_target = 0;                           // which of the colour-target pair this draw goes to (rr_frame_e2e alternates)
+    cudaEvent_t ev_frame_done[2] = {nullptr, nullptr};
     // stats
     uint32_t launches = 0;
     FaceTable faces;
@@ -180,10 +209,116 @@ int raster(rr_ctx* c, cudaStream_t st, const RasterParams& rp) {
 }
 
 void band_rows(const rr_ctx* c, int& band0, int& band1, int& row0, int& row1) {
-    band0 = 0; band1 = c->H;
-    if (c->cfg.band_y1 > c->cfg.band_y0) { band0 = std::max(0, c->cfg.band_y0); band1 = std::min(c->H, c->cfg.band_y1); }
-    if (c->cfg.band_halo < 0 || (band0 == 0 && band1 == c->H)) { row0 = 0; row1 = c->H; }
-    else { row0 = std::max(0, band0 - c->cfg.band_halo); row1 = std::min(c->H, band1 + c->cfg.band_halo); }
+    band0 = c->own_lo; band1 = c->own_hi; row0 = c->need_lo; row1 = c->need_hi;
+}
+
+// Rows this context shades (owned) and rasterises (needed = owned dilated by band_halo rows, for SSAO). Contiguous bands
+// are fully described by the two ranges; the interleaved split (band_tile) also gets per-row tables on the device.
+int setup_rows(rr_ctx* c) {
+    const int H = c->H;
+    const rr_config& g = c->cfg;
+    std::vector<uint8_t> mask((size_t)H, 0);
+    const bool tiled = g.band_tile > 0 && g.band_world > 1;
+    if (tiled && (g.band_rank < 0 || g.band_rank >= g.band_world)) return fail(RR_ERR_INVALID, "rr_create: band_rank %d outside band_world %d", g.band_rank, g.band_world);
+    const bool ranged = !tiled && g.band_y1 > g.band_y0;
+    for (int y = 0; y < H; y++) {
+        bool own = true;
+        if (tiled) own = (y / g.band_tile) % g.band_world == g.band_rank;
+        else if (ranged) own = y >= g.band_y0 && y < g.band_y1;
+        if (own) mask[y] |= ROW_OWNED;
+    }
+    const bool whole = !tiled && !ranged;
+    if (whole || g.band_halo < 0) { for (int y = 0; y < H; y++) mask[y] |= ROW_NEEDED; }
+    else {
+        int last_owned = -0x3FFFFFFF;
+        for (int y = 0; y < H; y++) { if (mask[y] & ROW_OWNED) last_owned = y; if (y - last_owned <= g.band_halo) mask[y] |= ROW_NEEDED; }
+        int next_owned = 0x3FFFFFFF;
+        for (int y = H - 1; y >= 0; y--) { if (mask[y] & ROW_OWNED) next_owned = y; if (next_owned - y <= g.band_halo) mask[y] |= ROW_NEEDED; }
+    }
+    c->own_lo = c->need_lo = H; c->own_hi = c->need_hi = 0;
+    for (int y = 0; y < H; y++) {
+        if (mask[y] & ROW_OWNED) { c->own_lo = std::min(c->own_lo, y); c->own_hi = y + 1; }
+        if (mask[y] & ROW_NEEDED) { c->need_lo = std::min(c->need_lo, y); c->need_hi = y + 1; }
+    }
+    if (c->own_hi == 0) { c->own_lo = 0; }                        // owns nothing (more contexts than tiles): empty ranges
+    if (c->need_hi == 0) { c->need_lo = 0; }
+    c->banded = !whole;
+    if (tiled) {
+        std::vector<int> pfx((size_t)H + 1, 0);
+        for (int y = 0; y < H; y++) pfx[y + 1] = pfx[y] + ((mask[y] & ROW_NEEDED) ? 1 : 0);
+        CU(cudaMalloc((void**)&c->d_rowmask, (size_t)H));
+        CU(cudaMalloc((void**)&c->d_rowpfx, ((size_t)H + 1) * sizeof(int)));
+        CU(cudaMemcpy(c->d_rowmask, mask.data(), (size_t)H, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_rowpfx, pfx.data(), ((size_t)H + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return RR_OK;
+}
+
+// (light, face) pair p of `total` is rendered by this context?
+bool owns_pair(const rr_ctx* c, uint32_t p, uint32_t total) {
+    if (c->cfg.face_world <= 1) return true;
+    if (c->cfg.face_interleave) return (int)(p % (uint32_t)c->cfg.face_world) == c->cfg.face_rank;
+    const uint32_t chunk = (total + c->cfg.face_world - 1) / c->cfg.face_world;
+    return (p / chunk) == (uint32_t)c->cfg.face_rank;
+}
+
+// ---- multi-GPU helpers (rr_mgpu_*) ------------------------------------------------------------------------------------
+unsigned long long mg_timeout_ns() {
+    const char* e = getenv("RR_MGPU_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 20000.0;
+    return (unsigned long long)(std::max(ms, 1.0) * 1e6);
+}
+
+// wait on `st` until every other context's flag (shadow or draw) in the LOCAL control block has reached `value`
+int mg_wait(rr_ctx* c, cudaStream_t st, bool shadow, uint32_t value) {
+    MgWait w;
+    w.n = 0; w.value = value; w.error = &c->mg.ctrl->error; w.timeout_ns = mg_timeout_ns();
+    for (int q = 0; q < c->mg.world; q++) {
+        if (q == c->mg.rank) continue;
+        w.flag[w.n++] = shadow ? &c->mg.ctrl->shadow_flag[q] : &c->mg.ctrl->draw_flag[q];
+    }
+    if (w.n == 0) return RR_OK;
+    k_wait_flags<<<1, 32, 0, st>>>(w);
+    c->launches++;
+    CU(cudaGetLastError());
+    return RR_OK;
+}
+
+int mg_owned_pairs(const rr_ctx* c, uint32_t* out) {
+    const uint32_t total = 6u * c->n_shadow;
+    int n = 0;
+    for (uint32_t p = 0; p < total; p++) if (owns_pair(c, p, total)) out[n++] = p;
+    return n;
+}
+
+// clear the owned faces of the epoch's buffer (the others are delivered by their owners and never cleared here)
+int mg_fill_owned(rr_ctx* c, cudaStream_t st, uint32_t* buffer) {
+    MgFillParams f;
+    f.buffer = buffer; f.face_words = (uint32_t)c->L * (uint32_t)c->L;
+    f.n_pairs = mg_owned_pairs(c, f.pair);
+    if (f.n_pairs == 0) return RR_OK;
+    k_fill_faces<<<grid_for(c, 8), 256, 0, st>>>(f);
+    c->launches++;
+    CU(cudaGetLastError());
+    return RR_OK;
+}
+
+// copy the owned faces into every peer's buffer of the same parity and raise this context's flag there
+int mg_push(rr_ctx* c, cudaStream_t st, int b, uint32_t epoch) {
+    MgPushParams p;
+    p.local = c->mg.shadow[b]; p.face_words = (uint32_t)c->L * (uint32_t)c->L; p.prev_dirty = c->mg.prev_dirty[b];
+    p.n_pairs = mg_owned_pairs(c, p.pair);
+    p.n_peers = 0; p.sig.n = 0; p.sig.counter = &c->mg.ctrl->push_done; p.sig.value = epoch;
+    for (int q = 0; q < c->mg.world; q++) {
+        if (q == c->mg.rank) continue;
+        p.peer[p.n_peers++] = c->mg.peer_shadow[q][b];
+        p.sig.flag[p.sig.n++] = &c->mg.peer_ctrl[q]->shadow_flag[c->mg.rank];
+    }
+    if (p.n_peers == 0) return RR_OK;
+    k_push_faces<<<grid_for(c, 4), 256, 0, st>>>(p);
+    c->launches++;
+    CU(cudaGetLastError());
+    return RR_OK;
 }
 
 }  // namespace
@@ -284,6 +419,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     cudaMemsetAsync(c->d_rgba8, 0, P * 4, c->stream);
     cudaMemsetAsync(c->d_normals, 0, P * 4, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("init sync");
+    if (setup_rows(c) != RR_OK) { rr_destroy(c); return nullptr; }
     return c;
 }
 
@@ -292,6 +428,8 @@ void rr_destroy(rr_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream3) cudaStreamSynchronize(c->stream3);
+    rr_mgpu_disconnect(c);
+    for (int i = 0; i < 2; i++) if (c->ev_frame_done[i]) cudaEventDestroy(c->ev_frame_done[i]);
     if (c->d_rgba8_alt) cudaFree(c->d_rgba8_alt);
     if (c->ev_draw_done) cudaEventDestroy(c->ev_draw_done);
     for (int i = 0; i < 2; i++) if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
@@ -302,6 +440,8 @@ void rr_destroy(rr_ctx* c) {
     if (c->ev_shadow_done) cudaEventDestroy(c->ev_shadow_done);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite); cudaFree(c->d_obj_r2); cudaFree(c->d_obj_rows);
+    cudaFree(c->d_clusters); cudaFree(c->d_cluster_vis); cudaFree(c->d_cluster_faces);
+    cudaFree(c->d_rowmask); cudaFree(c->d_rowpfx);
     cudaFree(c->d_atlas); cudaFree(c->d_nums); cudaFree(c->d_sizes); cudaFree(c->d_upload);
     cudaFree(c->d_lights); cudaFree(c->d_lightlite);
     if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
@@ -332,6 +472,11 @@ int rr_scene_alloc(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
     if ((r = dev_alloc(c->d_objlite, n_objs))) return r;
     if ((r = dev_alloc(c->d_obj_r2, n_objs))) return r;
     if ((r = dev_alloc(c->d_obj_rows, n_objs))) return r;
+    c->n_clusters = (n_tris + CLUSTER_TRIS - 1) / CLUSTER_TRIS;
+    if ((r = dev_alloc(c->d_clusters, (size_t)c->n_clusters))) return r;
+    if ((r = dev_alloc(c->d_cluster_vis, (size_t)c->n_clusters + 2))) return r;
+    if ((r = dev_alloc(c->d_cluster_faces, (size_t)c->n_clusters))) return r;
+    CU(cudaMemsetAsync(c->d_clusters, 0, std::max<size_t>(1, c->n_clusters) * sizeof(ClusterBox), c->stream));   // hi.w = 0: never culled until built
     CU(cudaMemsetAsync(c->d_obj_r2, 0, std::max<size_t>(1, n_objs) * 4, c->stream));
     // projected triangles: main pass needs <= 2T; a shadow pass (all lights at once) up to 12T per light in the worst
     // case (the reference allocates 12T, object_context.cpp:354). Default 6T + slack ; overflow is detected and reported.
@@ -354,6 +499,11 @@ int rr_scene_write_tris(rr_ctx* c, uint32_t first, uint32_t count, const rr_tria
     CU(cudaMemcpyAsync(c->d_tris + first, tris, (size_t)count * sizeof(rr_triangle), cudaMemcpyHostToDevice, c->stream));
     k_repack<<<(count + 255) / 256, 256, 0, c->stream>>>(c->d_tris, first, count, c->d_pa, c->d_pb, c->d_pc, c->d_obj_r2, c->n_objs);
     c->launches++;
+    {   // bounding boxes of the clusters this write touches
+        const uint32_t cl0 = first / CLUSTER_TRIS, cl1 = (first + count - 1) / CLUSTER_TRIS;
+        k_cluster_bounds<<<cl1 - cl0 + 1, CLUSTER_TRIS, 0, c->stream>>>(c->d_pa, c->d_pb, c->d_pc, c->n_tris, cl0, c->d_clusters);
+        c->launches++;
+    }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));      // caller may free `tris` on return (the reference keeps staging alive instead, object.cpp:729)
     return RR_OK;
@@ -475,18 +625,18 @@ int rr_lights_write(rr_ctx* c, const rr_light* lights, uint32_t n_active) {
 static int shadow_pass(rr_ctx* c, int only_static) {
     uint32_t* buffer = only_static ? c->d_shadow_static : c->d_shadow_dyn;
     const uint32_t total_pairs = 6u * (only_static ? c->n_static : c->n_shadow);
-    const uint32_t chunk = c->cfg.face_world > 1 ? (total_pairs + c->cfg.face_world - 1) / c->cfg.face_world : total_pairs;
+    const bool sharded = c->cfg.face_world > 1 && !only_static;      // static cubemaps are cached: every context renders all of theirs
     std::vector<ShadowLight> sel;
     uint32_t slab = 0;
     for (size_t i = 0; i < c->lights.size(); i++) {
         const rr_light& l = c->lights[i];
         const bool in_pass = only_static ? (l.shadow && l.is_static) : (l.shadow == 1);
         if (!in_pass) continue;
-        // (light, face) pairs are owned in contiguous chunks of ceil(total / face_world) so that the owned part of the
-        // cubemap buffer is one contiguous range (in-place all-gather across contexts)
+        // (light, face) pairs are owned either in contiguous chunks of ceil(total / face_world), so that the owned part of
+        // the cubemap buffer is one contiguous range (in-place all-gather across contexts), or round-robin (peer-memory push)
         uint32_t mask = 0;
         for (uint32_t kk = 0; kk < 6; kk++)
-            if (c->cfg.face_world <= 1 || ((slab * 6 + kk) / chunk) == (uint32_t)c->cfg.face_rank) mask |= 1u << kk;
+            if (!sharded || owns_pair(c, slab * 6 + kk, total_pairs)) mask |= 1u << kk;
         if (mask) sel.push_back(ShadowLight{l.pos[0], l.pos[1], l.pos[2], slab, mask});
         slab++;
     }
@@ -508,6 +658,15 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         sp.fragcnt = c->d_sfragcnt;
         sp.cutdown = c->d_scutdown; sp.cap_cut = c->cap_cut; sp.counters = c->d_scounters;
         sp.buffer = buffer;
+        sp.cluster_faces = nullptr;
+        if (sharded && c->n_objs && c->n_clusters) {   // clusters whose bounding box cannot reach a face rendered here are skipped whole
+            ObjFacesParams fp;
+            fp.n_lights = nl;
+            for (int k = 0; k < nl; k++) fp.lights[k] = sel[first + k];
+            k_cluster_faces<<<(c->n_clusters + 127) / 128, 128, 0, st>>>(c->d_clusters, c->n_clusters, c->d_objlite, c->n_objs, fp, c->d_cluster_faces);
+            c->launches++;
+            sp.cluster_faces = c->d_cluster_faces;
+        }
         k_shadow_setup<<<(c->n_tris + 127) / 128, 128, 0, st>>>(sp);
         c->launches++;
         if ((r = scan_big(c, st, c->d_scounters, c->d_sfragcnt, c->d_sbiglist, c->d_sbigslot, c->d_sscan_lookback, CTR_S_NFRAG, sp.cap_frags))) return r;
@@ -515,7 +674,7 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         dp.biglist = c->d_sbiglist; dp.bigslot = c->d_sbigslot;
         dp.n_index = CTR_S_NFRAG;
         dp.depth = buffer; dp.ids = nullptr; dp.width = (float)c->L; dp.height = (float)c->L; dp.W = c->L;
-        dp.row_lo = 0; dp.row_hi = c->L;
+        dp.row_lo = 0; dp.row_hi = c->L; dp.rowmask = nullptr; dp.rowbit = 0;
         if ((r = raster<RM_SHADOW>(c, st, dp))) return r;
     }
     CU(cudaGetLastError());
@@ -533,13 +692,25 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     CU(cudaEventRecord(c->ev[EV_SH0], c->stream2));
     const size_t slab = (size_t)6 * c->L * c->L;
+    int mgb = 0;
+    uint32_t mg_epoch = 0;
+    if (c->mg.connected) {
+        // peer-memory exchange: this epoch's cubemaps live in buffer (epoch & 1). Peers may only be written once they are
+        // done with the frame that last read that buffer, which their flag for the previous epoch implies.
+        mg_epoch = ++c->mg.shadow_epoch;
+        mgb = (int)(mg_epoch & 1u);
+        c->d_shadow_dyn = c->mg.shadow[mgb];
+        if (mg_epoch > 1 && (r = mg_wait(c, c->stream2, true, mg_epoch - 1))) return r;
+    }
     if (!c->lights.empty()) {                                                              // engine.cpp:1611-1626
         // a full clear (not only the owned faces) keeps the buffer defined for the all-gather that follows
-        if (c->n_shadow && (r = fill_u32(c, c->stream2, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
+        if (c->mg.connected) { if (c->n_shadow && (r = mg_fill_owned(c, c->stream2, c->d_shadow_dyn))) return r; }
+        else if (c->n_shadow && (r = fill_u32(c, c->stream2, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
         if (static_lights_dirty && c->n_static && (r = fill_u32(c, c->stream2, c->d_shadow_static, slab * c->n_static, 0xFFFFFFFFu))) return r;
     }
     if (c->n_shadow && (r = shadow_pass(c, 0))) return r;                                  // engine.cpp:1629-1697
     if (static_lights_dirty && c->n_static && (r = shadow_pass(c, 1))) return r;           // engine.cpp:1699-1784
+    if (c->mg.connected && c->n_shadow && (r = mg_push(c, c->stream2, mgb, mg_epoch))) return r;
     CU(cudaEventRecord(c->ev[EV_SH1], c->stream2));
     CU(cudaEventRecord(c->ev_shadow_done, c->stream2));
     c->have_shadow_ev = true;
@@ -578,11 +749,19 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     sp.counters = c->d_counters; sp.lookback = c->d_lookback;
     sp.depth = c->d_depth[c->cur]; sp.row_lo = row0; sp.row_hi = row1;
     sp.obj_rows = nullptr;
-    if ((row0 > 0 || row1 < c->H) && c->n_objs) {      // sort-first band: objects that cannot touch the rasterised rows are not set up here
+    sp.rowmask = c->d_rowmask;
+    if ((row0 > 0 || row1 < c->H || c->d_rowpfx) && c->n_objs) {      // sort-first band: objects that cannot touch the rasterised rows are not set up here
         k_obj_rows<<<(c->n_objs + 127) / 128, 128, 0, c->stream>>>(c->d_objlite, c->d_obj_r2, c->n_objs, cam, (float)c->H, c->fov,
-                                                                    (float)c->cfg.depth_icutoff, c->d_obj_rows);
+                                                                    (float)c->cfg.depth_icutoff, c->d_obj_rows, c->d_rowpfx, c->H);
         c->launches++;
         sp.obj_rows = c->d_obj_rows;
+    }
+    sp.cluster_vis = nullptr;
+    if (c->n_objs && c->n_clusters) {                  // cluster culling: off-screen geometry, and rows rasterised elsewhere
+        k_cluster_vis<<<(c->n_clusters + 127) / 128, 128, 0, c->stream>>>(c->d_clusters, c->n_clusters, c->d_objlite, c->n_objs, cam, (float)c->W, (float)c->H,
+                                                                          c->fov, (float)c->cfg.depth_icutoff, c->d_rowpfx, row0, row1, c->d_cluster_vis);
+        c->launches++;
+        sp.cluster_vis = c->d_cluster_vis;
     }
     sp.sl.samples = c->d_samples; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
     sp.sl.desc = c->d_sample_desc; sp.sl.cap_desc = c->cap_frags; sp.sl.desc_count = c->d_counters + CTR_NDESC; sp.sl.fragcnt = c->d_fragcnt;
@@ -596,11 +775,11 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     rp.n_index = CTR_NFRAG;
     rp.depth = c->d_depth[c->cur]; rp.ids = c->d_ids[c->cur];
     rp.width = (float)c->W; rp.height = (float)c->H; rp.W = c->W;
-    rp.row_lo = row0; rp.row_hi = row1;
+    rp.row_lo = row0; rp.row_hi = row1; rp.rowmask = c->d_rowmask; rp.rowbit = ROW_NEEDED;
     if ((r = raster<RM_DEPTH>(c, c->stream, rp))) return r;
     CU(cudaEventRecord(c->ev[EV_DEPTH], c->stream));
-    rp.row_lo = band0; rp.row_hi = band1;
-    k_ids_list<<<grid_for(c, 8), 256, 0, c->stream>>>(sp.sl, c->d_depth[c->cur], c->d_ids[c->cur], c->W, band0, band1);
+    rp.row_lo = band0; rp.row_hi = band1; rp.rowbit = ROW_OWNED;
+    k_ids_list<<<grid_for(c, 8), 256, 0, c->stream>>>(sp.sl, c->d_depth[c->cur], c->d_ids[c->cur], c->W, band0, band1, c->d_rowmask);
     c->launches++;
     if ((r = raster<RM_IDS>(c, c->stream, rp))) return r;
     CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
@@ -609,6 +788,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     hp.tris = c->d_tris; hp.objs = c->d_objs; hp.objlite = c->d_objlite; hp.lightlite = c->d_lightlite; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
     hp.depth = c->d_depth[c->cur]; hp.ids = c->d_ids[c->cur];
     hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
+    if (c->mg.connected) c->d_rgba8 = c->mg.rank == 0 ? c->mg.fb[c->mg_target] : c->mg.fb0[c->mg_target];   // every context stores into rank 0's target
     hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
     hp.atlas.texels = c->d_atlas; hp.atlas.nums = c->d_nums; hp.atlas.sizes = c->d_sizes; hp.atlas.mip_start = c->mipmap_start;
     hp.lights = c->d_lights; hp.n_lights = (int)c->lights.size();
@@ -621,7 +801,8 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     hp.shadow_bias = c->cfg.shadow_bias; hp.shadow_bias_max = powf(c->cfg.shadow_bias, c->cfg.shadow_exp);
     hp.linear = (c->cfg.test_linear && c->cfg.use_linear_rendering) ? 1 : 0;
     hp.no_ssao = c->cfg.no_ssao;
-    hp.row0 = row0; hp.row1 = row1; hp.band_y0 = band0; hp.band_y1 = band1;
+    hp.row0 = row0; hp.row1 = row1; hp.band_y0 = band0; hp.band_y1 = band1; hp.rowmask = c->d_rowmask;
+    if (c->mg.connected) ++c->mg.draw_epoch;
     if (hp.n_lights > 0 && (!c->d_lights)) return fail(RR_ERR_INVALID, "lights not written");
     hp.shade_list = c->d_shade_list; hp.shade_count = c->d_counters + CTR_NSHADE;
     CU(cudaMemsetAsync(c->d_counters + CTR_NSHADE, 0, 4, c->stream));
@@ -633,7 +814,13 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
         k_shade_pre<<<grid, 256, 0, c->stream>>>(hp);
     }
     if ((r = join_shadows(c))) return r;                                                   // the cubemaps must be complete before shading
+    if (c->mg.connected && c->mg.shadow_epoch && (r = mg_wait(c, c->stream, true, c->mg.shadow_epoch))) return r;   // ... the peers' faces too
     k_shade<<<grid_for(c, 12), 128, 0, c->stream>>>(hp);
+    if (c->mg.connected && c->mg.rank != 0) {                  // this context's rows are in rank 0's colour target
+        k_signal_flag<<<1, 1, 0, c->stream>>>(&c->mg.peer_ctrl[0]->draw_flag[c->mg.rank], c->mg.draw_epoch);
+        c->launches++;
+    }
+    if (c->mg.connected && c->mg.rank == 0 && (r = mg_wait(c, c->stream, false, c->mg.draw_epoch))) return r;         // composite complete
     CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
     c->launches += 3;
     c->have_frame_ev = true;
@@ -657,6 +844,11 @@ int rr_sync(rr_ctx* c) {
     CU(cudaStreamSynchronize(c->stream2));
     CU(cudaStreamSynchronize(c->stream3));
     c->copy_pending[0] = c->copy_pending[1] = false;
+    if (c->mg.connected) {
+        uint32_t perr = 0;
+        CU(cudaMemcpy(&perr, &c->mg.ctrl->error, 4, cudaMemcpyDeviceToHost));
+        if (perr) return fail(RR_ERR_PEER, "multi-GPU exchange: a peer context did not deliver its faces / rows within the time limit (rank %d of %d)", c->mg.rank, c->mg.world);
+    }
     const uint32_t ovf = c->h_counters[CTR_OVERFLOW] | c->h_counters[CTR_COUNT + CTR_OVERFLOW];
     if (ovf)
         return fail(RR_ERR_OVERFLOW, "raster storage exhausted (flags %u): fragments cap %u, projected-triangle cap %u", ovf, c->cap_frags, c->cap_cut);
@@ -763,6 +955,157 @@ int rr_shadows_done(rr_ctx* c) {
     return RR_OK;
 }
 
+// ---- multi-GPU exchange over peer memory ----------------------------------------------------------------------------
+static int mg_alloc(rr_ctx* c) {
+    if (c->mg.exported) return RR_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream2));
+    const size_t P = (size_t)c->W * c->H;
+    c->mg.shadow_words = std::max<size_t>((size_t)6 * c->L * c->L * c->n_shadow, 4);
+    uint32_t* sh = nullptr;
+    CU(cudaMalloc((void**)&sh, c->mg.shadow_words * 2 * 4));
+    c->mg.shadow[0] = sh; c->mg.shadow[1] = sh + c->mg.shadow_words;
+    CU(cudaMemset(sh, 0xFF, c->mg.shadow_words * 2 * 4));
+    uchar4* fb = nullptr;
+    CU(cudaMalloc((void**)&fb, P * 2 * 4));
+    c->mg.fb[0] = fb; c->mg.fb[1] = fb + P;
+    CU(cudaMemset(fb, 0, P * 2 * 4));
+    CU(cudaMalloc((void**)&c->mg.ctrl, sizeof(MgCtrl)));
+    CU(cudaMemset(c->mg.ctrl, 0, sizeof(MgCtrl)));
+    c->mg.exported = true;
+    return RR_OK;
+}
+
+int rr_mgpu_export(rr_ctx* c, rr_mgpu_handle* out) {
+    if (!c || !out) return fail(RR_ERR_INVALID, "null argument");
+    if (c->mg.connected) return fail(RR_ERR_INVALID, "rr_mgpu_export: already connected");
+    int r;
+    if ((r = mg_alloc(c))) return r;
+    memset(out, 0, sizeof *out);
+    static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle does not fit rr_mgpu_handle");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->mg.shadow[0])); memcpy(out->shadow, &h, sizeof h);
+    CU(cudaIpcGetMemHandle(&h, c->mg.fb[0])); memcpy(out->fb, &h, sizeof h);
+    CU(cudaIpcGetMemHandle(&h, c->mg.ctrl)); memcpy(out->ctrl, &h, sizeof h);
+    out->shadow_bytes = c->mg.shadow_words * 2 * 4; out->fb_bytes = (uint64_t)c->W * c->H * 2 * 4;
+    out->device = c->cfg.device; out->n_shadow = (int32_t)c->n_shadow; out->width = c->W; out->height = c->H; out->light_dim = c->L;
+    return RR_OK;
+}
+
+// common tail of rr_mgpu_connect / rr_mgpu_connect_local once the peer pointers are in place
+static int mg_finish_connect(rr_ctx* c, int rank, int world) {
+    if (c->cfg.face_world != world || c->cfg.face_rank != rank)
+        return fail(RR_ERR_INVALID, "rr_mgpu_connect: rr_config.face_rank/face_world (%d/%d) must equal rank/world (%d/%d)", c->cfg.face_rank, c->cfg.face_world, rank, world);
+    c->mg.rank = rank; c->mg.world = world;
+    uint32_t pairs[6 * SHADOW_MAX_LIGHTS];
+    if (c->n_shadow > SHADOW_MAX_LIGHTS) return fail(RR_ERR_INVALID, "rr_mgpu_connect: more than %d shadow-casting lights", SHADOW_MAX_LIGHTS);
+    const int np = mg_owned_pairs(c, pairs);
+    const size_t chunks = std::max<size_t>(1, (size_t)np * ((size_t)c->L * c->L / MG_PUSH_CHUNK_WORDS));
+    if (((size_t)c->L * c->L) % MG_PUSH_CHUNK_WORDS) return fail(RR_ERR_INVALID, "rr_mgpu_connect: light_dim^2 must be a multiple of %d", MG_PUSH_CHUNK_WORDS);
+    for (int b = 0; b < 2; b++) {
+        CU(cudaMalloc((void**)&c->mg.prev_dirty[b], chunks));
+        CU(cudaMemset(c->mg.prev_dirty[b], 0, chunks));
+    }
+    // the context now renders into the exchange buffers
+    c->mg.saved_shadow_dyn = c->d_shadow_dyn; c->mg.saved_ext_shadow = c->ext_shadow_dyn; c->mg.saved_shadow_words = c->shadow_dyn_words;
+    c->mg.saved_rgba8 = c->d_rgba8; c->mg.saved_ext_rgba8 = c->ext_rgba8;
+    c->d_shadow_dyn = c->mg.shadow[0]; c->ext_shadow_dyn = true; c->shadow_dyn_words = c->mg.shadow_words;
+    c->d_rgba8 = rank == 0 ? c->mg.fb[0] : c->mg.fb0[0]; c->ext_rgba8 = true;
+    c->mg.shadow_epoch = c->mg.draw_epoch = 0;
+    c->mg.connected = true;
+    return RR_OK;
+}
+
+int rr_mgpu_connect(rr_ctx* c, int rank, int world, const rr_mgpu_handle* handles) {
+    if (!c || !handles) return fail(RR_ERR_INVALID, "null argument");
+    if (world < 1 || world > MG_MAX_WORLD || rank < 0 || rank >= world) return fail(RR_ERR_INVALID, "rr_mgpu_connect: bad rank/world %d/%d", rank, world);
+    if (!c->mg.exported) return fail(RR_ERR_INVALID, "rr_mgpu_connect before rr_mgpu_export");
+    if (c->mg.connected) return fail(RR_ERR_INVALID, "rr_mgpu_connect: already connected");
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t P = (size_t)c->W * c->H;
+    for (int q = 0; q < world; q++) {
+        const rr_mgpu_handle& h = handles[q];
+        if (h.width != c->W || h.height != c->H || h.light_dim != c->L || h.n_shadow != (int32_t)c->n_shadow)
+            return fail(RR_ERR_INVALID, "rr_mgpu_connect: rank %d was created with a different frame / cubemap / light configuration", q);
+        if (q == rank) continue;
+        cudaIpcMemHandle_t ih;
+        void* p = nullptr;
+        memcpy(&ih, h.shadow, sizeof ih);
+        CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        c->mg.opened[q][0] = p;
+        c->mg.peer_shadow[q][0] = (uint32_t*)p; c->mg.peer_shadow[q][1] = (uint32_t*)p + c->mg.shadow_words;
+        memcpy(&ih, h.ctrl, sizeof ih);
+        CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        c->mg.opened[q][1] = p;
+        c->mg.peer_ctrl[q] = (MgCtrl*)p;
+        if (q == 0) {
+            memcpy(&ih, h.fb, sizeof ih);
+            CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+            c->mg.opened[q][2] = p;
+            c->mg.fb0[0] = (uchar4*)p; c->mg.fb0[1] = (uchar4*)p + P;
+        }
+    }
+    c->mg.ipc = true;
+    return mg_finish_connect(c, rank, world);
+}
+
+int rr_mgpu_connect_local(rr_ctx* const* ctxs, int world) {
+    if (!ctxs || world < 1 || world > MG_MAX_WORLD) return fail(RR_ERR_INVALID, "rr_mgpu_connect_local: bad arguments");
+    int r;
+    for (int k = 0; k < world; k++) {
+        if (!ctxs[k]) return fail(RR_ERR_INVALID, "null ctx");
+        if (ctxs[k]->mg.connected) return fail(RR_ERR_INVALID, "rr_mgpu_connect_local: context %d already connected", k);
+        if (ctxs[k]->W != ctxs[0]->W || ctxs[k]->H != ctxs[0]->H || ctxs[k]->L != ctxs[0]->L || ctxs[k]->n_shadow != ctxs[0]->n_shadow)
+            return fail(RR_ERR_INVALID, "rr_mgpu_connect_local: context %d has a different frame / cubemap / light configuration", k);
+        if ((r = mg_alloc(ctxs[k]))) return r;
+    }
+    for (int k = 0; k < world; k++)
+        for (int q = 0; q < world; q++) {
+            if (q == k || ctxs[q]->cfg.device == ctxs[k]->cfg.device) continue;
+            CU(cudaSetDevice(ctxs[k]->cfg.device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RR_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", ctxs[k]->cfg.device, ctxs[q]->cfg.device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    for (int k = 0; k < world; k++) {
+        rr_ctx* c = ctxs[k];
+        for (int q = 0; q < world; q++) {
+            if (q == k) continue;
+            c->mg.peer_shadow[q][0] = ctxs[q]->mg.shadow[0]; c->mg.peer_shadow[q][1] = ctxs[q]->mg.shadow[1];
+            c->mg.peer_ctrl[q] = ctxs[q]->mg.ctrl;
+        }
+        c->mg.fb0[0] = ctxs[0]->mg.fb[0]; c->mg.fb0[1] = ctxs[0]->mg.fb[1];
+        c->mg.ipc = false;
+        CU(cudaSetDevice(c->cfg.device));
+        if ((r = mg_finish_connect(c, k, world))) return r;
+    }
+    return RR_OK;
+}
+
+int rr_mgpu_disconnect(rr_ctx* c) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    if (c->stream3) cudaStreamSynchronize(c->stream3);
+    if (c->mg.connected) {
+        c->d_shadow_dyn = c->mg.saved_shadow_dyn; c->ext_shadow_dyn = c->mg.saved_ext_shadow; c->shadow_dyn_words = c->mg.saved_shadow_words;
+        c->d_rgba8 = c->mg.saved_rgba8; c->ext_rgba8 = c->mg.saved_ext_rgba8;
+        if (c->mg.ipc)
+            for (int q = 0; q < MG_MAX_WORLD; q++)
+                for (int i = 0; i < 3; i++) if (c->mg.opened[q][i]) { cudaIpcCloseMemHandle(c->mg.opened[q][i]); c->mg.opened[q][i] = nullptr; }
+        for (int b = 0; b < 2; b++) { cudaFree(c->mg.prev_dirty[b]); c->mg.prev_dirty[b] = nullptr; }
+        c->mg.connected = false;
+    }
+    if (c->mg.exported) {
+        cudaFree(c->mg.shadow[0]); cudaFree(c->mg.fb[0]); cudaFree(c->mg.ctrl);
+        c->mg.shadow[0] = c->mg.shadow[1] = nullptr; c->mg.fb[0] = c->mg.fb[1] = nullptr; c->mg.ctrl = nullptr;
+        c->mg.exported = false;
+    }
+    cudaGetLastError();
+    return RR_OK;
+}
+
 void* rr_host_alloc(size_t nbytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) { fail(RR_ERR_OOM, "rr_host_alloc(%zu) failed", nbytes); return nullptr; }
@@ -783,6 +1126,30 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     // frame is drawn into one of two colour targets while the copy stream is still moving the previous frame out of the
     // other. On return the PREVIOUS call's host buffer is complete; rr_sync() completes this one.
     const int k = c->fb_parity;
+    if (c->mg.connected) {
+        // multi-GPU: every context stores its rows into target k on rank 0; rank 0 alone reads the composite back. Target k is
+        // free again once rank 0's copy of two frames ago is done, which rank 0's main stream waits for before it forks this
+        // frame's shadow work — and no peer can shade this frame before rank 0 has delivered its faces.
+        c->mg_target = k;
+        if (c->mg.rank == 0 && c->copy_pending[k]) CU(cudaStreamWaitEvent(c->stream, c->ev_copy_done[k], 0));
+        if (with_shadows && (r = rr_frame_shadows(c, 0))) return r;
+        if ((r = rr_frame_draw(c, c_pos, c_rot, clear_rgba))) return r;
+        if (c->mg.rank == 0) {
+            CU(cudaEventRecord(c->ev_draw_done, c->stream));
+            CU(cudaStreamWaitEvent(c->stream3, c->ev_draw_done, 0));
+            CU(cudaMemcpyAsync(host_rgba8, c->mg.fb[k], (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream3));
+            CU(cudaEventRecord(c->ev_copy_done[k], c->stream3));
+            c->copy_pending[k] = true;
+            if (c->copy_pending[k ^ 1]) { CU(cudaEventSynchronize(c->ev_copy_done[k ^ 1])); c->copy_pending[k ^ 1] = false; }
+        } else {                                          // at most one frame in flight on the host side here too
+            if (!c->ev_frame_done[0]) for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_frame_done[i], cudaEventDisableTiming));
+            CU(cudaEventRecord(c->ev_frame_done[k], c->stream));
+            if (c->copy_pending[k ^ 1]) { CU(cudaEventSynchronize(c->ev_frame_done[k ^ 1])); c->copy_pending[k ^ 1] = false; }
+            c->copy_pending[k] = true;
+        }
+        c->fb_parity ^= 1;
+        return rr_swap_buffers(c);
+    }
     if (!c->ext_rgba8) {
         if (!c->d_rgba8_alt) CU(cudaMalloc((void**)&c->d_rgba8_alt, (size_t)c->W * c->H * 4));
         std::swap(c->d_rgba8, c->d_rgba8_alt);

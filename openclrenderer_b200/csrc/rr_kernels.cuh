@@ -24,6 +24,9 @@ enum {
     CTR_COUNT = 16
 };
 
+// per-row ownership bits of the sort-first split (rr_config.band_tile): built on the host at rr_create
+enum { ROW_NEEDED = 1, ROW_OWNED = 2 };
+
 struct CamParams {
     float3 pos;
     RotSC rot;
@@ -86,7 +89,8 @@ __global__ void __launch_bounds__(128) k_objlite(const rr_obj_desc* __restrict__
 // for this frame's camera. A triangle of an object whose rows cannot touch [row_lo, row_hi) is not set up at all on this
 // context — it cannot produce a fragment there. rows = (first, last) inclusive; (INT_MIN, INT_MAX) when in doubt.
 __global__ void __launch_bounds__(128) k_obj_rows(const ObjLite* __restrict__ objs, const uint32_t* __restrict__ obj_r2_bits, uint32_t n,
-                                                  CamParams cam, float height, float fov, float icut, int2* __restrict__ rows) {
+                                                  CamParams cam, float height, float fov, float icut, int2* __restrict__ rows,
+                                                  const int* __restrict__ rowpfx, int H) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const ObjLite G = objs[i];
@@ -98,8 +102,127 @@ __global__ void __launch_bounds__(128) k_obj_rows(const ObjLite* __restrict__ ob
         const float a = (c.y - R) * fov, b = (c.y + R) * fov;
         const float lo = fminf(a / zn, a / zf) + height * 0.5f, hi = fmaxf(b / zn, b / zf) + height * 0.5f;
         r = make_int2((int)fmaxf(floorf(lo) - 4.f, -1e9f), (int)fminf(ceilf(hi) + 4.f, 1e9f));
+        // interleaved bands: rowpfx[y] = number of rows < y this context rasterises; an object with none in its range is
+        // reported as the empty range
+        if (rowpfx) {
+            const int a = max(r.x, 0), b = min(r.y, H - 1);
+            if (a > b || rowpfx[b + 1] - rowpfx[a] == 0) r = make_int2(INT_MAX, INT_MIN);
+        }
     }
     rows[i] = r;
+}
+
+// ---- clusters: 128 consecutive triangles with an object-space bounding box ---------------------------------------------
+// Built once per rr_scene_write_tris. Every frame one thread per cluster transforms the 8 box corners exactly the way the
+// setup kernels transform vertices and decides, conservatively (pixel / unit margins far above the rounding differences
+// between corner and vertex arithmetic), that NONE of the cluster's triangles can produce a fragment this context needs:
+//   main view : the box lies entirely in front of the near plane and inside depth_far (so every triangle is unclipped:
+//               exactly one projected-triangle slot each, cl2.cl:4342) and its projection is off screen (the reference
+//               rejects each of its triangles, cl2.cl:4356-4359) or touches no row this context rasterises;
+//   shadows   : no point of the box can be assigned by ret_cubeface to a cube face rendered here.
+// Culled clusters cost a block one load and one flag: this is what makes the replicated setup stage scale in the sort-
+// first split, and it removes off-screen geometry on a single GPU. Clusters that span two objects are never culled.
+#define CLUSTER_TRIS 128
+struct ClusterBox { float4 lo; float4 hi; };   // lo.xyz / hi.xyz object space; lo.w = object id bits; hi.w = 1.f when usable
+
+__global__ void __launch_bounds__(CLUSTER_TRIS) k_cluster_bounds(const float4* __restrict__ pa, const float4* __restrict__ pb, const float2* __restrict__ pc,
+                                                                 uint32_t n_tris, uint32_t first_cluster, ClusterBox* __restrict__ out) {
+    __shared__ float s_red[6][CLUSTER_TRIS / 32];
+    __shared__ int s_ok[CLUSTER_TRIS / 32];
+    const uint32_t cl = first_cluster + blockIdx.x;
+    const uint32_t tri = cl * CLUSTER_TRIS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float INF = __int_as_float(0x7f800000);
+    float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
+    const uint32_t oid0 = __float_as_uint(__ldg(pc + (size_t)cl * CLUSTER_TRIS).y);
+    bool ok = true;
+    if (tri < n_tris) {
+        const float4 a = __ldg(pa + tri), b = __ldg(pb + tri);
+        const float2 c = __ldg(pc + tri);
+        const float vx[3] = {a.x, a.w, b.z}, vy[3] = {a.y, b.x, b.w}, vz[3] = {a.z, b.y, c.x};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            mn[0] = fminf(mn[0], vx[k]); mx[0] = fmaxf(mx[0], vx[k]);
+            mn[1] = fminf(mn[1], vy[k]); mx[1] = fmaxf(mx[1], vy[k]);
+            mn[2] = fminf(mn[2], vz[k]); mx[2] = fmaxf(mx[2], vz[k]);
+            ok = ok && isfinite(vx[k]) && isfinite(vy[k]) && isfinite(vz[k]);
+        }
+        ok = ok && __float_as_uint(c.y) == oid0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], d));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], d));
+        }
+    const bool wok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        for (int k = 0; k < 3; k++) { s_red[k][warp] = mn[k]; s_red[3 + k][warp] = mx[k]; }
+        s_ok[warp] = wok;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool all = true;
+        for (int w = 0; w < CLUSTER_TRIS / 32; w++) {
+            for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], s_red[k][w]); mx[k] = fmaxf(mx[k], s_red[3 + k][w]); }
+            all = all && s_ok[w];
+        }
+        ClusterBox bx;
+        bx.lo = make_float4(mn[0], mn[1], mn[2], __uint_as_float(oid0));
+        bx.hi = make_float4(mx[0], mx[1], mx[2], all ? 1.f : 0.f);
+        out[cl] = bx;
+    }
+}
+
+// corner k (bit 0: x, bit 1: y, bit 2: z) of a cluster box in world space, computed like a vertex (cl2.cl:505-507)
+__device__ __forceinline__ float3 cluster_corner_world(const ClusterBox& b, int k, const ObjLite& G) {
+    const float3 v = make_float3((k & 1) ? b.hi.x : b.lo.x, (k & 2) ? b.hi.y : b.lo.y, (k & 4) ? b.hi.z : b.lo.z);
+    return rot_quat_n(v * G.pos_scale.w, G.nquat) + make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
+}
+
+// main view: vis[cluster] = 0 when the cluster can be skipped by k_setup_main (its triangles still take their slots)
+__global__ void __launch_bounds__(128) k_cluster_vis(const ClusterBox* __restrict__ boxes, uint32_t n_clusters, const ObjLite* __restrict__ objs, uint32_t n_objs,
+                                                     CamParams cam, float width, float height, float fov, float icut,
+                                                     const int* __restrict__ rowpfx, int row_lo, int row_hi, uint8_t* __restrict__ vis) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_clusters) return;
+    const ClusterBox b = boxes[i];
+    const uint32_t oid = __float_as_uint(b.lo.w);
+    uint8_t v = 1;
+    if (b.hi.w == 1.f && oid < n_objs) {
+        const ObjLite G = objs[oid];
+        const float3 gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
+        const float INF = __int_as_float(0x7f800000);
+        float zmin = INF, zmax = -INF, xmin = INF, xmax = -INF, ymin = INF, ymax = -INF, amax = 0.f;
+        bool fin = isfinite(length3(gpos - cam.pos)) && !(length3(gpos - cam.pos) > RR_DEPTH_FAR * 0.999f);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float3 q = rot(cluster_corner_world(b, k, G), cam.pos, cam.rot);
+            zmin = fminf(zmin, q.z); zmax = fmaxf(zmax, q.z);
+            amax = fmaxf(amax, fmaxf(fabsf(q.x), fmaxf(fabsf(q.y), fabsf(q.z))));
+            const float kx = fov / fmaxf(q.z, 1e-3f);
+            const float px = fmaf(q.x, kx, width * 0.5f), py = fmaf(q.y, kx, height * 0.5f);
+            xmin = fminf(xmin, px); xmax = fmaxf(xmax, px); ymin = fminf(ymin, py); ymax = fmaxf(ymax, py);
+            fin = fin && isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && isfinite(px) && isfinite(py);
+        }
+        // camera-space slack for the arithmetic differences between corners and vertices, then its worst-case effect in pixels
+        const float eps = 1e-4f * amax + 1e-3f;
+        if (fin && zmin - eps > icut + 1.f && zmax + eps < RR_DEPTH_FAR * 0.999f) {
+            const float slack = 4.f + 4.f * eps * fov / (zmin - eps) * (1.f + amax / (zmin - eps));
+            if (isfinite(slack)) {
+                bool culled = xmax + slack < 0.f || xmin - slack >= width || ymax + slack < 0.f || ymin - slack >= height;
+                if (!culled) {
+                    // rows the triangles' boxes [round(min) - 1, round(max)] can touch, clamped like calc_min_max
+                    const int a = max((int)fmaxf(floorf(ymin - slack) - 2.f, -1e9f), 0), e = min((int)fminf(ceilf(ymax + slack) + 2.f, 1e9f), (int)height - 1);
+                    if (a > e || e < row_lo || a >= row_hi) culled = true;
+                    else if (rowpfx && rowpfx[e + 1] - rowpfx[a] == 0) culled = true;
+                }
+                v = culled ? 0 : 1;
+            }
+        }
+    }
+    vis[i] = v;
 }
 
 // One clipped + projected triangle after culling. keep == false -> no storage written, no fragments.
@@ -175,6 +298,7 @@ template <bool REC>
 struct InlineRaster {
     InlineQueue* q; int count;  // count is warp-uniform
     int op; float width, height; uint32_t* base; size_t face_stride; int row_lo, row_hi;
+    const uint8_t* rowmask;     // interleaved sort-first ownership: bit 0 = row rasterised here (nullptr: every row of [row_lo, row_hi))
     SampleList sl;
 
     // executed by all 32 lanes; lanes with !valid only take part in the warp collectives
@@ -209,8 +333,10 @@ struct InlineRaster {
         if (valid) {
             const float w = width;
             const int rlo = row_lo, rhi = row_hi;
+            const uint8_t* rm = rowmask;
             scan_chunk(g.mm, op, 0u, [&](float x, float y) {
                 if ((int)y < rlo || (int)y >= rhi) return;
+                if (rm && !(rm[(int)y] & 1)) return;
                 if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
                     const float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
                     const uint32_t d = sat_u32(RR_U32MAXF / fd);
@@ -284,6 +410,45 @@ __device__ __forceinline__ unsigned long long lb_pack(uint32_t flag, uint32_t c,
     return ((unsigned long long)flag << 62) | ((unsigned long long)c << 35) | (unsigned long long)f;
 }
 
+// Decoupled look-back of k_setup_main's single-pass scan, executed by one full warp of block `bid`: publishes the block's
+// aggregate, sums its predecessors' and publishes the inclusive prefix. The last block also writes the totals.
+__device__ __forceinline__ void setup_lookback(unsigned long long* lookback, uint32_t* counters, uint32_t bid, uint32_t tot_c, uint32_t tot_f,
+                                               uint32_t& base_c, uint32_t& base_f) {
+    const int lane = threadIdx.x & 31;
+    volatile unsigned long long* desc = lookback;
+    base_c = 0; base_f = 0;
+    if (bid == 0) {
+        if (lane == 0) { desc[0] = lb_pack(2, tot_c, tot_f); }
+    } else {
+        if (lane == 0) { desc[bid] = lb_pack(1, tot_c, tot_f); }
+        __threadfence();
+        int look = (int)bid - 1;
+        uint32_t watchdog = 0;
+        while (true) {
+            int idx = look - lane;
+            unsigned long long v = lb_pack(2, 0, 0);
+            if (idx >= 0) {
+                do {
+                    v = desc[idx];
+                    if (++watchdog > (1u << 26)) { atomicOr(&counters[CTR_OVERFLOW], 4u); v = lb_pack(2, 0, 0); break; }
+                } while ((v >> 62) == 0);
+            }
+            const uint32_t flag = (uint32_t)(v >> 62);
+            const unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2);
+            const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+            uint32_t vc = (lane <= first_incl) ? (uint32_t)((v >> 35) & 0x7FFFFFFull) : 0u;
+            uint32_t vf = (lane <= first_incl) ? (uint32_t)(v & 0x7FFFFFFFFull) : 0u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { vc += __shfl_xor_sync(0xffffffffu, vc, d); vf += __shfl_xor_sync(0xffffffffu, vf, d); }
+            base_c += vc; base_f += vf;
+            if (incl_mask) break;
+            look -= 32;
+        }
+        if (lane == 0) { desc[bid] = lb_pack(2, base_c + tot_c, base_f + tot_f); }
+    }
+    if (lane == 0 && bid == gridDim.x - 1) { counters[CTR_NCUT] = base_c + tot_c; counters[CTR_NFRAG] = base_f + tot_f; }
+}
+
 struct SetupMainParams {
     const float4* pa; const float4* pb; const float2* pc;
     const ObjLite* objs;
@@ -298,6 +463,8 @@ struct SetupMainParams {
     uint32_t* depth; int row_lo, row_hi;     // inline depth of small triangles
     SampleList sl;                           // their covered samples, for k_ids_list
     const int2* obj_rows;                    // band mode: per-object row range (k_obj_rows); nullptr = no object culling
+    const uint8_t* rowmask;                  // interleaved bands: per-row ownership bits (ROW_NEEDED | ROW_OWNED); nullptr = contiguous
+    const uint8_t* cluster_vis;              // k_cluster_vis: 0 = the cluster's triangles take their slots but produce nothing here
 };
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainParams P) {
@@ -311,11 +478,22 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     __shared__ uint32_t s_oid[SETUP_THREADS];
     __shared__ InlineQueue s_iq[SETUP_THREADS / 32];
 
+    static_assert(SETUP_THREADS == 2 * CLUSTER_TRIS, "one k_setup_main block == two clusters");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(&P.counters[CTR_TICKET], 1u);
     __syncthreads();
     const uint32_t bid = s_bid;
     const uint32_t tri = bid * SETUP_THREADS + tid;
+    // Both clusters of the block culled: every triangle is unclipped (one projected-triangle slot each, no fragments), so
+    // the block's aggregate is known without touching a vertex and it writes nothing: one warp keeps the scan going.
+    if (P.cluster_vis && !P.cluster_vis[2 * bid] && ((2 * bid + 1) * CLUSTER_TRIS >= P.n_tris || !P.cluster_vis[2 * bid + 1])) {
+        if (warp == 0) {
+            uint32_t bc, bf;
+            setup_lookback(P.lookback, P.counters, bid, min((uint32_t)SETUP_THREADS, P.n_tris - bid * SETUP_THREADS), 0u, bc, bf);
+        }
+        return;
+    }
+    const bool cl_culled = P.cluster_vis && tri < P.n_tris && !P.cluster_vis[tri / CLUSTER_TRIS];
 
     SubTri st0, st1;
     int num = 0;
@@ -329,7 +507,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
         const float3 gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
         bool in_band = true;
         if (P.obj_rows) { const int2 rw = __ldg(P.obj_rows + oid); in_band = !(rw.y < P.row_lo || rw.x >= P.row_hi); }
-        if (in_band && !(length3(gpos - P.cam.pos) > RR_DEPTH_FAR)) {           // cl2.cl:4321
+        if (cl_culled) num = 1;                                                  // slot taken (cl2.cl:4342), nothing kept
+        else if (in_band && !(length3(gpos - P.cam.pos) > RR_DEPTH_FAR)) {       // cl2.cl:4321
             const float sc = G.pos_scale.w;
             const float3 q0 = rot(rot_quat_n(make_float3(a.x, a.y, a.z) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);
             const float3 q1 = rot(rot_quat_n(make_float3(a.w, b.x, b.y) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);
@@ -369,41 +548,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
 
     // decoupled look-back (warp 0)
     if (warp == 0) {
-        volatile unsigned long long* desc = P.lookback;
-        uint32_t base_c = 0, base_f = 0;
-        if (bid == 0) {
-            if (lane == 0) { desc[0] = lb_pack(2, tot_c, tot_f); }
-        } else {
-            if (lane == 0) { desc[bid] = lb_pack(1, tot_c, tot_f); }
-            __threadfence();
-            int look = (int)bid - 1;
-            uint32_t watchdog = 0;
-            while (true) {
-                int idx = look - lane;
-                unsigned long long v = lb_pack(2, 0, 0);
-                if (idx >= 0) {
-                    do {
-                        v = desc[idx];
-                        if (++watchdog > (1u << 26)) { atomicOr(&P.counters[CTR_OVERFLOW], 4u); v = lb_pack(2, 0, 0); break; }
-                    } while ((v >> 62) == 0);
-                }
-                const uint32_t flag = (uint32_t)(v >> 62);
-                const unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2);
-                const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-                uint32_t vc = (lane <= first_incl) ? (uint32_t)((v >> 35) & 0x7FFFFFFull) : 0u;
-                uint32_t vf = (lane <= first_incl) ? (uint32_t)(v & 0x7FFFFFFFFull) : 0u;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { vc += __shfl_xor_sync(0xffffffffu, vc, d); vf += __shfl_xor_sync(0xffffffffu, vf, d); }
-                base_c += vc; base_f += vf;
-                if (incl_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) { desc[bid] = lb_pack(2, base_c + tot_c, base_f + tot_f); }
-        }
-        if (lane == 0) {
-            s_base_c = base_c; s_base_f = base_f; s_tot_f = tot_f;
-            if (bid == gridDim.x - 1) { P.counters[CTR_NCUT] = base_c + tot_c; P.counters[CTR_NFRAG] = base_f + tot_f; }
-        }
+        uint32_t base_c, base_f;
+        setup_lookback(P.lookback, P.counters, bid, tot_c, tot_f, base_c, base_f);
+        if (lane == 0) { s_base_c = base_c; s_base_f = base_f; s_tot_f = tot_f; }
     }
     // stage per-slot data for the cooperative record write
     const uint32_t cid0 = ex_c;    // block-relative; global added below
@@ -471,7 +618,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     __syncthreads();            // every fragcnt word of this block is written: the rasterising lane may now update its flags
     InlineRaster<true> ir;
     ir.q = &s_iq[warp]; ir.count = 0; ir.op = RR_OP_SIZE; ir.width = P.width; ir.height = P.height; ir.base = P.depth; ir.face_stride = 0;
-    ir.row_lo = P.row_lo; ir.row_hi = P.row_hi; ir.sl = P.sl;
+    ir.row_lo = P.row_lo; ir.row_hi = P.row_hi; ir.rowmask = P.rowmask; ir.sl = P.sl;
     ir.push(inl0 && frag_ok, st0, 0u, base_f + ex_f);                 // single-chunk triangles: their one fragment's index
     ir.push(inl1 && frag_ok, st1, 0u, base_f + ex_f + my_f0);
     ir.flush();
@@ -502,6 +649,7 @@ struct RasterParams {
     uint32_t slab_of_light[16];     // RM_SHADOW: record word 0 = light << 8 | face; slab index of each light of the pass
     float width, height; int W;
     int row_lo, row_hi;             // rows this context needs (band +- halo)
+    const uint8_t* rowmask; uint32_t rowbit;   // interleaved bands: rows whose mask has `rowbit` set (nullptr: all of [row_lo, row_hi))
 };
 
 template <int MODE>
@@ -559,13 +707,15 @@ __global__ void __launch_bounds__(256) k_raster_small(const RasterParams P) {
         load_fragment<MODE>(P, f, face, distance, g);
         if (MODE != RM_SHADOW && chunk_rows_outside(g.mm, OP, distance, P.row_lo, P.row_hi)) continue;
         scan_chunk(g.mm, OP, distance, [&](float x, float y) {
+            if (MODE != RM_SHADOW && P.rowmask && !(P.rowmask[(int)y] & P.rowbit)) return;
             if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) emit_sample<MODE>(P, x, y, g.A, g.B, g.C, face, f);
         });
     }
 }
 
 // kernel2 for the triangles the setup kernel rasterised inline: stream their recorded samples instead of walking again.
-__global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const uint32_t* __restrict__ depth, uint32_t* __restrict__ ids, int W, int row_lo, int row_hi) {
+__global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const uint32_t* __restrict__ depth, uint32_t* __restrict__ ids, int W, int row_lo, int row_hi,
+                                                  const uint8_t* __restrict__ rowmask) {
     const uint32_t n = min(*sl.desc_count, sl.cap_desc);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint4 de = sl.desc[i];
@@ -573,6 +723,7 @@ __global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const uin
             const uint2 sm = sl.samples[de.x + j];
             const int row = (int)(sm.x / (uint32_t)W);
             if (row < row_lo || row >= row_hi) continue;
+            if (rowmask && !(rowmask[row] & ROW_OWNED)) continue;
             const uint32_t val = depth[sm.x];
             if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) atomicMax(ids + sm.x, de.z);
         }
@@ -742,6 +893,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_big(const RasterParam
                 if (!walk_pixel(k, k0, width, cw.y, mm, x, y)) continue;
                 const int iy = (int)y;
                 if (MODE != RM_SHADOW && (iy < P.row_lo || iy >= P.row_hi)) continue;
+                if (MODE != RM_SHADOW && P.rowmask && !(P.rowmask[iy] & P.rowbit)) continue;
                 const float4 xa = s_xa[lo], yb = s_yb[lo];
                 if (!point_in_tri(x, y, xa.x, yb.x, xa.y, yb.y, xa.z, yb.z)) continue;
                 emit_sample<MODE>(P, x, y, xa.w, yb.w, cw.x, s_face[lo], s_frag[lo]);
@@ -776,6 +928,8 @@ struct ShadowSetupParams {
     float4* cutdown; uint32_t cap_cut;
     uint32_t* counters;
     uint32_t* buffer;                        // cubemap buffer of this pass (inline raster of small triangles)
+    const uint4* cluster_faces;              // face sharding: byte li of cluster_faces[block] = cube faces of light li the cluster's
+                                             // bounding box can reach (k_cluster_faces); nullptr = every face
 };
 
 // reserve `nc` projected-triangle slots and `nf` fragment records for this lane; one atomic per warp
@@ -795,13 +949,23 @@ __device__ __forceinline__ void warp_alloc2(uint32_t* counters, uint32_t nc, uin
 
 __global__ void __launch_bounds__(128) k_shadow_setup(const ShadowSetupParams P) {
     __shared__ InlineQueue s_iq[128 / 32];
+    static_assert(CLUSTER_TRIS == 128, "one k_shadow_setup block == one cluster");
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P.cluster_faces) {                   // face sharding: none of this context's faces can see the cluster -> the block is done
+        const uint4 m = __ldg(P.cluster_faces + blockIdx.x);
+        bool reach = false;
+        for (int li = 0; li < P.n_lights; li++) {
+            const uint32_t word = li < 4 ? m.x : (li < 8 ? m.y : (li < 12 ? m.z : m.w));
+            reach |= (((word >> ((li & 3) * 8)) & 0x3Fu) & P.lights[li].face_mask) != 0;
+        }
+        if (!reach) return;
+    }
     bool active = tri < P.n_tris;
     float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0, gpos = w0;
     bool two_sided = false;
     InlineRaster<false> ir;
     ir.q = &s_iq[threadIdx.x >> 5]; ir.count = 0; ir.op = RR_OP_SIZE_LIGHT; ir.width = P.L; ir.height = P.L; ir.base = P.buffer;
-    ir.face_stride = (size_t)(P.L * P.L); ir.row_lo = 0; ir.row_hi = 0x7FFFFFFF;
+    ir.face_stride = (size_t)(P.L * P.L); ir.row_lo = 0; ir.row_hi = 0x7FFFFFFF; ir.rowmask = nullptr;
     if (active) {
         const float4 a = __ldg(P.pa + tri), b = __ldg(P.pb + tri);
         const float2 c = __ldg(P.pc + tri);
@@ -872,6 +1036,176 @@ __global__ void __launch_bounds__(128) k_shadow_setup(const ShadowSetupParams P)
         }
     }
     ir.flush();
+}
+
+// Per-cluster cube-face reach for the face-sharded shadow pass: the faces of each light that ANY point of the cluster's
+// world-space bounding box can be assigned to by ret_cubeface (cl2.cl:1745-1790), by interval arithmetic on light-relative
+// coordinates. A conservative superset of what the per-vertex test of prearrange_realtime_shadowing (cl2.cl:4520-4539)
+// marks, so skipping a cluster whose reach misses the faces rendered here cannot change a cubemap texel.
+// Byte li of out[cluster] = 6-bit face mask for light li of the pass.
+struct ObjFacesParams { ShadowLight lights[SHADOW_MAX_LIGHTS]; int n_lights; };
+
+__device__ __forceinline__ float iv_min_abs(float lo, float hi) { return (lo <= 0.f && hi >= 0.f) ? 0.f : fminf(fabsf(lo), fabsf(hi)); }
+__device__ __forceinline__ float iv_max_abs(float lo, float hi) { return fmaxf(fabsf(lo), fabsf(hi)); }
+
+__global__ void __launch_bounds__(128) k_cluster_faces(const ClusterBox* __restrict__ boxes, uint32_t n_clusters, const ObjLite* __restrict__ objs, uint32_t n_objs,
+                                                       const ObjFacesParams P, uint4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_clusters) return;
+    const ClusterBox b = boxes[i];
+    const uint32_t oid = __float_as_uint(b.lo.w);
+    uint32_t w[4] = {0x3F3F3F3Fu, 0x3F3F3F3Fu, 0x3F3F3F3Fu, 0x3F3F3F3Fu};
+    if (b.hi.w == 1.f && oid < n_objs) {
+        const ObjLite G = objs[oid];
+        const float INF = __int_as_float(0x7f800000);
+        float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
+        bool fin = true;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float3 q = cluster_corner_world(b, k, G);
+            lo[0] = fminf(lo[0], q.x); hi[0] = fmaxf(hi[0], q.x);
+            lo[1] = fminf(lo[1], q.y); hi[1] = fmaxf(hi[1], q.y);
+            lo[2] = fminf(lo[2], q.z); hi[2] = fmaxf(hi[2], q.z);
+            fin = fin && isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
+        }
+        if (fin) {
+            w[0] = w[1] = w[2] = w[3] = 0u;
+            for (int li = 0; li < P.n_lights; li++) {
+                const float l[3] = {P.lights[li].x, P.lights[li].y, P.lights[li].z};
+                float rl[3], rh[3];
+                float amax = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { rl[k] = lo[k] - l[k]; rh[k] = hi[k] - l[k]; amax = fmaxf(amax, iv_max_abs(rl[k], rh[k])); }
+                const float e = 1e-4f * amax + 1e-3f;               // corner-vs-vertex arithmetic slack
+#pragma unroll
+                for (int k = 0; k < 3; k++) { rl[k] -= e; rh[k] += e; }
+                const float nx = iv_min_abs(rl[0], rh[0]), ny = iv_min_abs(rl[1], rh[1]), nz = iv_min_abs(rl[2], rh[2]);
+                const float xx = iv_max_abs(rl[0], rh[0]), xy = iv_max_abs(rl[1], rh[1]), xz = iv_max_abs(rl[2], rh[2]);
+                uint32_t m = 1u;                                    // face 0 is also ret_cubeface's fall-through: always kept
+                if (!isfinite(amax)) m = 0x3Fu;
+                if (xx >= ny && xx >= nz) m |= (rl[0] < 0.f ? 1u << 4 : 0u) | (rh[0] >= 0.f ? 1u << 5 : 0u);
+                if (xy >= nx && xy >= nz) m |= (rl[1] < 0.f ? 1u << 1 : 0u) | (rh[1] >= 0.f ? 1u << 3 : 0u);
+                if (xz >= nx && xz >= ny) m |= (rl[2] < 0.f ? 1u << 2 : 0u) | (rh[2] >= 0.f ? 1u << 0 : 0u);
+                w[li >> 2] |= m << ((li & 3) * 8);
+            }
+        }
+    }
+    out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// =====================================================================================================================
+// Multi-GPU exchange over peer memory (NVLink P2P). One process per GPU; every context maps its peers'
+// cubemap buffers, rank 0's colour target and a small control block (cudaIpc*, rr_mgpu_connect).
+//   shadow faces : each context rasterises the (light, face) pairs it owns into its own cubemap buffer, then k_push_faces
+//                  copies them into every peer's buffer with 16-byte stores and raises a flag in every peer's control
+//                  block. Only 512-byte chunks that hold a sample now, or held one the last time this buffer was used, are
+//                  sent (cubemaps are mostly empty): receivers never clear the faces they do not own.
+//   colour bands : k_shade / k_shade_pre* store straight into rank 0's frame buffer; the last CTA of k_shade raises the
+//                  context's flag on rank 0.
+// Flags are monotonically increasing frame counters, written after a system-scope fence by the last CTA of the producing
+// kernel and polled by k_wait_flags (one CTA) in front of the consuming kernel. Waits are bounded by a wall-clock limit.
+// =====================================================================================================================
+#define MG_MAX_WORLD 16
+#define MG_PUSH_CHUNK_WORDS 128             // one warp iteration: 32 lanes x uint4 = 512 bytes
+struct MgCtrl {
+    uint32_t shadow_flag[MG_MAX_WORLD];     // [q] = last shadow epoch whose faces rank q has delivered here
+    uint32_t draw_flag[MG_MAX_WORLD];       // [q] = last draw epoch rank q has finished storing into this context's colour target
+    uint32_t push_done, shade_done;         // last-CTA counters of the local producing kernels
+    uint32_t error;                         // bit 0: a wait timed out
+    uint32_t _pad[13];
+};
+
+struct MgSignal {                           // raised by the last CTA of a kernel; n == 0: nothing to do
+    uint32_t* counter;                      // local last-CTA counter
+    uint32_t* flag[MG_MAX_WORLD];           // remote (or local) flag words
+    int n;
+    uint32_t value;
+};
+
+__device__ __forceinline__ void mg_signal_tail(const MgSignal& S) {
+    if (S.n == 0) return;
+    __threadfence_system();                 // this thread's stores (peer memory included) before the counter
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(S.counter, 1u);
+        if (t == gridDim.x * gridDim.y - 1) {
+            *S.counter = 0u;
+            __threadfence_system();
+            for (int i = 0; i < S.n; i++) *reinterpret_cast<volatile uint32_t*>(S.flag[i]) = S.value;
+        }
+    }
+}
+
+// Raise one flag after everything enqueued before this launch on the same stream has completed (stream order makes those
+// kernels' stores, peer memory included, visible before this kernel starts; the fence orders them before the flag).
+// Used after k_shade: a tail inside k_shade would cost it 9 registers and an occupancy step.
+__global__ void k_signal_flag(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(flag) = value;
+}
+
+struct MgWait { const uint32_t* flag[MG_MAX_WORLD]; int n; uint32_t value; uint32_t* error; unsigned long long timeout_ns; };
+
+__global__ void __launch_bounds__(32) k_wait_flags(const MgWait Wt) {
+    const int lane = threadIdx.x;
+    if (lane >= Wt.n) return;
+    const volatile uint32_t* f = Wt.flag[lane];
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t spins = 0;
+    while ((int32_t)(*f - Wt.value) < 0) {
+        __nanosleep(200);
+        if ((++spins & 1023u) == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > Wt.timeout_ns) { atomicOr(Wt.error, 1u); break; }
+        }
+    }
+    __threadfence_system();                 // acquire side: the kernels that follow read what the flag's writer stored before it
+}
+
+struct MgPushParams {
+    const uint32_t* local;                  // this context's cubemap buffer of the epoch
+    uint32_t* peer[MG_MAX_WORLD];           // the same buffer on every other context
+    int n_peers;
+    uint32_t pair[6 * SHADOW_MAX_LIGHTS];   // owned (light, face) pairs: face slabs p * L * L
+    int n_pairs;
+    uint32_t face_words;                    // L * L
+    uint8_t* prev_dirty;                    // [n_pairs * face_words / MG_PUSH_CHUNK_WORDS] of this buffer
+    MgSignal sig;
+};
+
+__global__ void __launch_bounds__(256) k_push_faces(const MgPushParams P) {
+    const uint32_t chunks_per_face = P.face_words / MG_PUSH_CHUNK_WORDS;
+    const uint32_t total = chunks_per_face * (uint32_t)P.n_pairs;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < total; ch += warps) {
+        const uint32_t pi = ch / chunks_per_face, c = ch - pi * chunks_per_face;
+        const size_t off = (size_t)P.pair[pi] * P.face_words + (size_t)c * MG_PUSH_CHUNK_WORDS + (size_t)lane * 4;
+        const uint4 v = *reinterpret_cast<const uint4*>(P.local + off);
+        const bool dirty = __any_sync(0xffffffffu, (v.x & v.y & v.z & v.w) != 0xFFFFFFFFu);
+        const bool was = P.prev_dirty[ch] != 0;
+        if (dirty || was) {
+            for (int q = 0; q < P.n_peers; q++) *reinterpret_cast<uint4*>(P.peer[q] + off) = v;
+        }
+        __syncwarp();
+        if (lane == 0 && dirty != was) P.prev_dirty[ch] = dirty ? 1 : 0;
+    }
+    mg_signal_tail(P.sig);
+}
+
+struct MgFillParams { uint32_t* buffer; uint32_t pair[6 * SHADOW_MAX_LIGHTS]; int n_pairs; uint32_t face_words; };
+
+// clear of the owned cubemap faces only (the others are delivered by their owners)
+__global__ void __launch_bounds__(256) k_fill_faces(const MgFillParams P) {
+    const size_t per_face4 = P.face_words / 4;
+    const size_t total = per_face4 * (size_t)P.n_pairs;
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pi = i / per_face4, k = i - pi * per_face4;
+        reinterpret_cast<uint4*>(P.buffer + (size_t)P.pair[pi] * P.face_words)[k] = ones;
+    }
 }
 
 // =====================================================================================================================
@@ -995,6 +1329,7 @@ struct ShadeParams {
     int linear, no_ssao;
     int row0, row1;          // rows covered by the grid (band +- halo): cleared for the next frame
     int band_y0, band_y1;    // rows actually shaded
+    const uint8_t* rowmask;  // interleaved bands: ROW_NEEDED rows are cleared, ROW_OWNED rows are shaded (nullptr: the ranges above)
 };
 
 // read_tex_array_all_precalculated, cl2.cl:823-851
@@ -1298,9 +1633,12 @@ __global__ void __launch_bounds__(256) k_shade_pre(const ShadeParams P) {
         px = (uint32_t)y * (uint32_t)P.W + (uint32_t)x;
         const uint32_t d = P.depth[px];
         const uint32_t idv = (d != 0xFFFFFFFFu) ? P.ids[px] : 0u;
-        P.depth_next[px] = 0xFFFFFFFFu;
-        P.ids_next[px] = 0u;                                               // id image of the next frame (atomicMax needs a clean slate)
-        if (y >= P.band_y0 && y < P.band_y1) {
+        const uint32_t rbits = P.rowmask ? P.rowmask[y] : (uint32_t)(ROW_NEEDED | ROW_OWNED);
+        if (rbits & ROW_NEEDED) {
+            P.depth_next[px] = 0xFFFFFFFFu;
+            P.ids_next[px] = 0u;                                           // id image of the next frame (atomicMax needs a clean slate)
+        }
+        if (y >= P.band_y0 && y < P.band_y1 && (rbits & ROW_OWNED)) {
             // idv >= n_frags: stale id (buffers not swapped since an earlier frame) - never index past this frame's records (q7)
             covered = d != 0xFFFFFFFFu && idv < P.n_frags[0];
             if (!covered) P.rgba8[px] = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
@@ -1329,13 +1667,17 @@ __global__ void __launch_bounds__(256) k_shade_pre4(const ShadeParams P) {
     uint32_t px = 0;
     if (x < P.W && y < P.row1) {
         px = (uint32_t)y * (uint32_t)P.W + (uint32_t)x;
-        const uint4 d = *reinterpret_cast<const uint4*>(P.depth + px);
-        const bool any = (d.x & d.y & d.z & d.w) != 0xFFFFFFFFu;
+        const uint32_t rbits = P.rowmask ? P.rowmask[y] : (uint32_t)(ROW_NEEDED | ROW_OWNED);
+        uint4 d = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         uint4 idv = make_uint4(0, 0, 0, 0);
-        if (any) idv = *reinterpret_cast<const uint4*>(P.ids + px);
-        *reinterpret_cast<uint4*>(P.depth_next + px) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        *reinterpret_cast<uint4*>(P.ids_next + px) = make_uint4(0, 0, 0, 0);
-        if (y >= P.band_y0 && y < P.band_y1) {
+        if (rbits & ROW_NEEDED) {
+            d = *reinterpret_cast<const uint4*>(P.depth + px);
+            const bool any = (d.x & d.y & d.z & d.w) != 0xFFFFFFFFu;
+            if (any) idv = *reinterpret_cast<const uint4*>(P.ids + px);
+            *reinterpret_cast<uint4*>(P.depth_next + px) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            *reinterpret_cast<uint4*>(P.ids_next + px) = make_uint4(0, 0, 0, 0);
+        }
+        if (y >= P.band_y0 && y < P.band_y1 && (rbits & ROW_OWNED)) {
             const uint32_t nfr = P.n_frags[0];
             cov = (unsigned)(d.x != 0xFFFFFFFFu && idv.x < nfr) | ((unsigned)(d.y != 0xFFFFFFFFu && idv.y < nfr) << 1) |
                   ((unsigned)(d.z != 0xFFFFFFFFu && idv.z < nfr) << 2) | ((unsigned)(d.w != 0xFFFFFFFFu && idv.w < nfr) << 3);

@@ -6,6 +6,13 @@
                 its chunk, then one in-place all-gather makes all faces visible everywhere (4*L*L bytes per face).
 
 Works on any backend: NCCL on the B200s, gloo in the CPU tests (tests/test_multiproc_gloo.py).
+
+Two exchange paths:
+  "p2p"  (product) : interleaved row tiles + round-robin faces; the contexts map each other's buffers (rr_mgpu_export /
+                     rr_mgpu_connect, handles exchanged here with one all_gather) and the kernels themselves push cubemap
+                     faces into the peers and store shaded rows into rank 0's frame buffer over NVLink. No collective
+                     runs per frame.
+  "nccl" (baseline): contiguous bands + contiguous face chunks, one all_gather_into_tensor and one gather per frame.
 """
 import torch
 import torch.distributed as dist
@@ -74,3 +81,64 @@ def ssao_halo(scene, cameras=None, margin=8):
         return -1
     reach = 2.0 * (scene.cfg.ssao_rad + 0.5) * fov_for(scene.cfg) / z_near
     return int(np.ceil(reach)) + margin
+
+
+# ---- interleaved split + peer-memory exchange ("p2p") ------------------------------------------------------------------
+def choose_tile(height, world, halo, min_tile=8, max_tile=64):
+    """Rows per tile of the interleaved split: tile t belongs to rank t % world. Small tiles balance the load when the
+    geometry sits in a few rows, but every tile drags 2*halo extra depth rows along (SSAO reach); pick the largest tile
+    that still gives every rank the same number of tiles and at least ~6 tiles, preferring multiples of 8."""
+    best = None
+    for tile in range(max_tile, min_tile - 1, -1):
+        n_tiles = -(-height // tile)
+        per_rank = n_tiles / world
+        imbalance = (-(-n_tiles // world)) / per_rank - 1.0 if per_rank > 0 else 9.0
+        overhead = (tile + 2 * max(halo, 0)) / tile
+        score = (1.0 + imbalance) * (0.35 + 0.65 * overhead) * (1.0 if n_tiles >= 6 * world else 1.5) * (1.0 if tile % 8 == 0 else 1.02)
+        if best is None or score < best[0]:
+            best = (score, tile)
+    return best[1]
+
+
+def owned_rows(height, tile, world, rank):
+    import numpy as np
+    y = np.arange(height)
+    return (y // tile) % world == rank
+
+
+def tile_config(cfg, world, rank, tile, halo=-1):
+    """rr_config of rank `rank` for the p2p path: interleaved row tiles, round-robin (light, face) pairs."""
+    return cfg.copy(band_y0=0, band_y1=0, band_tile=tile, band_rank=rank, band_world=world, band_halo=halo,
+                    face_rank=rank, face_world=world, face_interleave=1)
+
+
+def connect_peers(renderer, rank, world, group=None, device=None):
+    """rr_mgpu_export on every rank, one all_gather of the handle bytes, rr_mgpu_connect. After this the contexts exchange
+    cubemap faces and frame rows themselves; call frame_shadows / frame_draw in lock-step on all ranks."""
+    mine = renderer.mgpu_export()
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    handles = [bytes(o.cpu().numpy().tobytes()) for o in out]
+    renderer.mgpu_connect(rank, world, handles)
+    dist.barrier(group=group)
+    return handles
+
+
+def gather_tiles(fb, tile, rank, world, dst=0, group=None):
+    """baseline / CPU-test counterpart of the in-kernel composite for the interleaved split: rank k's rows are the tiles
+    t = k, k + world, ...; after the call rank `dst` holds the whole frame. fb: (H, W, 4) uint8."""
+    H = fb.shape[0]
+    n_tiles = -(-H // tile)
+    rows = lambda k: [y for t in range(k, n_tiles, world) for y in range(t * tile, min(H, (t + 1) * tile))]
+    mine = fb[rows(rank)].contiguous()
+    if rank == dst:
+        lst = [torch.empty((len(rows(k)),) + tuple(fb.shape[1:]), dtype=fb.dtype, device=fb.device) for k in range(world)]
+        dist.gather(mine, lst, dst=dst, group=group)
+        for k in range(world):
+            if k != rank:
+                fb[rows(k)] = lst[k]
+    else:
+        dist.gather(mine, None, dst=dst, group=group)

@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-from ._abi import CApi, Config, RRError, RR_OK, _F4, _P, _ptr
+from ._abi import CApi, Config, MgpuHandle, RRError, RR_OK, _F4, _P, _ptr
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -44,6 +44,14 @@ def load_library():
         _LIB.rr_host_free.argtypes = [_P]
         _LIB.rr_microbench_atomic_min.restype = C.c_int
         _LIB.rr_microbench_atomic_min.argtypes = [_P, C.c_size_t, C.c_uint64, C.POINTER(C.c_float)]
+        _LIB.rr_mgpu_export.restype = C.c_int
+        _LIB.rr_mgpu_export.argtypes = [_P, C.POINTER(MgpuHandle)]
+        _LIB.rr_mgpu_connect.restype = C.c_int
+        _LIB.rr_mgpu_connect.argtypes = [_P, C.c_int, C.c_int, C.POINTER(MgpuHandle)]
+        _LIB.rr_mgpu_connect_local.restype = C.c_int
+        _LIB.rr_mgpu_connect_local.argtypes = [C.POINTER(_P), C.c_int]
+        _LIB.rr_mgpu_disconnect.restype = C.c_int
+        _LIB.rr_mgpu_disconnect.argtypes = [_P]
         _LIB.rr_microbench_copy.restype = C.c_int
         _LIB.rr_microbench_copy.argtypes = [_P, C.c_size_t, C.POINTER(C.c_float)]
     return _LIB
@@ -102,6 +110,27 @@ class Renderer(CApi):
         if r != RR_OK:
             raise RRError(r, self.last_error())
 
+    # -- multi-GPU exchange over peer memory (include/rr.h rr_mgpu_*)
+    def mgpu_export(self):
+        """-> bytes of this context's rr_mgpu_handle (to be exchanged between the processes, any transport)"""
+        h = MgpuHandle()
+        r = self._lib.rr_mgpu_export(self._ctx, C.byref(h))
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+        return bytes(h)
+
+    def mgpu_connect(self, rank, world, handles):
+        """handles: list of `world` byte strings from mgpu_export, in rank order"""
+        arr = (MgpuHandle * world)()
+        for k, b in enumerate(handles):
+            C.memmove(C.byref(arr[k]), bytes(b), C.sizeof(MgpuHandle))
+        r = self._lib.rr_mgpu_connect(self._ctx, rank, world, arr)
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+
+    def mgpu_disconnect(self):
+        self._lib.rr_mgpu_disconnect(self._ctx)
+
     def microbench_atomic_min(self, footprint_bytes, n_ops):
         ms = C.c_float(0)
         r = self._lib.rr_microbench_atomic_min(self._ctx, footprint_bytes, n_ops, C.byref(ms))
@@ -115,3 +144,12 @@ class Renderer(CApi):
         if r != RR_OK:
             raise RRError(r, self.last_error())
         return ms.value
+
+
+def mgpu_connect_local(renderers):
+    """Wire contexts that live in this process (one per GPU, or several on one GPU in the tests): renderers[k] becomes rank k."""
+    lib = load_library()
+    arr = (_P * len(renderers))(*[r._ctx for r in renderers])
+    r = lib.rr_mgpu_connect_local(arr, len(renderers))
+    if r != RR_OK:
+        raise RRError(r, lib.rr_last_error().decode())

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# several contexts with three streams each live in one process in the multi-context tests: give every stream its own
+# hardware queue so that a polling kernel can never sit in front of the kernel it is waiting for
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -1,0 +1,99 @@
+"""gpu: the multi-GPU exchange over peer memory (include/rr.h rr_mgpu_*) exercised on ONE device — several
+contexts in this process wired with rr_mgpu_connect_local, so the whole protocol (owned-face clear, k_push_faces, frame
+flags, k_wait_flags, shading straight into rank 0's frame buffer, interleaved row tiles, per-object face reach) runs and
+is compared bit for bit with a single-context frame. The cross-process / cross-GPU variant (cudaIpc handles over
+torch.distributed) is what bench.py --gpus N runs; tests/test_gpu_mgpu_ipc.py launches it when >= 2 GPUs are present."""
+import numpy as np
+import pytest
+
+from openclrenderer_b200 import Renderer, distributed as rrd, rr, scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _cams(s, n):
+    return [((s.c_pos[0] + 35.0 * i, s.c_pos[1] + 5.0 * i, s.c_pos[2]), (s.c_rot[0] + 0.01 * i, 0.0, 0.0)) for i in range(n)]
+
+
+def _frames_single(s, cams):
+    a = Renderer(s.cfg)
+    s.upload(a)
+    out = []
+    for i, (p, r) in enumerate(cams):
+        a.frame_shadows(1 if i == 0 else 0)
+        a.frame_draw(p, r, s.clear)
+        a.sync()
+        out.append((a.read_rgba8(), a.read_depth(), [a.read_shadow(0, k) for k in range(a.n_shadow)]))
+        a.swap_buffers()
+    return out
+
+
+@pytest.mark.parametrize("world,tile,halo", [(2, 16, 24), (4, 8, 24), (3, 32, -1), (8, 16, 24)])
+def test_peer_exchange_equals_single_context(world, tile, halo):
+    s = scene.scene_spheres(640, 384, n_spheres=12, grid=(4, 3), seed=11, n_lights=3, light_dim=128, tex_sizes=(128, 64))
+    cams = _cams(s, 4)
+    want = _frames_single(s, cams)
+    rs = [Renderer(rrd.tile_config(s.cfg, world, k, tile, halo)) for k in range(world)]
+    for r in rs:
+        s.upload(r)
+    rr.mgpu_connect_local(rs)
+    for i, (p, rot) in enumerate(cams):
+        for r in rs:                       # producers first: every wait only depends on work already enqueued
+            r.frame_shadows(1 if i == 0 else 0)
+        for r in reversed(rs):             # rank 0 last: its final wait needs every peer's shading kernel
+            r.frame_draw(p, rot, s.clear)
+        for r in rs:
+            r.sync()
+        col, depth, shadows = want[i]
+        assert np.array_equal(rs[0].read_rgba8(), col), f"frame {i}: composite differs"
+        for k, r in enumerate(rs):
+            own = rrd.owned_rows(s.cfg.height, tile, world, k)
+            assert np.array_equal(r.read_depth()[own], depth[own]), f"frame {i} rank {k}: depth differs"
+            for li in range(r.n_shadow):
+                assert np.array_equal(r.read_shadow(0, li), shadows[li]), f"frame {i} rank {k}: cubemap {li} differs"
+        for r in rs:
+            r.swap_buffers()
+
+def test_peer_exchange_e2e_pipelined():
+    """rr_frame_e2e in multi-GPU mode: alternating colour targets on rank 0, pipelined read-back, same frames."""
+    s = scene.scene_spheres(640, 360, n_spheres=8, grid=(4, 2), seed=21, n_lights=2, light_dim=128, tex_sizes=(128, 64))
+    cams = _cams(s, 5)
+    want = _frames_single(s, cams)
+    world, tile = 3, 24
+    rs = [Renderer(rrd.tile_config(s.cfg, world, k, tile, 24)) for k in range(world)]
+    for r in rs:
+        s.upload(r)
+    rr.mgpu_connect_local(rs)
+    for r in rs:
+        r.frame_shadows(1)
+    bufs = [rr.host_alloc((s.cfg.height, s.cfg.width, 4)), rr.host_alloc((s.cfg.height, s.cfg.width, 4))]
+    dummy = rr.host_alloc((s.cfg.height, s.cfg.width, 4))
+    got = []
+    for i, (p, rot) in enumerate(cams):
+        for r in reversed(rs):
+            r.frame_e2e(p, rot, s.clear, 1, bufs[i % 2] if r is rs[0] else dummy)
+        if i >= 1:
+            got.append(bufs[(i - 1) % 2].copy())
+    for r in rs:
+        r.sync()
+    got.append(bufs[(len(cams) - 1) % 2].copy())
+    for i in range(len(cams)):
+        assert np.array_equal(got[i], want[i][0]), f"frame {i}"
+
+
+def test_interleaved_rows_without_exchange():
+    """band_tile ownership alone (no peer wiring): each context's owned rows equal the full frame's."""
+    s = scene.scene_spheres(640, 384, n_spheres=12, grid=(4, 3), seed=11, n_lights=2, light_dim=128, tex_sizes=(128, 64))
+    full = Renderer(s.cfg)
+    s.upload(full)
+    s.render(full, frames=2)
+    fd, fc = full.read_depth(), full.read_rgba8()
+    world, tile = 4, 24
+    for k in range(world):
+        cfg = s.cfg.copy(band_tile=tile, band_rank=k, band_world=world, band_halo=24)
+        b = Renderer(cfg)
+        s.upload(b)
+        s.render(b, frames=2)
+        own = rrd.owned_rows(s.cfg.height, tile, world, k)
+        assert np.array_equal(b.read_depth()[own], fd[own])
+        assert np.array_equal(b.read_rgba8()[own], fc[own])

@@ -160,6 +160,18 @@ def test_face_sharding_union_equals_full_cubemap():
         assert np.array_equal(acc[k], ref[k])
 
 
+@pytest.mark.parametrize("rot_y,rot_x", [(1.3, 0.1), (-2.4, 0.3), (0.4, -0.6)])
+def test_cluster_culling_keeps_records_exact(rot_y, rot_x):
+    """camera inside the sphere field looking sideways / backwards / up: most 128-triangle clusters are off screen and are
+    skipped by k_cluster_vis; depth, ids, fragment records (incl. the c_id numbering with its holes, cl2.cl:4342) and colours
+    must still equal the oracle's, which tests every triangle."""
+    s = scene.scene_spheres(640, 384, n_spheres=24, grid=(6, 4), seed=17, n_lights=2, light_dim=128, tex_sizes=(128, 64))
+    s.c_pos = (s.c_pos[0] + 150.0, s.c_pos[1] - 300.0, s.c_pos[2] + 2500.0)
+    s.c_rot = (rot_x, rot_y, 0.0)
+    g, o = render_both(s, frames=2)
+    assert_frame_parity(g, o, label=f"culling rot_y={rot_y}")
+
+
 def test_overflow_is_reported():
     s = _soup(5, 400, 320, 200, True)
     cfg = s.cfg.copy(max_fragments=64)

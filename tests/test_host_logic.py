@@ -92,6 +92,21 @@ def test_band_and_face_partition():
     assert (c.band_y0, c.band_y1, c.face_rank, c.face_world) == (240, 360, 2, 4)
 
 
+def test_interleaved_tiles_and_round_robin_faces():
+    """the p2p split: tile t of band_tile rows belongs to rank t % world; the row sets partition the screen; the config
+    carries round-robin face ownership; the tile chooser returns something the screen divides into."""
+    H, world, tile = 2160, 8, 24
+    masks = [rrd.owned_rows(H, tile, world, k) for k in range(world)]
+    assert np.array_equal(np.sum(masks, axis=0), np.ones(H, int))
+    assert masks[3][3 * tile] and masks[3][(3 + world) * tile + 5] and not masks[3][0]
+    c = rrd.tile_config(Config.default(3840, H), world, 5, tile, halo=12)
+    assert (c.band_tile, c.band_rank, c.band_world, c.band_halo, c.face_rank, c.face_world, c.face_interleave) == (tile, 5, world, 12, 5, world, 1)
+    assert (c.band_y0, c.band_y1) == (0, 0)
+    for hh, ww, halo in [(2160, 8, 12), (2160, 2, 12), (4320, 8, 24), (384, 4, 24)]:
+        t = rrd.choose_tile(hh, ww, halo)
+        assert 8 <= t <= 64
+
+
 def test_struct_layout_matches_header():
     """compile a tiny C program against include/rr.h and compare sizeof/offsetof with the ctypes / numpy mirrors."""
     src = r'''
@@ -101,6 +116,7 @@ def test_struct_layout_matches_header():
 int main(void){
  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rr_vertex), sizeof(rr_triangle), sizeof(rr_obj_desc), sizeof(rr_light), sizeof(rr_config),
    sizeof(rr_timings), offsetof(rr_obj_desc, scale), offsetof(rr_obj_desc, feature_flag), offsetof(rr_light, shadow), offsetof(rr_config, max_fragments));
+ printf("%zu %zu %zu\n", sizeof(rr_mgpu_handle), offsetof(rr_config, band_tile), offsetof(rr_mgpu_handle, shadow_bytes));
  return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
@@ -109,7 +125,8 @@ int main(void){
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     want = [48, 144, 144, 64, ctypes.sizeof(Config), ctypes.sizeof(_abi.Timings), OBJ_DESC.fields["scale"][1], OBJ_DESC.fields["feature_flag"][1],
-            LIGHT.fields["shadow"][1], Config.max_fragments.offset]
+            LIGHT.fields["shadow"][1], Config.max_fragments.offset,
+            ctypes.sizeof(_abi.MgpuHandle), Config.band_tile.offset, _abi.MgpuHandle.shadow_bytes.offset]
     assert got == want
 
 
