@@ -134,6 +134,7 @@ struct rr_ctx {
     uint32_t n_clusters = 0;
     ClusterBox* d_clusters = nullptr;
     uint8_t* d_cluster_vis = nullptr;            // main view: 0 = culled this frame (k_cluster_vis)
+    uint32_t *d_active = nullptr, *d_skipped = nullptr;   // k_block_compact: surviving setup blocks, slots skipped in front of each
     uint4* d_cluster_faces = nullptr;            // face sharding: per-cluster cube-face reach of the lights of the pass
     // multi-GPU exchange over peer memory (rr_mgpu_*)
     struct Mg {
@@ -440,7 +441,7 @@ void rr_destroy(rr_ctx* c) {
     if (c->ev_shadow_done) cudaEventDestroy(c->ev_shadow_done);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite); cudaFree(c->d_obj_r2); cudaFree(c->d_obj_rows);
-    cudaFree(c->d_clusters); cudaFree(c->d_cluster_vis); cudaFree(c->d_cluster_faces);
+    cudaFree(c->d_clusters); cudaFree(c->d_cluster_vis); cudaFree(c->d_cluster_faces); cudaFree(c->d_active); cudaFree(c->d_skipped);
     cudaFree(c->d_rowmask); cudaFree(c->d_rowpfx);
     cudaFree(c->d_atlas); cudaFree(c->d_nums); cudaFree(c->d_sizes); cudaFree(c->d_upload);
     cudaFree(c->d_lights); cudaFree(c->d_lightlite);
@@ -486,6 +487,8 @@ int rr_scene_alloc(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
     if ((r = dev_alloc(c->d_scutdown, (size_t)c->cap_cut * 3))) return r;
     c->lookback_blocks = (n_tris + SETUP_THREADS - 1) / SETUP_THREADS;
     if ((r = dev_alloc(c->d_lookback, (size_t)c->lookback_blocks))) return r;
+    if ((r = dev_alloc(c->d_active, (size_t)c->lookback_blocks))) return r;
+    if ((r = dev_alloc(c->d_skipped, (size_t)c->lookback_blocks))) return r;
     if (c->h_objs_pinned) { cudaFreeHost(c->h_objs_pinned); c->h_objs_pinned = nullptr; }
     CU(cudaMallocHost((void**)&c->h_objs_pinned, std::max<size_t>(1, n_objs) * sizeof(rr_obj_desc)));
     c->objlite_dirty = true;
@@ -756,12 +759,14 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
         c->launches++;
         sp.obj_rows = c->d_obj_rows;
     }
-    sp.cluster_vis = nullptr;
+    sp.rowpfx = c->d_rowpfx; sp.cull_rows = c->banded ? 1 : 0;
+    sp.cluster_vis = nullptr; sp.active = nullptr; sp.skipped_before = nullptr;
     if (c->n_objs && c->n_clusters) {                  // cluster culling: off-screen geometry, and rows rasterised elsewhere
         k_cluster_vis<<<(c->n_clusters + 127) / 128, 128, 0, c->stream>>>(c->d_clusters, c->n_clusters, c->d_objlite, c->n_objs, cam, (float)c->W, (float)c->H,
                                                                           c->fov, (float)c->cfg.depth_icutoff, c->d_rowpfx, row0, row1, c->d_cluster_vis);
-        c->launches++;
-        sp.cluster_vis = c->d_cluster_vis;
+        k_block_compact<<<1, COMPACT_THREADS, 0, c->stream>>>(c->d_cluster_vis, c->n_clusters, c->n_tris, c->lookback_blocks, c->d_active, c->d_skipped, c->d_counters);
+        c->launches += 2;
+        sp.cluster_vis = c->d_cluster_vis; sp.active = c->d_active; sp.skipped_before = c->d_skipped;
     }
     sp.sl.samples = c->d_samples; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
     sp.sl.desc = c->d_sample_desc; sp.sl.cap_desc = c->cap_frags; sp.sl.desc_count = c->d_counters + CTR_NDESC; sp.sl.fragcnt = c->d_fragcnt;

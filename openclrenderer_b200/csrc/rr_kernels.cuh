@@ -21,6 +21,8 @@ enum {
     CTR_NSHADE = 10,   // covered pixels in the shading list
     CTR_NSAMPLES = 11, // entries reserved in the sample list (inline-rasterised triangles)
     CTR_NDESC = 12,    // descriptors in the sample list
+    CTR_NACTIVE = 13,  // k_block_compact: setup blocks with at least one cluster that is not culled
+    CTR_CUT_SKIPPED = 14,  // ... and the projected-triangle slots of the blocks that were skipped
     CTR_COUNT = 16
 };
 
@@ -207,7 +209,8 @@ __global__ void __launch_bounds__(128) k_cluster_vis(const ClusterBox* __restric
             fin = fin && isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && isfinite(px) && isfinite(py);
         }
         // camera-space slack for the arithmetic differences between corners and vertices, then its worst-case effect in pixels
-        const float eps = 1e-4f * amax + 1e-3f;
+        // (both go through the same rot_quat_n / rot code: the difference is a few ulps of the largest coordinate; 32 ulps kept)
+        const float eps = 4e-6f * amax + 1e-4f;
         if (fin && zmin - eps > icut + 1.f && zmax + eps < RR_DEPTH_FAR * 0.999f) {
             const float slack = 4.f + 4.f * eps * fov / (zmin - eps) * (1.f + amax / (zmin - eps));
             if (isfinite(slack)) {
@@ -229,7 +232,9 @@ __global__ void __launch_bounds__(128) k_cluster_vis(const ClusterBox* __restric
 struct SubTri { float3 p0, p1, p2; float rconst; int n_frag; int box; bool keep; };
 
 // cull + bbox + fragment count, cl2.cl:4352-4377 (main) / 4571-4597 (shadow)
-__device__ __forceinline__ void classify(SubTri& s, bool two_sided, float ewidth, float eheight, float op_size) {
+// Sort-first split (rows != nullptr): a triangle whose box touches no row this context rasterises is dropped like a culled one.
+struct RowCull { const int* pfx; int lo, hi; bool on; };
+__device__ __forceinline__ void classify(SubTri& s, bool two_sided, float ewidth, float eheight, float op_size, const RowCull rc = RowCull{nullptr, 0, 0, false}) {
     bool valid = two_sided || front_facing(s.p0, s.p1, s.p2);
     bool cond = (s.p0.x < 0 && s.p1.x < 0 && s.p2.x < 0) || (s.p0.x >= ewidth && s.p1.x >= ewidth && s.p2.x >= ewidth) ||
                 (s.p0.y < 0 && s.p1.y < 0 && s.p2.y < 0) || (s.p0.y >= eheight && s.p1.y >= eheight && s.p2.y >= eheight);
@@ -242,6 +247,10 @@ __device__ __forceinline__ void classify(SubTri& s, bool two_sided, float ewidth
     float3 yr = make_float3(roundf(s.p0.y), roundf(s.p1.y), roundf(s.p2.y));
     s.rconst = calc_rconstant_v(xr, yr);
     float4 mm = calc_min_max(xr, yr, ewidth, eheight);
+    if (rc.on) {
+        const int a = (int)mm.z, e = (int)mm.w - 1;               // the walk visits rows [mm.z, mm.w)
+        if (e < a || e < rc.lo || a >= rc.hi || (rc.pfx && rc.pfx[e + 1] - rc.pfx[a] == 0)) { s.keep = false; return; }
+    }
     float area = (mm.y - mm.x) * (mm.w - mm.z);
     s.n_frag = (int)ceilf(area / op_size);
     s.box = (int)area;                        // width * rows, exact (both are small integers)
@@ -412,8 +421,8 @@ __device__ __forceinline__ unsigned long long lb_pack(uint32_t flag, uint32_t c,
 
 // Decoupled look-back of k_setup_main's single-pass scan, executed by one full warp of block `bid`: publishes the block's
 // aggregate, sums its predecessors' and publishes the inclusive prefix. The last block also writes the totals.
-__device__ __forceinline__ void setup_lookback(unsigned long long* lookback, uint32_t* counters, uint32_t bid, uint32_t tot_c, uint32_t tot_f,
-                                               uint32_t& base_c, uint32_t& base_f) {
+__device__ __forceinline__ void setup_lookback(unsigned long long* lookback, uint32_t* counters, uint32_t bid, bool is_last, uint32_t cut_extra,
+                                               uint32_t tot_c, uint32_t tot_f, uint32_t& base_c, uint32_t& base_f) {
     const int lane = threadIdx.x & 31;
     volatile unsigned long long* desc = lookback;
     base_c = 0; base_f = 0;
@@ -446,7 +455,43 @@ __device__ __forceinline__ void setup_lookback(unsigned long long* lookback, uin
         }
         if (lane == 0) { desc[bid] = lb_pack(2, base_c + tot_c, base_f + tot_f); }
     }
-    if (lane == 0 && bid == gridDim.x - 1) { counters[CTR_NCUT] = base_c + tot_c; counters[CTR_NFRAG] = base_f + tot_f; }
+    if (lane == 0 && is_last) { counters[CTR_NCUT] = base_c + tot_c + cut_extra; counters[CTR_NFRAG] = base_f + tot_f; }
+}
+
+// Compaction of the setup blocks (one CTA): a block of SETUP_THREADS triangles whose clusters are all culled contributes
+// exactly its triangle count to the projected-triangle numbering and nothing else, so k_setup_main never runs it.
+// active[i] = i-th surviving block, skipped_before[i] = slots of the culled blocks in front of it.
+#define COMPACT_THREADS 1024
+__global__ void __launch_bounds__(COMPACT_THREADS) k_block_compact(const uint8_t* __restrict__ vis, uint32_t n_clusters, uint32_t n_tris, uint32_t n_blocks,
+                                                                   uint32_t* __restrict__ active, uint32_t* __restrict__ skipped_before, uint32_t* __restrict__ counters) {
+    __shared__ uint32_t s_a[COMPACT_THREADS / 32], s_s[COMPACT_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (n_blocks + COMPACT_THREADS - 1) / COMPACT_THREADS;
+    const uint32_t b0 = min(n_blocks, tid * per), b1 = min(n_blocks, b0 + per);
+    auto culled = [&](uint32_t b) { return !vis[2 * b] && (2 * b + 1 >= n_clusters || !vis[2 * b + 1]); };
+    auto count = [&](uint32_t b) { return min(2u * CLUSTER_TRIS, n_tris - b * 2u * CLUSTER_TRIS); };
+    uint32_t na = 0, ns = 0;
+    for (uint32_t b = b0; b < b1; b++) { if (culled(b)) ns += count(b); else na++; }
+    uint32_t ia = na, is = ns;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, d), ts = __shfl_up_sync(0xffffffffu, is, d);
+        if (lane >= d) { ia += ta; is += ts; }
+    }
+    if (lane == 31) { s_a[warp] = ia; s_s[warp] = is; }
+    __syncthreads();
+    uint32_t oa = 0, os = 0, ta = 0, ts = 0;
+    for (int w = 0; w < COMPACT_THREADS / 32; w++) { if (w < warp) { oa += s_a[w]; os += s_s[w]; } ta += s_a[w]; ts += s_s[w]; }
+    uint32_t at = oa + ia - na, sk = os + is - ns;
+    for (uint32_t b = b0; b < b1; b++) {
+        if (culled(b)) sk += count(b);
+        else { active[at] = b; skipped_before[at] = sk; at++; }
+    }
+    if (tid == 0) {
+        counters[CTR_NACTIVE] = ta;
+        counters[CTR_CUT_SKIPPED] = ts;
+        if (ta == 0) { counters[CTR_NCUT] = ts; counters[CTR_NFRAG] = 0u; }     // nothing survives: k_setup_main's blocks all leave at once
+    }
 }
 
 struct SetupMainParams {
@@ -465,6 +510,8 @@ struct SetupMainParams {
     const int2* obj_rows;                    // band mode: per-object row range (k_obj_rows); nullptr = no object culling
     const uint8_t* rowmask;                  // interleaved bands: per-row ownership bits (ROW_NEEDED | ROW_OWNED); nullptr = contiguous
     const uint8_t* cluster_vis;              // k_cluster_vis: 0 = the cluster's triangles take their slots but produce nothing here
+    const uint32_t* active; const uint32_t* skipped_before;   // k_block_compact (valid when cluster_vis != nullptr)
+    const int* rowpfx; int cull_rows;        // sort-first split: per-triangle row culling (prefix count of rasterised rows; nullptr = [row_lo, row_hi))
 };
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainParams P) {
@@ -482,17 +529,15 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(&P.counters[CTR_TICKET], 1u);
     __syncthreads();
-    const uint32_t bid = s_bid;
-    const uint32_t tri = bid * SETUP_THREADS + tid;
-    // Both clusters of the block culled: every triangle is unclipped (one projected-triangle slot each, no fragments), so
-    // the block's aggregate is known without touching a vertex and it writes nothing: one warp keeps the scan going.
-    if (P.cluster_vis && !P.cluster_vis[2 * bid] && ((2 * bid + 1) * CLUSTER_TRIS >= P.n_tris || !P.cluster_vis[2 * bid + 1])) {
-        if (warp == 0) {
-            uint32_t bc, bf;
-            setup_lookback(P.lookback, P.counters, bid, min((uint32_t)SETUP_THREADS, P.n_tris - bid * SETUP_THREADS), 0u, bc, bf);
-        }
-        return;
+    const uint32_t bid = s_bid;                                   // position in the scan
+    uint32_t tblock = bid, n_active = gridDim.x, cut_skipped = 0, cut_skipped_total = 0;
+    if (P.cluster_vis) {                                          // only the blocks k_block_compact kept run; the others' slots are added in
+        n_active = P.counters[CTR_NACTIVE];
+        if (bid >= n_active) return;
+        tblock = P.active[bid]; cut_skipped = P.skipped_before[bid]; cut_skipped_total = P.counters[CTR_CUT_SKIPPED];
     }
+    const bool is_last = bid == n_active - 1;
+    const uint32_t tri = tblock * SETUP_THREADS + tid;
     const bool cl_culled = P.cluster_vis && tri < P.n_tris && !P.cluster_vis[tri / CLUSTER_TRIS];
 
     SubTri st0, st1;
@@ -515,8 +560,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
             const float3 q2 = rot(rot_quat_n(make_float3(b.z, b.w, c.x) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);
             num = clip_project(q0, q1, q2, P.icut, P.width / 2.f, P.height / 2.f, P.fov, st0, st1);
             const bool two_sided = (G.feature_flag & RR_FEATURE_TWO_SIDED) > 0;
-            if (num > 0) classify(st0, two_sided, P.width, P.height, (float)RR_OP_SIZE);
-            if (num > 1) classify(st1, two_sided, P.width, P.height, (float)RR_OP_SIZE);
+            const RowCull rc{P.rowpfx, P.row_lo, P.row_hi, P.cull_rows != 0};
+            if (num > 0) classify(st0, two_sided, P.width, P.height, (float)RR_OP_SIZE, rc);
+            if (num > 1) classify(st1, two_sided, P.width, P.height, (float)RR_OP_SIZE, rc);
         }
     }
     const bool inl0 = num > 0 && inline_candidate(st0), inl1 = num > 1 && inline_candidate(st1);
@@ -549,8 +595,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     // decoupled look-back (warp 0)
     if (warp == 0) {
         uint32_t base_c, base_f;
-        setup_lookback(P.lookback, P.counters, bid, tot_c, tot_f, base_c, base_f);
-        if (lane == 0) { s_base_c = base_c; s_base_f = base_f; s_tot_f = tot_f; }
+        setup_lookback(P.lookback, P.counters, bid, is_last, cut_skipped_total, tot_c, tot_f, base_c, base_f);
+        if (lane == 0) { s_base_c = base_c + cut_skipped; s_base_f = base_f; s_tot_f = tot_f; }
     }
     // stage per-slot data for the cooperative record write
     const uint32_t cid0 = ex_c;    // block-relative; global added below
@@ -602,7 +648,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
         const int slot = lo;
         uint32_t val;
         switch (field) {
-            case 0: val = bid * SETUP_THREADS + (uint32_t)(slot >> 1); break;
+            case 0: val = tblock * SETUP_THREADS + (uint32_t)(slot >> 1); break;
             case 1: val = r - s_fexcl[slot]; break;
             case 2: val = s_cid[slot]; break;
             case 3: val = __float_as_uint(s_rconst[slot]); break;
@@ -951,14 +997,15 @@ __global__ void __launch_bounds__(128) k_shadow_setup(const ShadowSetupParams P)
     __shared__ InlineQueue s_iq[128 / 32];
     static_assert(CLUSTER_TRIS == 128, "one k_shadow_setup block == one cluster");
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t light_reach = 0xFFFFFFFFu;      // bit li: the cluster can reach a face of light li that is rendered here (block-uniform)
     if (P.cluster_faces) {                   // face sharding: none of this context's faces can see the cluster -> the block is done
         const uint4 m = __ldg(P.cluster_faces + blockIdx.x);
-        bool reach = false;
+        light_reach = 0u;
         for (int li = 0; li < P.n_lights; li++) {
             const uint32_t word = li < 4 ? m.x : (li < 8 ? m.y : (li < 12 ? m.z : m.w));
-            reach |= (((word >> ((li & 3) * 8)) & 0x3Fu) & P.lights[li].face_mask) != 0;
+            if ((((word >> ((li & 3) * 8)) & 0x3Fu) & P.lights[li].face_mask) != 0) light_reach |= 1u << li;
         }
-        if (!reach) return;
+        if (!light_reach) return;
     }
     bool active = tri < P.n_tris;
     float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0, gpos = w0;
@@ -982,6 +1029,7 @@ __global__ void __launch_bounds__(128) k_shadow_setup(const ShadowSetupParams P)
         }
     }
     for (int li = 0; li < P.n_lights; li++) {
+        if (!((light_reach >> li) & 1u)) continue;
         const float3 lpos = make_float3(P.lights[li].x, P.lights[li].y, P.lights[li].z);
         uint32_t faces = 0;
         if (active && !(length3(gpos - lpos) > RR_DEPTH_FAR)) {                                  // cl2.cl:4472
@@ -1076,13 +1124,13 @@ __global__ void __launch_bounds__(128) k_cluster_faces(const ClusterBox* __restr
                 float amax = 0.f;
 #pragma unroll
                 for (int k = 0; k < 3; k++) { rl[k] = lo[k] - l[k]; rh[k] = hi[k] - l[k]; amax = fmaxf(amax, iv_max_abs(rl[k], rh[k])); }
-                const float e = 1e-4f * amax + 1e-3f;               // corner-vs-vertex arithmetic slack
+                const float e = 1e-5f * amax + 1e-3f;               // corner-vs-vertex arithmetic slack (~100 ulps)
 #pragma unroll
                 for (int k = 0; k < 3; k++) { rl[k] -= e; rh[k] += e; }
                 const float nx = iv_min_abs(rl[0], rh[0]), ny = iv_min_abs(rl[1], rh[1]), nz = iv_min_abs(rl[2], rh[2]);
                 const float xx = iv_max_abs(rl[0], rh[0]), xy = iv_max_abs(rl[1], rh[1]), xz = iv_max_abs(rl[2], rh[2]);
-                uint32_t m = 1u;                                    // face 0 is also ret_cubeface's fall-through: always kept
-                if (!isfinite(amax)) m = 0x3Fu;
+                // (ret_cubeface's fall-through to face 0 needs a NaN: for finite coordinates one of its three tests holds)
+                uint32_t m = isfinite(amax) ? 0u : 0x3Fu;
                 if (xx >= ny && xx >= nz) m |= (rl[0] < 0.f ? 1u << 4 : 0u) | (rh[0] >= 0.f ? 1u << 5 : 0u);
                 if (xy >= nx && xy >= nz) m |= (rl[1] < 0.f ? 1u << 1 : 0u) | (rh[1] >= 0.f ? 1u << 3 : 0u);
                 if (xz >= nx && xz >= ny) m |= (rl[2] < 0.f ? 1u << 2 : 0u) | (rh[2] >= 0.f ? 1u << 0 : 0u);

@@ -86,18 +86,14 @@ def ssao_halo(scene, cameras=None, margin=8):
 # ---- interleaved split + peer-memory exchange ("p2p") ------------------------------------------------------------------
 def choose_tile(height, world, halo, min_tile=8, max_tile=64):
     """Rows per tile of the interleaved split: tile t belongs to rank t % world. Small tiles balance the load when the
-    geometry sits in a few rows, but every tile drags 2*halo extra depth rows along (SSAO reach); pick the largest tile
-    that still gives every rank the same number of tiles and at least ~6 tiles, preferring multiples of 8."""
-    best = None
-    for tile in range(max_tile, min_tile - 1, -1):
-        n_tiles = -(-height // tile)
-        per_rank = n_tiles / world
-        imbalance = (-(-n_tiles // world)) / per_rank - 1.0 if per_rank > 0 else 9.0
-        overhead = (tile + 2 * max(halo, 0)) / tile
-        score = (1.0 + imbalance) * (0.35 + 0.65 * overhead) * (1.0 if n_tiles >= 6 * world else 1.5) * (1.0 if tile % 8 == 0 else 1.02)
-        if best is None or score < best[0]:
-            best = (score, tile)
-    return best[1]
+    geometry sits in a few hundred rows, but every tile drags 2*halo extra depth rows along (SSAO reach) and whole
+    clusters / triangles are set up wherever they touch a needed row, so small tiles also replicate more setup work.
+    Measured with examples/scaling_probe.py on config 3 (profiles/r1m_scaling_probe.jsonl): 64 rows is best at 2 ranks,
+    32 rows at 4 and 8 (max-over-ranks frame time 0.44 / 0.33 / 0.26 ms)."""
+    tile = 64 if world <= 2 else 32
+    while tile > min_tile and -(-height // tile) < 2 * world:      # tiny frames: keep at least two tiles per rank
+        tile //= 2
+    return max(min_tile, min(max_tile, tile))
 
 
 def owned_rows(height, tile, world, rank):
