@@ -42,6 +42,10 @@ def parse():
                     help="N>1: p2p = interleaved row tiles, faces pushed and rows composited by the kernels over peer memory (product); "
                          "nccl = contiguous bands, all_gather + gather collectives per frame (baseline)")
     ap.add_argument("--tile", type=int, default=0, help="rows per tile of the interleaved split (p2p; 0 = choose)")
+    ap.add_argument("--readback", default="distributed", choices=["distributed", "rank0"],
+                    help="N>1 p2p end-to-end leg: distributed = every GPU DMAs the rows it shaded into one shared host frame over its own PCIe "
+                         "link; rank0 = rows composited on GPU 0 over NVLink, GPU 0 reads the whole frame back")
+    ap.add_argument("--depth", type=int, default=3, help="colour-target ring of the end-to-end leg (rr_set_pipeline_depth): frames in flight + 1")
     ap.add_argument("--verify", action="store_true", help="N>1: rank 0 also renders the frame alone and checks the composite bit for bit")
     return ap.parse_args()
 
@@ -237,8 +241,32 @@ def run_ours(args):
         shadow = torch.full((chunk * world * L * L,), -1, dtype=torch.int32, device=dev)
         r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
     s.upload(r)
+
+    def all_ok(ok):
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
     if p2p:
-        rrd.connect_peers(r, rank, world, device=dev)     # after this the kernels exchange faces and rows themselves
+        try:
+            rrd.connect_peers(r, rank, world, device=dev, barrier=False)     # after this the kernels exchange faces and rows themselves
+            ok = True
+        except Exception as e:                                               # no peer access between these GPUs
+            sys.stderr.write(f"rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL exchange\n")
+            ok = False
+        if not all_ok(ok):
+            # same renderer, other exchange: contiguous bands + collectives (every rank takes this branch together)
+            r.close()
+            p2p = False
+            args.exchange = "nccl (peer access unavailable)"
+            cfg = rrd.band_config(s.cfg.copy(device=local), world, rank, args.halo)
+            r = Renderer(cfg)
+            fb = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+            r.bind_external(RR_BUF_RGBA8, fb.data_ptr(), fb.numel())
+            shadow = torch.full((chunk * world * L * L,), -1, dtype=torch.int32, device=dev)
+            r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
+            s.upload(r)
+        dist.barrier()
     stream = torch.cuda.ExternalStream(r.stream(), device=dev)
     sh_stream = torch.cuda.ExternalStream(r.shadow_stream(), device=dev)
 
@@ -303,18 +331,47 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers: H2D of the per-frame inputs (object descriptors from
     # pinned memory, as object_context::flush_locations does) and D2H of the finished frame, inside the timed region
-    host_fb = rr.host_alloc((H, W, 4), np.uint8) if rank == 0 else None
-    host_fb2 = rr.host_alloc((H, W, 4), np.uint8) if (rank == 0 and (world == 1 or p2p)) else None
-    pinned_t = torch.from_numpy(host_fb) if rank == 0 else None
+    dist_rb = p2p and args.readback == "distributed"
+    shared = None
+    D = max(2, min(4, args.depth))
+    if dist_rb:
+        shared = rrd.SharedFrames(H, W, rank, world, depth=D)      # one ring of host frames mapped and page-locked by every rank
+        if not shared.ok:
+            sys.stderr.write(f"rank {rank}: shared host frame unavailable ({shared.error}); GPU 0 reads the frame back\n")
+        if not all_ok(shared.ok):
+            shared.close()
+            dist_rb, shared = False, None
+    if dist_rb:
+        r.mgpu_set_readback(1)
+        host_ring = shared.frames
+    else:
+        host_ring = [rr.host_alloc((H, W, 4), np.uint8) for _ in range(D if (world == 1 or p2p) else 1)] if rank == 0 else None
+    if world == 1 or p2p:
+        r.set_pipeline_depth(D)
+    pinned_t = torch.from_numpy(host_ring[0]) if (rank == 0 and not dist_rb) else None
     dummy = np.zeros(4, np.uint8)
+    e2e_i = [0]
 
     def frame_e2e(i):
         c_pos, c_rot = camera(s, i)
         if world == 1:
-            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_fb if i % 2 == 0 else host_fb2)   # pipelined read-back; swaps buffers itself
+            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_ring[e2e_i[0] % D])   # pipelined read-back over a ring of D targets; swaps buffers itself
+            e2e_i[0] += 1
+        elif dist_rb:
+            # every rank uploads its descriptors, renders its rows and DMAs them into the shared host frame; when the call
+            # returns this rank's rows of the frame issued D-1 calls ago are in host memory, which it publishes; rank 0 (the
+            # consumer) takes a frame only when every rank has published it
+            n = e2e_i[0]
+            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_ring[n % D])
+            done = max(0, n - D + 2)
+            shared.publish(done)
+            if rank == 0:
+                shared.wait_complete(done)
+            e2e_i[0] = n + 1
         elif p2p:
             # every rank uploads its descriptors and renders its rows into rank 0's target; rank 0 reads the composite back
-            r.frame_e2e(c_pos, c_rot, s.clear, 1, (host_fb if i % 2 == 0 else host_fb2) if rank == 0 else dummy)
+            r.frame_e2e(c_pos, c_rot, s.clear, 1, host_ring[e2e_i[0] % D] if rank == 0 else dummy)
+            e2e_i[0] += 1
         else:
             r.scene_write_objs(s.objs)
             frame(i)
@@ -336,7 +393,28 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te[0])
     e2e = {"value": round(T / (e2e_ms * 1e-3) / 1e6, 3), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
-           "h2d_bytes_per_step": int(len(s.objs) * 144 * world + 32 * world), "d2h_bytes_per_step": int(W * H * 4)}
+           "h2d_bytes_per_step": int(len(s.objs) * 144 * world + 32 * world), "d2h_bytes_per_step": int(W * H * 4),
+           "readback": ("distributed: every GPU DMAs the rows it shaded into one shared, page-locked host frame" if dist_rb else
+                        "GPU 0 reads the whole frame back") if world > 1 else "pipelined",
+           "ring_depth": D if (world == 1 or p2p) else 1}
+    e2e_check = None
+    if dist_rb:
+        # the last frame of the e2e loop, as the consumer sees it in host memory, against the device composite of the same camera
+        r.sync()
+        dist.barrier()
+        last = e2e_i[0] - 1
+        r.mgpu_set_readback(0)
+        c_pos, c_rot = camera(s, 3 + args.steps - 1)
+        r.frame_shadows(0)
+        r.frame_draw(c_pos, c_rot, s.clear)
+        barrier()
+        if rank == 0:
+            dev = r.read_rgba8()
+            e2e_check = int((dev != shared.frames[last % D]).any(axis=-1).sum())
+            e2e["host_frame_pixels_differing_from_device_composite"] = e2e_check
+        r.swap_buffers()
+        barrier()
+        shared.close()
 
     line = None
     if rank == 0:

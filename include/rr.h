@@ -103,6 +103,8 @@ typedef struct rr_config {
     int32_t band_tile;             /* > 0: row y belongs to this context iff (y / band_tile) % band_world == band_rank; band_y0/y1 ignored */
     int32_t band_rank, band_world;
     int32_t face_interleave;       /* 1: pair p is rendered here iff p % face_world == face_rank (peer-memory exchange); 0: contiguous chunks */
+    int32_t cluster_cull;          /* per-frame culling of 128-triangle clusters (off-screen; rows rasterised elsewhere) before triangle setup:
+                                      0 = only when the frame is split across contexts, 1 = always (worth it when much of the scene is off screen), -1 = never */
 } rr_config;
 
 typedef struct rr_timings {      /* CUDA-event milliseconds of the last rr_frame_* calls (reference: -DPROFILING, engine.hpp:625-640) */
@@ -190,16 +192,26 @@ int rr_mgpu_export(rr_ctx*, rr_mgpu_handle* out);
 int rr_mgpu_connect(rr_ctx*, int rank, int world, const rr_mgpu_handle* handles /* [world], rank order */);
 int rr_mgpu_connect_local(rr_ctx* const* ctxs, int world);   /* ctxs[k] becomes rank k */
 int rr_mgpu_disconnect(rr_ctx*);
+/* Where the colour rows go. 0 (default): every context stores its rows into rank 0's colour target over NVLink (the composite
+ * lives on GPU 0; rr_frame_e2e on rank 0 reads it back). 1: rows stay on the GPU that shaded them and rr_frame_e2e copies
+ * exactly those rows into `host_rgba8` — pass every context the SAME host frame (memory shared between the processes and
+ * page-locked in each with rr_host_register): each GPU then moves 1/world of the frame over its own PCIe link. */
+int rr_mgpu_set_readback(rr_ctx*, int distributed);
+int rr_host_register(void* p, size_t nbytes);     /* cudaHostRegister(portable): make caller-owned (e.g. shared) memory a DMA target */
+int rr_host_unregister(void* p);
 
 void* rr_host_alloc(size_t nbytes);            /* page-locked host memory for read-backs (CL_MEM_ALLOC_HOST_PTR role; async_read.hpp:30-60 host buffers) */
 void  rr_host_free(void* p);
 
 /* ---- host-to-host frame: upload the per-frame inputs (object descriptors), draw, read RGBA8 back ------------------
- * Pipelined like the reference's read-back ring (async_read.hpp:30-144): the call returns once the PREVIOUS call's
- * host buffer is complete; this call's buffer is complete after the next rr_frame_e2e or rr_sync. Alternate between
- * two host buffers (page-locked ones from rr_host_alloc make the copy a direct DMA). Swaps buffers itself. */
+ * Pipelined like the reference's read-back ring (async_read.hpp:30-144) over D colour targets (D = 2 unless changed with
+ * rr_set_pipeline_depth): the call returns once the host buffer passed D-1 calls ago is complete (D = 2: the PREVIOUS
+ * call's); rr_sync completes all. Cycle through D host buffers (page-locked ones from rr_host_alloc make the copy a
+ * direct DMA). Swaps buffers itself. D = 3 keeps two frames in flight, which hides the host's launch time behind the copy. */
+#define RR_RING_MAX 4
 int rr_frame_e2e(rr_ctx*, const float c_pos[4], const float c_rot[4], const float clear_rgba[4],
                  int with_shadows, uint8_t* host_rgba8);
+int rr_set_pipeline_depth(rr_ctx*, int depth);     /* 2..RR_RING_MAX */
 
 /* ---- roofline micro-benchmarks (R_atomic is not in MEASURED_PEAKS.json) ------------------------- */
 int rr_microbench_atomic_min(rr_ctx*, size_t footprint_bytes, uint64_t n_ops, float* ms_out);

@@ -35,7 +35,8 @@ class Config(C.Structure):
                 ("shadow_bias", C.c_float), ("shadow_exp", C.c_float), ("test_linear", C.c_int32), ("use_linear_rendering", C.c_int32),
                 ("no_ssao", C.c_int32), ("device", C.c_int32), ("band_y0", C.c_int32), ("band_y1", C.c_int32), ("band_halo", C.c_int32),
                 ("face_rank", C.c_int32), ("face_world", C.c_int32), ("max_fragments", C.c_uint32), ("max_cutdown", C.c_uint32),
-                ("band_tile", C.c_int32), ("band_rank", C.c_int32), ("band_world", C.c_int32), ("face_interleave", C.c_int32)]
+                ("band_tile", C.c_int32), ("band_rank", C.c_int32), ("band_world", C.c_int32), ("face_interleave", C.c_int32),
+                ("cluster_cull", C.c_int32)]
 
     @staticmethod
     def default(width=800, height=600, **kw):
@@ -43,7 +44,7 @@ class Config(C.Structure):
         c = Config(width=width, height=height, light_dim=1024, fov_const=0.0, hfov_deg=120.0, depth_icutoff=20, ambient=0.2, ssao_rad=5.0,
                    ssao_div=2.5, mip_bias=1.1, shadow_bias=50.0, shadow_exp=1.0, test_linear=0, use_linear_rendering=1, no_ssao=0, device=0,
                    band_y0=0, band_y1=0, band_halo=-1, face_rank=0, face_world=0, max_fragments=0, max_cutdown=0,
-                   band_tile=0, band_rank=0, band_world=0, face_interleave=0)
+                   band_tile=0, band_rank=0, band_world=0, face_interleave=0, cluster_cull=0)
         for k, v in kw.items():
             if not hasattr(c, k):
                 raise AttributeError(k)

@@ -91,12 +91,14 @@ struct rr_ctx {
     uint32_t* d_ids[2] = {nullptr, nullptr};
     int cur = 0;
     uchar4* d_rgba8 = nullptr;          // colour target of the frame being / last drawn
-    uchar4* d_rgba8_alt = nullptr;      // second target for pipelined read-back (rr_frame_e2e), like async_read.hpp's host ring
+    // ring of colour targets for pipelined read-back (rr_frame_e2e), like async_read.hpp's ring of host buffers:
+    // d_ring[0] is the context's own target; the others are allocated when first used
+    uchar4* d_ring[RR_RING_MAX] = {};
+    int ring_depth = 2, ring_pos = 0;
     bool ext_rgba8 = false;
     cudaStream_t stream3 = nullptr;     // copy stream
-    cudaEvent_t ev_draw_done = nullptr, ev_copy_done[2] = {nullptr, nullptr};
-    bool copy_pending[2] = {false, false};
-    int fb_parity = 0;
+    cudaEvent_t ev_draw_done = nullptr, ev_copy_done[RR_RING_MAX] = {};
+    bool copy_pending[RR_RING_MAX] = {};
     ushort2* d_normals = nullptr;
     uint32_t* d_shade_list = nullptr;            // compacted covered pixels
     uint2* d_samples = nullptr;                  // covered samples of inline-rasterised triangles (pixel, depth)
@@ -134,18 +136,20 @@ struct rr_ctx {
     uint32_t n_clusters = 0;
     ClusterBox* d_clusters = nullptr;
     uint8_t* d_cluster_vis = nullptr;            // main view: 0 = culled this frame (k_cluster_vis)
-    uint32_t *d_active = nullptr, *d_skipped = nullptr;   // k_block_compact: surviving setup blocks, slots skipped in front of each
+    uint32_t *d_active = nullptr, *d_skipped = nullptr;   // k_frame_prologue: surviving setup blocks, slots skipped in front of each
+    int cluster_cull = 0;                        // rr_config.cluster_cull: 0 = when the frame is split (sort-first), 1 = always, -1 = never
     uint4* d_cluster_faces = nullptr;            // face sharding: per-cluster cube-face reach of the lights of the pass
     // multi-GPU exchange over peer memory (rr_mgpu_*)
     struct Mg {
         bool exported = false, connected = false, ipc = false;
+        bool local_readback = false;                         // rr_mgpu_set_readback: rows stay local and go to the host over this GPU's own PCIe link
         int rank = 0, world = 1;
         uint32_t* shadow[2] = {nullptr, nullptr};            // local double-buffered dynamic cubemaps (one allocation)
-        uchar4* fb[2] = {nullptr, nullptr};                  // local colour-target pair (rank 0's are the composite targets)
+        uchar4* fb[RR_RING_MAX] = {};                        // local colour-target ring (rank 0's are the composite targets)
         MgCtrl* ctrl = nullptr;
         size_t shadow_words = 0;                             // per buffer
         uint32_t* peer_shadow[MG_MAX_WORLD][2] = {};
-        uchar4* fb0[2] = {nullptr, nullptr};                 // rank 0's colour targets as seen from here
+        uchar4* fb0[RR_RING_MAX] = {};                       // rank 0's colour targets as seen from here
         MgCtrl* peer_ctrl[MG_MAX_WORLD] = {};
         void* opened[MG_MAX_WORLD][3] = {};                  // cudaIpcOpenMemHandle results to close
         uint8_t* prev_dirty[2] = {nullptr, nullptr};
@@ -154,7 +158,6 @@ struct rr_ctx {
         uchar4* saved_rgba8 = nullptr; bool saved_ext_rgba8 = false;
     } mg;
     int mg_target = 0;                           // which of the colour-target pair this draw goes to (rr_frame_e2e alternates)
-    cudaEvent_t ev_frame_done[2] = {nullptr, nullptr};
     // stats
     uint32_t launches = 0;
     FaceTable faces;
@@ -191,9 +194,11 @@ int ensure_objlite(rr_ctx* c) {
 
 // compact the big fragments of the list whose length is counters[n_index] and prefix-sum their slot counts
 int scan_big(rr_ctx* c, cudaStream_t st, uint32_t* counters, const uint32_t* fragcnt, uint32_t* biglist, uint32_t* bigslot,
-             unsigned long long* lookback, int n_index, uint32_t cap) {
-    CU(cudaMemsetAsync(counters + CTR_SLOTS, 0, 3 * 4, st));                               // CTR_SLOTS, CTR_SCAN_TICKET, CTR_NBIG
-    CU(cudaMemsetAsync(lookback, 0, (size_t)c->scan_tiles * 8, st));
+             unsigned long long* lookback, int n_index, uint32_t cap, bool zeroed = false) {
+    if (!zeroed) {                                                                         // the main pass has k_frame_prologue do this
+        CU(cudaMemsetAsync(counters + CTR_SLOTS, 0, 3 * 4, st));                           // CTR_SLOTS, CTR_SCAN_TICKET, CTR_NBIG
+        CU(cudaMemsetAsync(lookback, 0, (size_t)c->scan_tiles * 8, st));
+    }
     k_scan_big<<<grid_for(c, 2), SCAN_THREADS, 0, st>>>(fragcnt, counters + n_index, cap, biglist, bigslot, counters, lookback);
     c->launches++;
     CU(cudaGetLastError());
@@ -372,6 +377,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     c->fov = cfg->fov_const > 0 ? cfg->fov_const : rr_fov_const_from_hfov(cfg->hfov_deg, (float)cfg->width);
     c->sm_count = prop.multiProcessorCount;
     c->faces = make_face_table();
+    c->cluster_cull = cfg->cluster_cull;
     auto bail = [&](const char* what) { fail(RR_ERR_CUDA, "rr_create: %s: %s", what, cudaGetErrorString(cudaGetLastError())); rr_destroy(c); return (rr_ctx*)nullptr; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
     for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail("event");
@@ -397,7 +403,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail("stream2");
     if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail("stream3");
     if (cudaEventCreateWithFlags(&c->ev_draw_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
-    for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    for (int i = 0; i < RR_RING_MAX; i++) if (cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (cudaEventCreateWithFlags(&c->ev_shadow_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     {
@@ -430,10 +436,10 @@ void rr_destroy(rr_ctx* c) {
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream3) cudaStreamSynchronize(c->stream3);
     rr_mgpu_disconnect(c);
-    for (int i = 0; i < 2; i++) if (c->ev_frame_done[i]) cudaEventDestroy(c->ev_frame_done[i]);
-    if (c->d_rgba8_alt) cudaFree(c->d_rgba8_alt);
+    for (int i = 1; i < RR_RING_MAX; i++) if (c->d_ring[i]) cudaFree(c->d_ring[i]);
+    if (!c->ext_rgba8 && c->d_ring[0]) c->d_rgba8 = c->d_ring[0];      // the context's own target (freed below)
     if (c->ev_draw_done) cudaEventDestroy(c->ev_draw_done);
-    for (int i = 0; i < 2; i++) if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
+    for (int i = 0; i < RR_RING_MAX; i++) if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
     if (c->stream3) cudaStreamDestroy(c->stream3);
     cudaFree(c->d_sfrags); cudaFree(c->d_sfragcnt); cudaFree(c->d_sbiglist); cudaFree(c->d_sbigslot); cudaFree(c->d_scounters);
     cudaFree(c->d_scutdown); cudaFree(c->d_sscan_lookback);
@@ -742,9 +748,6 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
 
     CU(cudaEventRecord(c->ev[EV_F0], c->stream));
     // prearrange
-    CU(cudaMemsetAsync(c->d_counters, 0, 4 * 4, c->stream));                               // n_cut, n_frag, overflow, ticket
-    CU(cudaMemsetAsync(c->d_counters + CTR_NSAMPLES, 0, 2 * 4, c->stream));                // sample list
-    CU(cudaMemsetAsync(c->d_lookback, 0, (size_t)c->lookback_blocks * 8, c->stream));
     SetupMainParams sp;
     sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
     sp.cam = cam; sp.width = (float)c->W; sp.height = (float)c->H; sp.fov = c->fov; sp.icut = (float)c->cfg.depth_icutoff;
@@ -761,19 +764,33 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     }
     sp.rowpfx = c->d_rowpfx; sp.cull_rows = c->banded ? 1 : 0;
     sp.cluster_vis = nullptr; sp.active = nullptr; sp.skipped_before = nullptr;
-    if (c->n_objs && c->n_clusters) {                  // cluster culling: off-screen geometry, and rows rasterised elsewhere
-        k_cluster_vis<<<(c->n_clusters + 127) / 128, 128, 0, c->stream>>>(c->d_clusters, c->n_clusters, c->d_objlite, c->n_objs, cam, (float)c->W, (float)c->H,
-                                                                          c->fov, (float)c->cfg.depth_icutoff, c->d_rowpfx, row0, row1, c->d_cluster_vis);
-        k_block_compact<<<1, COMPACT_THREADS, 0, c->stream>>>(c->d_cluster_vis, c->n_clusters, c->n_tris, c->lookback_blocks, c->d_active, c->d_skipped, c->d_counters);
-        c->launches += 2;
+    const bool cull = c->n_objs > 0 && (c->cluster_cull > 0 || (c->cluster_cull == 0 && c->banded));
+    bool scan_zeroed = false;
+    if (!cull) {                                                                           // whole frame on one GPU: nothing to cull by default
+        CU(cudaMemsetAsync(c->d_counters, 0, 4 * 4, c->stream));                           // n_cut, n_frag, overflow, ticket
+        CU(cudaMemsetAsync(c->d_counters + CTR_NSHADE, 0, 3 * 4, c->stream));              // shading list, sample list
+        CU(cudaMemsetAsync(c->d_lookback, 0, (size_t)c->lookback_blocks * 8, c->stream));
+    } else {   // one launch: zero the scan state, classify the clusters (off-screen geometry; rows rasterised elsewhere), compact the blocks
+        scan_zeroed = true;
+        PrologueParams pp;
+        pp.cv.boxes = c->d_clusters; pp.cv.n_clusters = c->n_clusters; pp.cv.objs = c->d_objlite; pp.cv.n_objs = c->n_objs;
+        pp.cv.cam = cam; pp.cv.width = (float)c->W; pp.cv.height = (float)c->H; pp.cv.fov = c->fov; pp.cv.icut = (float)c->cfg.depth_icutoff;
+        pp.cv.rowpfx = c->d_rowpfx; pp.cv.row_lo = row0; pp.cv.row_hi = row1;
+        pp.vis = c->d_cluster_vis; pp.n_tris = c->n_tris; pp.n_blocks = c->lookback_blocks;
+        pp.active = c->d_active; pp.skipped_before = c->d_skipped; pp.counters = c->d_counters; pp.lookback = c->d_lookback;
+        pp.scan_lookback = c->d_scan_lookback; pp.scan_tiles = c->scan_tiles;
+        pp.cull = 1;
+        k_frame_prologue<<<std::max(1u, (c->n_clusters + PROLOGUE_THREADS - 1) / PROLOGUE_THREADS), PROLOGUE_THREADS, 0, c->stream>>>(pp);
+        c->launches++;
         sp.cluster_vis = c->d_cluster_vis; sp.active = c->d_active; sp.skipped_before = c->d_skipped;
     }
     sp.sl.samples = c->d_samples; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
     sp.sl.desc = c->d_sample_desc; sp.sl.cap_desc = c->cap_frags; sp.sl.desc_count = c->d_counters + CTR_NDESC; sp.sl.fragcnt = c->d_fragcnt;
-    k_setup_main<<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
+    if (c->banded) k_setup_main<true><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
+    else k_setup_main<false><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
     // kernel1 / kernel2
-    if ((r = scan_big(c, c->stream, c->d_counters, c->d_fragcnt, c->d_biglist, c->d_bigslot, c->d_scan_lookback, CTR_NFRAG, c->cap_frags))) return r;
+    if ((r = scan_big(c, c->stream, c->d_counters, c->d_fragcnt, c->d_biglist, c->d_bigslot, c->d_scan_lookback, CTR_NFRAG, c->cap_frags, scan_zeroed))) return r;
     RasterParams rp;
     rp.frags = c->d_frags; rp.cutdown = c->d_cutdown; rp.fragcnt = c->d_fragcnt; rp.counters = c->d_counters; rp.cap_frags = c->cap_frags;
     rp.biglist = c->d_biglist; rp.bigslot = c->d_bigslot;
@@ -793,7 +810,8 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     hp.tris = c->d_tris; hp.objs = c->d_objs; hp.objlite = c->d_objlite; hp.lightlite = c->d_lightlite; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
     hp.depth = c->d_depth[c->cur]; hp.ids = c->d_ids[c->cur];
     hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
-    if (c->mg.connected) c->d_rgba8 = c->mg.rank == 0 ? c->mg.fb[c->mg_target] : c->mg.fb0[c->mg_target];   // every context stores into rank 0's target
+    const bool mg_composite = c->mg.connected && !c->mg.local_readback;      // rows of all contexts meet in rank 0's colour target
+    if (c->mg.connected) c->d_rgba8 = (c->mg.rank == 0 || c->mg.local_readback) ? c->mg.fb[c->mg_target] : c->mg.fb0[c->mg_target];
     hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
     hp.atlas.texels = c->d_atlas; hp.atlas.nums = c->d_nums; hp.atlas.sizes = c->d_sizes; hp.atlas.mip_start = c->mipmap_start;
     hp.lights = c->d_lights; hp.n_lights = (int)c->lights.size();
@@ -810,7 +828,6 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     if (c->mg.connected) ++c->mg.draw_epoch;
     if (hp.n_lights > 0 && (!c->d_lights)) return fail(RR_ERR_INVALID, "lights not written");
     hp.shade_list = c->d_shade_list; hp.shade_count = c->d_counters + CTR_NSHADE;
-    CU(cudaMemsetAsync(c->d_counters + CTR_NSHADE, 0, 4, c->stream));
     if (c->W % 4 == 0) {
         dim3 grid4((c->W + 127) / 128, (row1 - row0 + 7) / 8);
         k_shade_pre4<<<grid4, 256, 0, c->stream>>>(hp);
@@ -821,11 +838,11 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     if ((r = join_shadows(c))) return r;                                                   // the cubemaps must be complete before shading
     if (c->mg.connected && c->mg.shadow_epoch && (r = mg_wait(c, c->stream, true, c->mg.shadow_epoch))) return r;   // ... the peers' faces too
     k_shade<<<grid_for(c, 12), 128, 0, c->stream>>>(hp);
-    if (c->mg.connected && c->mg.rank != 0) {                  // this context's rows are in rank 0's colour target
+    if (mg_composite && c->mg.rank != 0) {                     // this context's rows are in rank 0's colour target
         k_signal_flag<<<1, 1, 0, c->stream>>>(&c->mg.peer_ctrl[0]->draw_flag[c->mg.rank], c->mg.draw_epoch);
         c->launches++;
     }
-    if (c->mg.connected && c->mg.rank == 0 && (r = mg_wait(c, c->stream, false, c->mg.draw_epoch))) return r;         // composite complete
+    if (mg_composite && c->mg.rank == 0 && (r = mg_wait(c, c->stream, false, c->mg.draw_epoch))) return r;             // composite complete
     CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
     c->launches += 3;
     c->have_frame_ev = true;
@@ -848,7 +865,7 @@ int rr_sync(rr_ctx* c) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->stream2));
     CU(cudaStreamSynchronize(c->stream3));
-    c->copy_pending[0] = c->copy_pending[1] = false;
+    for (int i = 0; i < RR_RING_MAX; i++) c->copy_pending[i] = false;
     if (c->mg.connected) {
         uint32_t perr = 0;
         CU(cudaMemcpy(&perr, &c->mg.ctrl->error, 4, cudaMemcpyDeviceToHost));
@@ -973,9 +990,9 @@ static int mg_alloc(rr_ctx* c) {
     c->mg.shadow[0] = sh; c->mg.shadow[1] = sh + c->mg.shadow_words;
     CU(cudaMemset(sh, 0xFF, c->mg.shadow_words * 2 * 4));
     uchar4* fb = nullptr;
-    CU(cudaMalloc((void**)&fb, P * 2 * 4));
-    c->mg.fb[0] = fb; c->mg.fb[1] = fb + P;
-    CU(cudaMemset(fb, 0, P * 2 * 4));
+    CU(cudaMalloc((void**)&fb, P * RR_RING_MAX * 4));
+    for (int i = 0; i < RR_RING_MAX; i++) c->mg.fb[i] = fb + (size_t)i * P;
+    CU(cudaMemset(fb, 0, P * RR_RING_MAX * 4));
     CU(cudaMalloc((void**)&c->mg.ctrl, sizeof(MgCtrl)));
     CU(cudaMemset(c->mg.ctrl, 0, sizeof(MgCtrl)));
     c->mg.exported = true;
@@ -993,7 +1010,7 @@ int rr_mgpu_export(rr_ctx* c, rr_mgpu_handle* out) {
     CU(cudaIpcGetMemHandle(&h, c->mg.shadow[0])); memcpy(out->shadow, &h, sizeof h);
     CU(cudaIpcGetMemHandle(&h, c->mg.fb[0])); memcpy(out->fb, &h, sizeof h);
     CU(cudaIpcGetMemHandle(&h, c->mg.ctrl)); memcpy(out->ctrl, &h, sizeof h);
-    out->shadow_bytes = c->mg.shadow_words * 2 * 4; out->fb_bytes = (uint64_t)c->W * c->H * 2 * 4;
+    out->shadow_bytes = c->mg.shadow_words * 2 * 4; out->fb_bytes = (uint64_t)c->W * c->H * RR_RING_MAX * 4;
     out->device = c->cfg.device; out->n_shadow = (int32_t)c->n_shadow; out->width = c->W; out->height = c->H; out->light_dim = c->L;
     return RR_OK;
 }
@@ -1048,7 +1065,7 @@ int rr_mgpu_connect(rr_ctx* c, int rank, int world, const rr_mgpu_handle* handle
             memcpy(&ih, h.fb, sizeof ih);
             CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
             c->mg.opened[q][2] = p;
-            c->mg.fb0[0] = (uchar4*)p; c->mg.fb0[1] = (uchar4*)p + P;
+            for (int i = 0; i < RR_RING_MAX; i++) c->mg.fb0[i] = (uchar4*)p + (size_t)i * P;
         }
     }
     c->mg.ipc = true;
@@ -1080,7 +1097,7 @@ int rr_mgpu_connect_local(rr_ctx* const* ctxs, int world) {
             c->mg.peer_shadow[q][0] = ctxs[q]->mg.shadow[0]; c->mg.peer_shadow[q][1] = ctxs[q]->mg.shadow[1];
             c->mg.peer_ctrl[q] = ctxs[q]->mg.ctrl;
         }
-        c->mg.fb0[0] = ctxs[0]->mg.fb[0]; c->mg.fb0[1] = ctxs[0]->mg.fb[1];
+        for (int i = 0; i < RR_RING_MAX; i++) c->mg.fb0[i] = ctxs[0]->mg.fb[i];
         c->mg.ipc = false;
         CU(cudaSetDevice(c->cfg.device));
         if ((r = mg_finish_connect(c, k, world))) return r;
@@ -1104,10 +1121,30 @@ int rr_mgpu_disconnect(rr_ctx* c) {
     }
     if (c->mg.exported) {
         cudaFree(c->mg.shadow[0]); cudaFree(c->mg.fb[0]); cudaFree(c->mg.ctrl);
-        c->mg.shadow[0] = c->mg.shadow[1] = nullptr; c->mg.fb[0] = c->mg.fb[1] = nullptr; c->mg.ctrl = nullptr;
+        c->mg.shadow[0] = c->mg.shadow[1] = nullptr; for (int i = 0; i < RR_RING_MAX; i++) c->mg.fb[i] = nullptr;
+        c->mg.ctrl = nullptr;
         c->mg.exported = false;
     }
     cudaGetLastError();
+    return RR_OK;
+}
+
+int rr_mgpu_set_readback(rr_ctx* c, int distributed) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream3));
+    c->mg.local_readback = distributed != 0;
+    return RR_OK;
+}
+
+int rr_host_register(void* p, size_t nbytes) {
+    if (!p || !nbytes) return fail(RR_ERR_INVALID, "rr_host_register: null argument");
+    CU(cudaHostRegister(p, nbytes, cudaHostRegisterPortable));
+    return RR_OK;
+}
+int rr_host_unregister(void* p) {
+    if (!p) return fail(RR_ERR_INVALID, "rr_host_unregister: null argument");
+    CU(cudaHostUnregister(p));
     return RR_OK;
 }
 
@@ -1119,6 +1156,15 @@ void* rr_host_alloc(size_t nbytes) {
 void rr_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---- host-to-host frame --------------------------------------------------------------------------------------------
+int rr_set_pipeline_depth(rr_ctx* c, int depth) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    if (depth < 2 || depth > RR_RING_MAX) return fail(RR_ERR_INVALID, "rr_set_pipeline_depth: depth must be 2..%d", RR_RING_MAX);
+    int r = rr_sync(c);
+    if (r && r != RR_ERR_OVERFLOW) return r;
+    c->ring_depth = depth; c->ring_pos = 0;
+    return RR_OK;
+}
+
 int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const float clear_rgba[4], int with_shadows, uint8_t* host_rgba8) {
     if (!c || !host_rgba8) return fail(RR_ERR_INVALID, "null argument");
     int r;
@@ -1127,59 +1173,64 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
         CU(cudaMemcpyAsync(c->d_objs, c->h_objs_pinned, (size_t)c->n_objs * sizeof(rr_obj_desc), cudaMemcpyHostToDevice, c->stream));
         c->objlite_dirty = true;
     }
-    // Pipelined read-back (the reference keeps a ring of host buffers for the same reason, async_read.hpp:30-144): this
-    // frame is drawn into one of two colour targets while the copy stream is still moving the previous frame out of the
-    // other. On return the PREVIOUS call's host buffer is complete; rr_sync() completes this one.
-    const int k = c->fb_parity;
-    if (c->mg.connected) {
-        // multi-GPU: every context stores its rows into target k on rank 0; rank 0 alone reads the composite back. Target k is
-        // free again once rank 0's copy of two frames ago is done, which rank 0's main stream waits for before it forks this
-        // frame's shadow work — and no peer can shade this frame before rank 0 has delivered its faces.
-        c->mg_target = k;
-        if (c->mg.rank == 0 && c->copy_pending[k]) CU(cudaStreamWaitEvent(c->stream, c->ev_copy_done[k], 0));
-        if (with_shadows && (r = rr_frame_shadows(c, 0))) return r;
-        if ((r = rr_frame_draw(c, c_pos, c_rot, clear_rgba))) return r;
-        if (c->mg.rank == 0) {
-            CU(cudaEventRecord(c->ev_draw_done, c->stream));
-            CU(cudaStreamWaitEvent(c->stream3, c->ev_draw_done, 0));
-            CU(cudaMemcpyAsync(host_rgba8, c->mg.fb[k], (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream3));
-            CU(cudaEventRecord(c->ev_copy_done[k], c->stream3));
-            c->copy_pending[k] = true;
-            if (c->copy_pending[k ^ 1]) { CU(cudaEventSynchronize(c->ev_copy_done[k ^ 1])); c->copy_pending[k ^ 1] = false; }
-        } else {                                          // at most one frame in flight on the host side here too
-            if (!c->ev_frame_done[0]) for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_frame_done[i], cudaEventDisableTiming));
-            CU(cudaEventRecord(c->ev_frame_done[k], c->stream));
-            if (c->copy_pending[k ^ 1]) { CU(cudaEventSynchronize(c->ev_frame_done[k ^ 1])); c->copy_pending[k ^ 1] = false; }
-            c->copy_pending[k] = true;
-        }
-        c->fb_parity ^= 1;
-        return rr_swap_buffers(c);
+    // Pipelined read-back over a ring of D colour targets (the reference keeps a ring of host buffers for the same reason,
+    // async_read.hpp:30-144): frame n is drawn into target n % D while the copy stream is still moving earlier frames out of
+    // the others. On return the host buffer passed D-1 calls ago is complete (D = 2: the previous call's); rr_sync()
+    // completes all. The caller cycles through D host buffers.
+    const int D = c->ring_depth, k = c->ring_pos;
+    const bool mg = c->mg.connected;
+    const bool pipelined = mg || !c->ext_rgba8;
+    const size_t P = (size_t)c->W * c->H, rowb = (size_t)c->W * 4;
+    if (mg) c->mg_target = k;                       // rr_frame_draw picks the local or rank-0 target of the ring
+    else if (pipelined) {
+        if (!c->d_ring[0]) c->d_ring[0] = c->d_rgba8;
+        if (!c->d_ring[k]) CU(cudaMalloc((void**)&c->d_ring[k], P * 4));
+        c->d_rgba8 = c->d_ring[k];
     }
-    if (!c->ext_rgba8) {
-        if (!c->d_rgba8_alt) CU(cudaMalloc((void**)&c->d_rgba8_alt, (size_t)c->W * c->H * 4));
-        std::swap(c->d_rgba8, c->d_rgba8_alt);
-        if (c->copy_pending[k]) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy_done[k], 0)); }   // target k is free again
-    }
+    // target k is free again once the copy of frame n - D is done. Multi-GPU: rank 0's main stream waits for that before it
+    // forks this frame's shadow work, and no peer can shade this frame before rank 0 has delivered its faces.
+    if (pipelined && c->copy_pending[k]) CU(cudaStreamWaitEvent(c->stream, c->ev_copy_done[k], 0));
     if (with_shadows && (r = rr_frame_shadows(c, 0))) return r;
     if ((r = rr_frame_draw(c, c_pos, c_rot, clear_rgba))) return r;
-    int band0, band1, row0, row1;
-    band_rows(c, band0, band1, row0, row1);
-    const size_t off = (size_t)band0 * c->W * 4, len = (size_t)(band1 - band0) * c->W * 4;
     CU(cudaEventRecord(c->ev_draw_done, c->stream));
     CU(cudaStreamWaitEvent(c->stream3, c->ev_draw_done, 0));
-    CU(cudaMemcpyAsync(host_rgba8 + off, (uint8_t*)c->d_rgba8 + off, len, cudaMemcpyDeviceToHost, c->stream3));   // direct DMA when host_rgba8 is pinned (rr_host_alloc)
+    const uint8_t* src = (const uint8_t*)c->d_rgba8;
+    if (mg && c->mg.local_readback) {
+        // distributed read-back: this context's rows only, from its own target, over its own PCIe link
+        if (c->cfg.band_tile > 0 && c->cfg.band_world > 1) {
+            const int tile = c->cfg.band_tile, world = c->cfg.band_world, rank = c->cfg.band_rank;
+            const int n_tiles = (c->H + tile - 1) / tile;
+            int full = 0;                                       // owned tiles that are complete: one strided copy
+            for (int t = rank; t < n_tiles; t += world) if ((t + 1) * tile <= c->H) full++;
+            const size_t off = (size_t)rank * tile * rowb, pitch = (size_t)tile * world * rowb;
+            if (full) CU(cudaMemcpy2DAsync(host_rgba8 + off, pitch, src + off, pitch, (size_t)tile * rowb, (size_t)full, cudaMemcpyDeviceToHost, c->stream3));
+            const int t_last = n_tiles - 1;                     // a partial last tile, if it is ours
+            if (t_last % world == rank && (t_last + 1) * tile > c->H) {
+                const size_t o2 = (size_t)t_last * tile * rowb;
+                CU(cudaMemcpyAsync(host_rgba8 + o2, src + o2, (size_t)(c->H - t_last * tile) * rowb, cudaMemcpyDeviceToHost, c->stream3));
+            }
+        } else if (c->own_hi > c->own_lo) {
+            const size_t off = (size_t)c->own_lo * rowb;
+            CU(cudaMemcpyAsync(host_rgba8 + off, src + off, (size_t)(c->own_hi - c->own_lo) * rowb, cudaMemcpyDeviceToHost, c->stream3));
+        }
+    } else if (mg) {
+        // composite on rank 0 (every context stored its rows there over NVLink): rank 0 alone reads the frame back
+        if (c->mg.rank == 0) CU(cudaMemcpyAsync(host_rgba8, src, P * 4, cudaMemcpyDeviceToHost, c->stream3));
+    } else {
+        const size_t off = (size_t)c->own_lo * rowb, len = (size_t)(c->own_hi - c->own_lo) * rowb;
+        if (len) CU(cudaMemcpyAsync(host_rgba8 + off, src + off, len, cudaMemcpyDeviceToHost, c->stream3));   // direct DMA when host_rgba8 is page-locked
+    }
     CU(cudaEventRecord(c->ev_copy_done[k], c->stream3));
     c->copy_pending[k] = true;
-    if (c->ext_rgba8) {                                   // one caller-owned target: no pipelining possible
+    if (!pipelined) {                                     // one caller-owned target: nothing to overlap with
         CU(cudaEventSynchronize(c->ev_copy_done[k]));
         c->copy_pending[k] = false;
-    } else if (c->copy_pending[k ^ 1]) {                  // at most one frame in flight
-        CU(cudaEventSynchronize(c->ev_copy_done[k ^ 1]));
-        c->copy_pending[k ^ 1] = false;
+    } else {
+        const int j = (k + 1) % D;                        // the frame issued D-1 calls ago
+        if (c->copy_pending[j]) { CU(cudaEventSynchronize(c->ev_copy_done[j])); c->copy_pending[j] = false; }
     }
-    c->fb_parity ^= 1;
-    if ((r = rr_swap_buffers(c))) return r;
-    return RR_OK;
+    c->ring_pos = (k + 1) % D;
+    return rr_swap_buffers(c);
 }
 
 // ---- micro-benchmarks ----------------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@ enum {
     CTR_NDESC = 12,    // descriptors in the sample list
     CTR_NACTIVE = 13,  // k_block_compact: setup blocks with at least one cluster that is not culled
     CTR_CUT_SKIPPED = 14,  // ... and the projected-triangle slots of the blocks that were skipped
+    CTR_PROLOGUE_TICKET = 15,  // last-CTA detection of k_frame_prologue (self-resetting)
     CTR_COUNT = 16
 };
 
@@ -183,12 +184,16 @@ __device__ __forceinline__ float3 cluster_corner_world(const ClusterBox& b, int 
     return rot_quat_n(v * G.pos_scale.w, G.nquat) + make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
 }
 
-// main view: vis[cluster] = 0 when the cluster can be skipped by k_setup_main (its triangles still take their slots)
-__global__ void __launch_bounds__(128) k_cluster_vis(const ClusterBox* __restrict__ boxes, uint32_t n_clusters, const ObjLite* __restrict__ objs, uint32_t n_objs,
-                                                     CamParams cam, float width, float height, float fov, float icut,
-                                                     const int* __restrict__ rowpfx, int row_lo, int row_hi, uint8_t* __restrict__ vis) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_clusters) return;
+// main view: 0 when the cluster can be skipped by k_setup_main (its triangles still take their slots)
+struct ClusterVisParams {
+    const ClusterBox* boxes; uint32_t n_clusters; const ObjLite* objs; uint32_t n_objs;
+    CamParams cam; float width, height, fov, icut;
+    const int* rowpfx; int row_lo, row_hi;
+};
+__device__ __forceinline__ uint8_t cluster_visible(const ClusterVisParams& P, uint32_t i) {
+    const ClusterBox* boxes = P.boxes; const ObjLite* objs = P.objs; const uint32_t n_objs = P.n_objs;
+    const CamParams& cam = P.cam; const float width = P.width, height = P.height, fov = P.fov, icut = P.icut;
+    const int* rowpfx = P.rowpfx; const int row_lo = P.row_lo, row_hi = P.row_hi;
     const ClusterBox b = boxes[i];
     const uint32_t oid = __float_as_uint(b.lo.w);
     uint8_t v = 1;
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(128) k_cluster_vis(const ClusterBox* __restric
             }
         }
     }
-    vis[i] = v;
+    return v;
 }
 
 // One clipped + projected triangle after culling. keep == false -> no storage written, no fragments.
@@ -303,7 +308,7 @@ struct InlineQueue { float f[IQ_FIELDS][IQ_SLOTS]; };
 
 struct SampleList { uint2* samples; uint32_t cap; uint32_t* count; uint4* desc; uint32_t cap_desc; uint32_t* desc_count; uint32_t* fragcnt; };
 
-template <bool REC>
+template <bool REC, bool MASKED = false>
 struct InlineRaster {
     InlineQueue* q; int count;  // count is warp-uniform
     int op; float width, height; uint32_t* base; size_t face_stride; int row_lo, row_hi;
@@ -345,7 +350,7 @@ struct InlineRaster {
             const uint8_t* rm = rowmask;
             scan_chunk(g.mm, op, 0u, [&](float x, float y) {
                 if ((int)y < rlo || (int)y >= rhi) return;
-                if (rm && !(rm[(int)y] & 1)) return;
+                if (MASKED && rm && !(rm[(int)y] & 1)) return;
                 if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
                     const float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
                     const uint32_t d = sat_u32(RR_U32MAXF / fd);
@@ -458,39 +463,80 @@ __device__ __forceinline__ void setup_lookback(unsigned long long* lookback, uin
     if (lane == 0 && is_last) { counters[CTR_NCUT] = base_c + tot_c + cut_extra; counters[CTR_NFRAG] = base_f + tot_f; }
 }
 
-// Compaction of the setup blocks (one CTA): a block of SETUP_THREADS triangles whose clusters are all culled contributes
-// exactly its triangle count to the projected-triangle numbering and nothing else, so k_setup_main never runs it.
-// active[i] = i-th surviving block, skipped_before[i] = slots of the culled blocks in front of it.
-#define COMPACT_THREADS 1024
-__global__ void __launch_bounds__(COMPACT_THREADS) k_block_compact(const uint8_t* __restrict__ vis, uint32_t n_clusters, uint32_t n_tris, uint32_t n_blocks,
-                                                                   uint32_t* __restrict__ active, uint32_t* __restrict__ skipped_before, uint32_t* __restrict__ counters) {
-    __shared__ uint32_t s_a[COMPACT_THREADS / 32], s_s[COMPACT_THREADS / 32];
+// k_frame_prologue: everything k_setup_main needs before it starts, in ONE launch (it replaces three memsets and two
+// kernels): zero the scan descriptors and the frame counters, classify the clusters (cluster_visible), and — in the CTA
+// that finishes last — compact the setup blocks: a block of SETUP_THREADS triangles whose clusters are all culled
+// contributes exactly its triangle count to the projected-triangle numbering and nothing else, so k_setup_main never
+// runs it. active[i] = i-th surviving block, skipped_before[i] = slots of the culled blocks in front of it.
+#define PROLOGUE_THREADS 256
+struct PrologueParams {
+    ClusterVisParams cv;
+    uint8_t* vis;
+    uint32_t n_tris, n_blocks;
+    uint32_t* active; uint32_t* skipped_before;
+    uint32_t* counters; unsigned long long* lookback;
+    unsigned long long* scan_lookback; uint32_t scan_tiles;   // k_scan_big's descriptors of the main pass, zeroed here too
+    int cull;                                // 0: no culling (vis = 1 everywhere, identity compaction)
+};
+
+__global__ void __launch_bounds__(PROLOGUE_THREADS) k_frame_prologue(const PrologueParams P) {
+    __shared__ uint32_t s_a[PROLOGUE_THREADS / 32], s_s[PROLOGUE_THREADS / 32];
+    __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (n_blocks + COMPACT_THREADS - 1) / COMPACT_THREADS;
-    const uint32_t b0 = min(n_blocks, tid * per), b1 = min(n_blocks, b0 + per);
-    auto culled = [&](uint32_t b) { return !vis[2 * b] && (2 * b + 1 >= n_clusters || !vis[2 * b + 1]); };
-    auto count = [&](uint32_t b) { return min(2u * CLUSTER_TRIS, n_tris - b * 2u * CLUSTER_TRIS); };
-    uint32_t na = 0, ns = 0;
-    for (uint32_t b = b0; b < b1; b++) { if (culled(b)) ns += count(b); else na++; }
-    uint32_t ia = na, is = ns;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, d), ts = __shfl_up_sync(0xffffffffu, is, d);
-        if (lane >= d) { ia += ta; is += ts; }
-    }
-    if (lane == 31) { s_a[warp] = ia; s_s[warp] = is; }
+    const uint32_t i = blockIdx.x * blockDim.x + tid;
+    if (i < P.cv.n_clusters) P.vis[i] = P.cull ? cluster_visible(P.cv, i) : (uint8_t)1;
+    for (uint32_t j = i; j < P.n_blocks; j += gridDim.x * blockDim.x) P.lookback[j] = 0ull;
+    for (uint32_t j = i; j < P.scan_tiles; j += gridDim.x * blockDim.x) P.scan_lookback[j] = 0ull;
+    __threadfence();
     __syncthreads();
-    uint32_t oa = 0, os = 0, ta = 0, ts = 0;
-    for (int w = 0; w < COMPACT_THREADS / 32; w++) { if (w < warp) { oa += s_a[w]; os += s_s[w]; } ta += s_a[w]; ts += s_s[w]; }
-    uint32_t at = oa + ia - na, sk = os + is - ns;
-    for (uint32_t b = b0; b < b1; b++) {
-        if (culled(b)) sk += count(b);
-        else { active[at] = b; skipped_before[at] = sk; at++; }
+    if (tid == 0) s_last = atomicAdd(&P.counters[CTR_PROLOGUE_TICKET], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    // ---- last CTA: compaction over all setup blocks. Two passes over the flags (count, then place); a warp takes 32 blocks per
+    // step with one 16-bit load per lane, so the loads of a pass are independent and stay in flight together.
+    const uint32_t n_clusters = P.cv.n_clusters, n_tris = P.n_tris, n_blocks = P.n_blocks;
+    const unsigned short* vis16 = reinterpret_cast<const unsigned short*>(P.vis);      // written by other CTAs of this launch: ld.cg
+    constexpr uint32_t NW = PROLOGUE_THREADS / 32;
+    const uint32_t per_w = ((n_blocks + NW * 32 - 1) / (NW * 32)) * 32;
+    const uint32_t w0 = min(n_blocks, warp * per_w), w1 = min(n_blocks, w0 + per_w);
+    auto culled = [&](uint32_t b) {
+        const uint32_t v = __ldcg(vis16 + b);
+        return (v & 0xFFu) == 0u && (2 * b + 1 >= n_clusters || (v >> 8) == 0u);
+    };
+    const uint32_t last_count = n_tris - (n_blocks - 1) * 2u * CLUSTER_TRIS;           // only the last block can be short
+    uint32_t na = 0, ns = 0;
+    for (uint32_t base = w0; base < w1; base += 32) {
+        const uint32_t b = base + lane;
+        if (b < w1) { if (culled(b)) ns += (b == n_blocks - 1) ? last_count : 2u * CLUSTER_TRIS; else na++; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, d); ns += __shfl_xor_sync(0xffffffffu, ns, d); }
+    if (lane == 0) { s_a[warp] = na; s_s[warp] = ns; }
+    __syncthreads();
+    uint32_t at = 0, sk = 0, ta = 0, ts = 0;
+    for (int w = 0; w < (int)NW; w++) { if (w < warp) { at += s_a[w]; sk += s_s[w]; } ta += s_a[w]; ts += s_s[w]; }
+    for (uint32_t base = w0; base < w1; base += 32) {
+        const uint32_t b = base + lane;
+        const bool in = b < w1;
+        const bool cu = in && culled(b);
+        const unsigned mc = __ballot_sync(0xffffffffu, cu), ma = __ballot_sync(0xffffffffu, in && !cu);
+        const unsigned lt = (1u << lane) - 1u;
+        if (in && !cu) {
+            const uint32_t pos = at + __popc(ma & lt);
+            P.active[pos] = b;
+            P.skipped_before[pos] = sk + 2u * CLUSTER_TRIS * __popc(mc & lt);         // a short last block has nothing behind it
+        }
+        at += __popc(ma);
+        sk += 2u * CLUSTER_TRIS * __popc(mc);
     }
     if (tid == 0) {
-        counters[CTR_NACTIVE] = ta;
-        counters[CTR_CUT_SKIPPED] = ts;
-        if (ta == 0) { counters[CTR_NCUT] = ts; counters[CTR_NFRAG] = 0u; }     // nothing survives: k_setup_main's blocks all leave at once
+        P.counters[CTR_PROLOGUE_TICKET] = 0u;
+        P.counters[CTR_NCUT] = ta == 0 ? ts : 0u;                 // nothing survives: k_setup_main's blocks all leave at once
+        P.counters[CTR_NFRAG] = 0u; P.counters[CTR_OVERFLOW] = 0u; P.counters[CTR_TICKET] = 0u;
+        P.counters[CTR_NSAMPLES] = 0u; P.counters[CTR_NDESC] = 0u; P.counters[CTR_NSHADE] = 0u;
+        P.counters[CTR_SLOTS] = 0u; P.counters[CTR_SCAN_TICKET] = 0u; P.counters[CTR_NBIG] = 0u;
+        P.counters[CTR_NACTIVE] = ta;
+        P.counters[CTR_CUT_SKIPPED] = ts;
     }
 }
 
@@ -514,7 +560,9 @@ struct SetupMainParams {
     const int* rowpfx; int cull_rows;        // sort-first split: per-triangle row culling (prefix count of rasterised rows; nullptr = [row_lo, row_hi))
 };
 
-__global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainParams P) {
+// BANDED: sort-first split (row masks, per-triangle row culling); false compiles those paths out for the whole-frame case
+template <bool BANDED>
+__global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup_main(const SetupMainParams P) {
     __shared__ uint32_t s_bid;
     __shared__ uint32_t s_warp_c[SETUP_THREADS / 32], s_warp_f[SETUP_THREADS / 32];
     __shared__ uint32_t s_base_c, s_base_f, s_tot_f;
@@ -527,15 +575,14 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
 
     static_assert(SETUP_THREADS == 2 * CLUSTER_TRIS, "one k_setup_main block == two clusters");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t n_active = gridDim.x, cut_skipped_total = 0;
+    if (P.cluster_vis) { n_active = P.counters[CTR_NACTIVE]; cut_skipped_total = P.counters[CTR_CUT_SKIPPED]; }   // independent of the ticket
     if (tid == 0) s_bid = atomicAdd(&P.counters[CTR_TICKET], 1u);
     __syncthreads();
     const uint32_t bid = s_bid;                                   // position in the scan
-    uint32_t tblock = bid, n_active = gridDim.x, cut_skipped = 0, cut_skipped_total = 0;
-    if (P.cluster_vis) {                                          // only the blocks k_block_compact kept run; the others' slots are added in
-        n_active = P.counters[CTR_NACTIVE];
-        if (bid >= n_active) return;
-        tblock = P.active[bid]; cut_skipped = P.skipped_before[bid]; cut_skipped_total = P.counters[CTR_CUT_SKIPPED];
-    }
+    uint32_t tblock = bid, cut_skipped = 0;
+    if (bid >= n_active) return;                                  // only the blocks k_frame_prologue kept run; the others' slots are added in
+    if (n_active != gridDim.x) { tblock = P.active[bid]; cut_skipped = P.skipped_before[bid]; }   // nothing culled: identity, no indirection
     const bool is_last = bid == n_active - 1;
     const uint32_t tri = tblock * SETUP_THREADS + tid;
     const bool cl_culled = P.cluster_vis && tri < P.n_tris && !P.cluster_vis[tri / CLUSTER_TRIS];
@@ -551,7 +598,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
         const ObjLite G = P.objs[oid];
         const float3 gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
         bool in_band = true;
-        if (P.obj_rows) { const int2 rw = __ldg(P.obj_rows + oid); in_band = !(rw.y < P.row_lo || rw.x >= P.row_hi); }
+        if (BANDED && P.obj_rows) { const int2 rw = __ldg(P.obj_rows + oid); in_band = !(rw.y < P.row_lo || rw.x >= P.row_hi); }
         if (cl_culled) num = 1;                                                  // slot taken (cl2.cl:4342), nothing kept
         else if (in_band && !(length3(gpos - P.cam.pos) > RR_DEPTH_FAR)) {       // cl2.cl:4321
             const float sc = G.pos_scale.w;
@@ -560,7 +607,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
             const float3 q2 = rot(rot_quat_n(make_float3(b.z, b.w, c.x) * sc, G.nquat) + gpos, P.cam.pos, P.cam.rot);
             num = clip_project(q0, q1, q2, P.icut, P.width / 2.f, P.height / 2.f, P.fov, st0, st1);
             const bool two_sided = (G.feature_flag & RR_FEATURE_TWO_SIDED) > 0;
-            const RowCull rc{P.rowpfx, P.row_lo, P.row_hi, P.cull_rows != 0};
+            const RowCull rc{P.rowpfx, P.row_lo, P.row_hi, BANDED && P.cull_rows != 0};
             if (num > 0) classify(st0, two_sided, P.width, P.height, (float)RR_OP_SIZE, rc);
             if (num > 1) classify(st1, two_sided, P.width, P.height, (float)RR_OP_SIZE, rc);
         }
@@ -662,7 +709,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup_main(const SetupMainPar
     }
     // kernel1's work for the small single-chunk triangles, after everything other blocks wait for has been published
     __syncthreads();            // every fragcnt word of this block is written: the rasterising lane may now update its flags
-    InlineRaster<true> ir;
+    InlineRaster<true, BANDED> ir;
     ir.q = &s_iq[warp]; ir.count = 0; ir.op = RR_OP_SIZE; ir.width = P.width; ir.height = P.height; ir.base = P.depth; ir.face_stride = 0;
     ir.row_lo = P.row_lo; ir.row_hi = P.row_hi; ir.rowmask = P.rowmask; ir.sl = P.sl;
     ir.push(inl0 && frag_ok, st0, 0u, base_f + ex_f);                 // single-chunk triangles: their one fragment's index

@@ -108,7 +108,7 @@ def tile_config(cfg, world, rank, tile, halo=-1):
                     face_rank=rank, face_world=world, face_interleave=1)
 
 
-def connect_peers(renderer, rank, world, group=None, device=None):
+def connect_peers(renderer, rank, world, group=None, device=None, barrier=True):
     """rr_mgpu_export on every rank, one all_gather of the handle bytes, rr_mgpu_connect. After this the contexts exchange
     cubemap faces and frame rows themselves; call frame_shadows / frame_draw in lock-step on all ranks."""
     mine = renderer.mgpu_export()
@@ -119,7 +119,8 @@ def connect_peers(renderer, rank, world, group=None, device=None):
     dist.all_gather(out, t, group=group)
     handles = [bytes(o.cpu().numpy().tobytes()) for o in out]
     renderer.mgpu_connect(rank, world, handles)
-    dist.barrier(group=group)
+    if barrier:
+        dist.barrier(group=group)
     return handles
 
 
@@ -138,3 +139,61 @@ def gather_tiles(fb, tile, rank, world, dst=0, group=None):
                 fb[rows(k)] = lst[k]
     else:
         dist.gather(mine, None, dst=dst, group=group)
+
+
+class SharedFrames:
+    """Host side of the distributed read-back (rr_mgpu_set_readback(1)): a ring of `depth` full frames plus one completion
+    counter per rank in ONE block of shared memory (/dev/shm), mapped by every process and page-locked for its GPU
+    (rr_host_register). Every rank's rr_frame_e2e DMAs its own rows of frame i into frames[i % depth]; when the call for
+    frame i + depth - 1 returns those rows are complete (rr_set_pipeline_depth(depth)) and the rank publishes i + 1 in its
+    counter; the consumer (rank 0) owns frame i once every counter has reached i + 1."""
+    HEADER = 4096
+
+    def __init__(self, height, width, rank, world, group=None, depth=2):
+        import os
+        import numpy as np
+        from . import rr
+        self.rank, self.world = rank, world
+        self.depth = depth
+        self.nbytes = self.HEADER + depth * height * width * 4
+        name = [f"/dev/shm/rr_frames_{os.getpid()}"] if rank == 0 else [None]
+        if rank == 0:
+            with open(name[0], "wb") as f:
+                f.truncate(self.nbytes)
+        if world > 1:
+            dist.broadcast_object_list(name, src=0, group=group)
+        self.path = name[0]
+        self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.nbytes,))
+        self.ok, self.error = True, None                # page-locking can fail; every rank still reaches the barrier below
+        try:
+            rr.host_register(self.map)
+        except Exception as e:
+            self.ok, self.error = False, e
+        self.counters = self.map[:8 * world].view(np.int64)
+        fsz = height * width * 4
+        self.frames = [self.map[self.HEADER + i * fsz:self.HEADER + (i + 1) * fsz].reshape(height, width, 4) for i in range(depth)]
+        if world > 1:
+            dist.barrier(group=group)
+
+    def publish(self, n_complete):
+        self.counters[self.rank] = n_complete
+
+    def wait_complete(self, n_complete, timeout_s=30.0):
+        """block until every rank has published >= n_complete (frames 0 .. n_complete-1 are whole in host memory)"""
+        import time
+        t0 = time.perf_counter()
+        while int(self.counters.min()) < n_complete:
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError(f"frame {n_complete - 1}: ranks at {list(self.counters)}")
+
+    def close(self, group=None):
+        import os
+        from . import rr
+        if self.world > 1:
+            dist.barrier(group=group)
+        if self.ok:
+            rr.host_unregister(self.map)
+        del self.frames, self.counters
+        self.map._mmap.close()
+        if self.rank == 0:
+            os.unlink(self.path)

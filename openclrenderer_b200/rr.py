@@ -39,6 +39,8 @@ def load_library():
         _LIB.rr_shadows_done.argtypes = [_P]
         _LIB.rr_frame_e2e.restype = C.c_int
         _LIB.rr_frame_e2e.argtypes = [_P, _F4, _F4, _F4, C.c_int, _P]
+        _LIB.rr_set_pipeline_depth.restype = C.c_int
+        _LIB.rr_set_pipeline_depth.argtypes = [_P, C.c_int]
         _LIB.rr_host_alloc.restype = _P
         _LIB.rr_host_alloc.argtypes = [C.c_size_t]
         _LIB.rr_host_free.argtypes = [_P]
@@ -52,6 +54,12 @@ def load_library():
         _LIB.rr_mgpu_connect_local.argtypes = [C.POINTER(_P), C.c_int]
         _LIB.rr_mgpu_disconnect.restype = C.c_int
         _LIB.rr_mgpu_disconnect.argtypes = [_P]
+        _LIB.rr_mgpu_set_readback.restype = C.c_int
+        _LIB.rr_mgpu_set_readback.argtypes = [_P, C.c_int]
+        _LIB.rr_host_register.restype = C.c_int
+        _LIB.rr_host_register.argtypes = [_P, C.c_size_t]
+        _LIB.rr_host_unregister.restype = C.c_int
+        _LIB.rr_host_unregister.argtypes = [_P]
         _LIB.rr_microbench_copy.restype = C.c_int
         _LIB.rr_microbench_copy.argtypes = [_P, C.c_size_t, C.POINTER(C.c_float)]
     return _LIB
@@ -102,6 +110,11 @@ class Renderer(CApi):
         if r != RR_OK:
             raise RRError(r, self.last_error())
 
+    def set_pipeline_depth(self, depth):
+        r = self._lib.rr_set_pipeline_depth(self._ctx, int(depth))
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+
     def frame_e2e(self, c_pos, c_rot, clear, with_shadows, host_rgba8):
         def f4(v):
             v = list(v) + [0.0] * (4 - len(v))
@@ -125,6 +138,11 @@ class Renderer(CApi):
         for k, b in enumerate(handles):
             C.memmove(C.byref(arr[k]), bytes(b), C.sizeof(MgpuHandle))
         r = self._lib.rr_mgpu_connect(self._ctx, rank, world, arr)
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+
+    def mgpu_set_readback(self, distributed):
+        r = self._lib.rr_mgpu_set_readback(self._ctx, int(distributed))
         if r != RR_OK:
             raise RRError(r, self.last_error())
 
@@ -153,3 +171,15 @@ def mgpu_connect_local(renderers):
     r = lib.rr_mgpu_connect_local(arr, len(renderers))
     if r != RR_OK:
         raise RRError(r, lib.rr_last_error().decode())
+
+
+def host_register(arr):
+    """page-lock caller-owned memory (e.g. a numpy view of a multiprocessing.shared_memory block) for direct DMA"""
+    lib = load_library()
+    r = lib.rr_host_register(_ptr(arr), arr.nbytes)
+    if r != RR_OK:
+        raise RRError(r, lib.rr_last_error().decode())
+
+
+def host_unregister(arr):
+    load_library().rr_host_unregister(_ptr(arr))

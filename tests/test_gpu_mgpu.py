@@ -81,6 +81,38 @@ def test_peer_exchange_e2e_pipelined():
         assert np.array_equal(got[i], want[i][0]), f"frame {i}"
 
 
+@pytest.mark.parametrize("depth", [2, 3])
+def test_distributed_readback_shared_host_frame(depth):
+    """rr_mgpu_set_readback(1): every context keeps its rows and copies exactly those into ONE shared host frame."""
+    s = scene.scene_spheres(640, 360, n_spheres=8, grid=(4, 2), seed=21, n_lights=2, light_dim=128, tex_sizes=(128, 64))
+    cams = _cams(s, 5)
+    want = _frames_single(s, cams)
+    world, tile = 4, 32                                  # 360 rows: 11 full tiles and a partial one (rank 3's)
+    rs = [Renderer(rrd.tile_config(s.cfg, world, k, tile, 24)) for k in range(world)]
+    for r in rs:
+        s.upload(r)
+    rr.mgpu_connect_local(rs)
+    for r in rs:
+        r.mgpu_set_readback(1)
+        r.set_pipeline_depth(depth)
+        r.frame_shadows(1)
+    bufs = [rr.host_alloc((s.cfg.height, s.cfg.width, 4)) for _ in range(depth)]
+    for b in bufs:
+        b[:] = 7
+    got = []
+    for i, (p, rot) in enumerate(cams):
+        for r in rs:
+            r.frame_e2e(p, rot, s.clear, 1, bufs[i % depth])
+        if i >= depth - 1:
+            got.append(bufs[(i - depth + 1) % depth].copy())   # every context's call for frame i has returned: frame i-depth+1 is whole
+    for r in rs:
+        r.sync()
+    for i in range(len(cams) - depth + 1, len(cams)):
+        got.append(bufs[i % depth].copy())
+    for i in range(len(cams)):
+        assert np.array_equal(got[i], want[i][0]), f"frame {i}"
+
+
 def test_interleaved_rows_without_exchange():
     """band_tile ownership alone (no peer wiring): each context's owned rows equal the full frame's."""
     s = scene.scene_spheres(640, 384, n_spheres=12, grid=(4, 3), seed=11, n_lights=2, light_dim=128, tex_sizes=(128, 64))

@@ -168,6 +168,7 @@ def test_cluster_culling_keeps_records_exact(rot_y, rot_x):
     s = scene.scene_spheres(640, 384, n_spheres=24, grid=(6, 4), seed=17, n_lights=2, light_dim=128, tex_sizes=(128, 64))
     s.c_pos = (s.c_pos[0] + 150.0, s.c_pos[1] - 300.0, s.c_pos[2] + 2500.0)
     s.c_rot = (rot_x, rot_y, 0.0)
+    s.cfg = s.cfg.copy(cluster_cull=1)              # single context: culling is opt-in (it is on by default only when the frame is split)
     g, o = render_both(s, frames=2)
     assert_frame_parity(g, o, label=f"culling rot_y={rot_y}")
 
@@ -213,12 +214,13 @@ def test_full_size_properties_c3():
     assert t["overflow"] == 0 and t["n_fragments"] == len(frags)
 
 
-def test_frame_e2e_pipelined_readback_matches_plain_frames():
-    """rr_frame_e2e (descriptor upload + shadows + draw + pipelined read-back into alternating pinned buffers) returns the
-    same frames as frame_draw + read_rgba8, for a moving camera."""
+@pytest.mark.parametrize("depth", [2, 3, 4])
+def test_frame_e2e_pipelined_readback_matches_plain_frames(depth):
+    """rr_frame_e2e (descriptor upload + shadows + draw + pipelined read-back into a ring of pinned buffers) returns the
+    same frames as frame_draw + read_rgba8, for a moving camera; ring depth D: the buffer passed D-1 calls ago is complete."""
     from openclrenderer_b200 import rr
     s = scene.scene_spheres(640, 360, n_spheres=8, grid=(4, 2), seed=21, n_lights=2, light_dim=128, tex_sizes=(128, 64))
-    cams = [((s.c_pos[0] + 40.0 * i, s.c_pos[1], s.c_pos[2]), (s.c_rot[0] + 0.01 * i, 0.0, 0.0)) for i in range(5)]
+    cams = [((s.c_pos[0] + 40.0 * i, s.c_pos[1], s.c_pos[2]), (s.c_rot[0] + 0.01 * i, 0.0, 0.0)) for i in range(7)]
     a = Renderer(s.cfg)
     s.upload(a)
     want = []
@@ -231,14 +233,16 @@ def test_frame_e2e_pipelined_readback_matches_plain_frames():
     b = Renderer(s.cfg)
     s.upload(b)
     b.frame_shadows(1)
-    bufs = [rr.host_alloc((s.cfg.height, s.cfg.width, 4)), rr.host_alloc((s.cfg.height, s.cfg.width, 4))]
+    b.set_pipeline_depth(depth)
+    bufs = [rr.host_alloc((s.cfg.height, s.cfg.width, 4)) for _ in range(depth)]
     got = []
     for i, (p, r) in enumerate(cams):
-        b.frame_e2e(p, r, s.clear, 1, bufs[i % 2])
-        if i >= 1:
-            got.append(bufs[(i - 1) % 2].copy())          # the previous call's buffer is complete on return
+        b.frame_e2e(p, r, s.clear, 1, bufs[i % depth])
+        if i >= depth - 1:
+            got.append(bufs[(i - depth + 1) % depth].copy())          # the buffer passed depth-1 calls ago is complete on return
     b.sync()
-    got.append(bufs[(len(cams) - 1) % 2].copy())
+    for i in range(len(cams) - depth + 1, len(cams)):
+        got.append(bufs[i % depth].copy())
     for i in range(len(cams)):
         assert np.array_equal(got[i], want[i]), f"frame {i}"
 
