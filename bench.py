@@ -470,6 +470,15 @@ def run_ours(args):
                                                         "id": "k_raster_small<ids> + k_raster_big<ids>", "shade": "k_shade_pre + k_shade"}[dom],
                             "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4), "traffic": None,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": int(B[dom]), "avg_ms": round(ms_of[dom], 4)}
+        try:                                   # DRAM bytes of the stage's dominant kernel from the committed ncu capture (per launch)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            kname = {"setup": "k_setup_main", "shadow": "k_shadow_setup", "shade": "k_shade"}.get(dom)
+            if kname in tr:
+                line["roofline"]["traffic"] = int(tr[kname])
+                line["roofline"]["traffic_kernel"] = kname
+                line["roofline"]["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of that kernel)"
+        except Exception:
+            pass
         line["roofline"]["note"] = ("stages are issue-bound, not HBM-bound (ncu: DRAM 3-6 %, issue-active ~50 %): the pinned IEEE arithmetic of the "
                                     "reference's per-pixel/per-triangle math dominates; shadow stage runs concurrently with setup/depth/id on a second stream, "
                                     "so stage times overlap and do not add up to ms_per_step")
