@@ -123,7 +123,7 @@ enum rr_buffer {                 /* names for rr_bind_external / rr_device_ptr *
     RR_BUF_SHADOW_DYNAMIC = 1,   /* uint32[6*L*L*n_shadow]  engine::g_shadow_light_buffer (light.cpp:236) */
     RR_BUF_SHADOW_STATIC = 2,    /* uint32[6*L*L*n_static]  engine::g_static_shadow_light_buffer (light.cpp:253) */
     RR_BUF_DEPTH = 3,            /* uint32[W*H] current depth buffer (object_context.cpp:47) */
-    RR_BUF_IDS = 4               /* uint32[W*H] fragment-id image (object_context.cpp:36-38) */
+    RR_BUF_IDS = 4               /* uint32[W*H] fragment-id image (object_context.cpp:36-38); on the device: fragment index + 1, 0 = unresolved */
 };
 
 /* ---- context -------------------------------------------------------------------------------------------------- */
@@ -158,7 +158,7 @@ int rr_sync(rr_ctx*);                                                           
 
 /* ---- read-back of the frame just drawn (replaces clEnqueueReadImage cl_gl_interop_texture.hpp:235, async_read.hpp:51) */
 int rr_read_depth(rr_ctx*, uint32_t* dst);            /* W*H uint32, the depth buffer kernel1 filled */
-int rr_read_ids(rr_ctx*, uint32_t* dst);              /* W*H uint32 fragment indices (0 where nothing was drawn) */
+int rr_read_ids(rr_ctx*, uint32_t* dst);              /* W*H uint32 fragment indices (0 where nothing was drawn or no fragment passed kernel2's depth window) */
 int rr_read_rgba8(rr_ctx*, uint8_t* dst);             /* W*H*4, q = (uint8)(clamp(c,0,1)*255+0.5) */
 int rr_read_normals(rr_ctx*, uint16_t* dst);          /* W*H*2 ushort2, screen_normals_optional cl2.cl:6390 */
 int rr_read_shadow(rr_ctx*, int is_static, uint32_t slab, uint32_t* dst);  /* 6*L*L uint32 of one light's cubemap */

@@ -885,7 +885,13 @@ static int read_back(rr_ctx* c, void* dst, const void* src, size_t bytes) {
     return RR_OK;
 }
 int rr_read_depth(rr_ctx* c, uint32_t* dst) { return read_back(c, dst, c->d_depth[c->cur], (size_t)c->W * c->H * 4); }
-int rr_read_ids(rr_ctx* c, uint32_t* dst) { return read_back(c, dst, c->d_ids[c->cur], (size_t)c->W * c->H * 4); }
+int rr_read_ids(rr_ctx* c, uint32_t* dst) {
+    int r = read_back(c, dst, c->d_ids[c->cur], (size_t)c->W * c->H * 4);
+    if (r) return r;
+    const size_t P = (size_t)c->W * c->H;                 // the device image holds fragment index + 1 (0 = unresolved)
+    for (size_t i = 0; i < P; i++) dst[i] = dst[i] ? dst[i] - 1u : 0u;
+    return RR_OK;
+}
 int rr_read_rgba8(rr_ctx* c, uint8_t* dst) { return read_back(c, dst, c->d_rgba8, (size_t)c->W * c->H * 4); }
 int rr_read_normals(rr_ctx* c, uint16_t* dst) { return read_back(c, dst, c->d_normals, (size_t)c->W * c->H * 4); }
 int rr_read_shadow(rr_ctx* c, int is_static, uint32_t slab_idx, uint32_t* dst) {

@@ -756,8 +756,10 @@ __device__ __forceinline__ void emit_sample(const RasterParams& P, float x, floa
     } else {
         const int px = (int)y * P.W + (int)x;
         const uint32_t val = P.depth[px];
-        // racing plain stores in the reference; canonical winner = highest fragment index (last writer in id order)
-        if (d > val - RR_BUF_ERROR && d < val + RR_BUF_ERROR) atomicMax(P.ids + px, f);
+        // racing plain stores in the reference; canonical winner = highest fragment index (last writer in id order).
+        // The id image holds fragment index + 1: 0 = no fragment passed the test (e.g. depth < 20, where the reference's
+        // unsigned window wraps, cl2.cl:5534) — such pixels are shaded like uncovered ones instead of with a stale id (q7)
+        if (d > val - RR_BUF_ERROR && d < val + RR_BUF_ERROR) atomicMax(P.ids + px, f + 1u);
     }
 }
 
@@ -818,7 +820,7 @@ __global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const uin
             if (row < row_lo || row >= row_hi) continue;
             if (rowmask && !(rowmask[row] & ROW_OWNED)) continue;
             const uint32_t val = depth[sm.x];
-            if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) atomicMax(ids + sm.x, de.z);
+            if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) atomicMax(ids + sm.x, de.z + 1u);
         }
     }
 }
@@ -1553,7 +1555,7 @@ __device__ __forceinline__ void shade_pixel(const ShadeParams& P, const int x, c
     const int W = P.W, H = P.H;
     const size_t px = (size_t)y * W + x;
     const uint32_t d = P.depth[px];
-    const uint32_t idv = P.ids[px];
+    const uint32_t idv = P.ids[px] - 1u;                             // the id image holds fragment index + 1 (k_shade_pre lists resolved pixels only)
     const uint32_t* rec = P.frags + (size_t)idv * RR_FRAG_WORDS;
     const uint32_t tri_global = __ldg(rec + 0), ctri = __ldg(rec + 2);
     const float rconst = __uint_as_float(__ldg(rec + 3));
@@ -1734,8 +1736,9 @@ __global__ void __launch_bounds__(256) k_shade_pre(const ShadeParams P) {
             P.ids_next[px] = 0u;                                           // id image of the next frame (atomicMax needs a clean slate)
         }
         if (y >= P.band_y0 && y < P.band_y1 && (rbits & ROW_OWNED)) {
-            // idv >= n_frags: stale id (buffers not swapped since an earlier frame) - never index past this frame's records (q7)
-            covered = d != 0xFFFFFFFFu && idv < P.n_frags[0];
+            // idv holds fragment index + 1; 0: unresolved; > n_frags: stale id (buffers not swapped since an earlier frame) -
+            // never index past this frame's records (q7)
+            covered = d != 0xFFFFFFFFu && idv != 0u && idv <= P.n_frags[0];
             if (!covered) P.rgba8[px] = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
         }
     }
@@ -1774,8 +1777,9 @@ __global__ void __launch_bounds__(256) k_shade_pre4(const ShadeParams P) {
         }
         if (y >= P.band_y0 && y < P.band_y1 && (rbits & ROW_OWNED)) {
             const uint32_t nfr = P.n_frags[0];
-            cov = (unsigned)(d.x != 0xFFFFFFFFu && idv.x < nfr) | ((unsigned)(d.y != 0xFFFFFFFFu && idv.y < nfr) << 1) |
-                  ((unsigned)(d.z != 0xFFFFFFFFu && idv.z < nfr) << 2) | ((unsigned)(d.w != 0xFFFFFFFFu && idv.w < nfr) << 3);
+            // ids hold fragment index + 1 (0 = unresolved): covered <=> 1 <= id <= nfr
+            cov = (unsigned)(d.x != 0xFFFFFFFFu && idv.x - 1u < nfr) | ((unsigned)(d.y != 0xFFFFFFFFu && idv.y - 1u < nfr) << 1) |
+                  ((unsigned)(d.z != 0xFFFFFFFFu && idv.z - 1u < nfr) << 2) | ((unsigned)(d.w != 0xFFFFFFFFu && idv.w - 1u < nfr) << 3);
             if (cov != 0xFu) {          // covered pixels are overwritten by k_shade afterwards
                 const uchar4 c = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
                 const uint32_t cw = *reinterpret_cast<const uint32_t*>(&c);

@@ -487,7 +487,8 @@ void kernel2(orc_ctx* c) {
                 uint32_t mydepth = sat_u32(U32MAXF / fmydepth);
                 uint32_t val = depth[(int)y * W + (int)x];
                 int c2 = mydepth > val - BUF_ERROR && mydepth < val + BUF_ERROR;   // unsigned wrap kept
-                if (c2) atomic_max_u32(&ids[(int)y * W + (int)x], (uint32_t)id);
+                // the id image holds fragment index + 1: 0 = no fragment passed the window (q7: such pixels are shaded like uncovered ones)
+                if (c2) atomic_max_u32(&ids[(int)y * W + (int)x], (uint32_t)id + 1u);
             }
         });
     }
@@ -866,11 +867,11 @@ void kernel3(orc_ctx* c, const float c_pos4[4], const rotsc& crot, const float c
             if (y < y0 || y >= y1) continue;
             const uint32_t ft_depth = depth_buffer[px];
             float* out = &c->colour[px * 4];
-            if (ft_depth == 0xFFFFFFFFu) {                           // 5835-5862
+            if (ft_depth == 0xFFFFFFFFu || c->ids[px] == 0u) {       // 5835-5862; unresolved id (never written by kernel2): same treatment
                 for (int k = 0; k < 4; k++) out[k] = clear[k];
                 continue;
             }
-            uint32_t idv = c->ids[px];
+            uint32_t idv = c->ids[px] - 1u;
             uint32_t tri_global = c->frags[(size_t)idv * FRAG_MUL + 0];
             uint32_t ctri = c->frags[(size_t)idv * FRAG_MUL + 2];
             float rconst = as_float(c->frags[(size_t)idv * FRAG_MUL + 3]);
@@ -1189,7 +1190,10 @@ int orc_sync(orc_ctx*) { return RR_OK; }
 
 // After orc_frame_draw and BEFORE orc_swap_buffers these return the frame just drawn.
 int orc_read_depth(orc_ctx* c, uint32_t* d) { memcpy(d, c->depth[c->cur].data(), c->depth[0].size() * 4); return RR_OK; }
-int orc_read_ids(orc_ctx* c, uint32_t* d) { memcpy(d, c->ids.data(), c->ids.size() * 4); return RR_OK; }
+int orc_read_ids(orc_ctx* c, uint32_t* d) {
+    for (size_t i = 0; i < c->ids.size(); i++) d[i] = c->ids[i] ? c->ids[i] - 1u : 0u;
+    return RR_OK;
+}
 int orc_read_rgba8(orc_ctx* c, uint8_t* d) { memcpy(d, c->rgba8.data(), c->rgba8.size()); return RR_OK; }
 int orc_read_colour_f32(orc_ctx* c, float* d) { memcpy(d, c->colour.data(), c->colour.size() * 4); return RR_OK; }
 int orc_read_normals(orc_ctx* c, uint16_t* d) { memcpy(d, c->normals.data(), c->normals.size() * 2); return RR_OK; }
