@@ -237,7 +237,7 @@ def run_ours(args):
     if fb is not None:
         r.bind_external(RR_BUF_RGBA8, fb.data_ptr(), fb.numel())
     chunk = rrd.face_chunk(n_shadow, world)
-    if not p2p:
+    if world > 1 and not p2p:
         shadow = torch.full((chunk * world * L * L,), -1, dtype=torch.int32, device=dev)
         r.bind_external(RR_BUF_SHADOW_DYNAMIC, shadow.data_ptr(), shadow.numel() * 4)
     s.upload(r)

@@ -837,7 +837,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     }
     if ((r = join_shadows(c))) return r;                                                   // the cubemaps must be complete before shading
     if (c->mg.connected && c->mg.shadow_epoch && (r = mg_wait(c, c->stream, true, c->mg.shadow_epoch))) return r;   // ... the peers' faces too
-    k_shade<<<grid_for(c, 12), 128, 0, c->stream>>>(hp);
+    k_shade<<<grid_for(c, 48), 128, 0, c->stream>>>(hp);      // 4x more CTAs than fit: the tail of the stride loop balances better (0.232 -> 0.219 ms on c3)
     if (mg_composite && c->mg.rank != 0) {                     // this context's rows are in rank 0's colour target
         k_signal_flag<<<1, 1, 0, c->stream>>>(&c->mg.peer_ctrl[0]->draw_flag[c->mg.rank], c->mg.draw_epoch);
         c->launches++;
