@@ -323,7 +323,10 @@ def run_ours(args):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_total, launches = float(tmax[0]), int(tsum[1])
     if os.environ.get("RR_BENCH_RANK_TIMINGS"):
+        r.set_profiling(True)
+        frame(10_000)
         tm = r.timings()
+        r.set_profiling(False)
         sys.stderr.write("rank %d: %s\n" % (rank, json.dumps({k: round(v, 4) if isinstance(v, float) else v for k, v in tm.items()})))
     ms = ms_total / args.steps
     T = len(s.tris)
@@ -430,11 +433,13 @@ def run_ours(args):
         stage = {k: 0.0 for k in ("shadow_depth_ms", "setup_ms", "depth_ms", "id_ms", "shade_ms", "frame_ms")}
         n_prof = 8
         tm = None
+        r.set_profiling(True)                  # per-stage events only for these frames: they are not free (rr.h rr_set_profiling)
         for i in range(n_prof):
             frame(1000 + i)
             tm = r.timings()
             for k in stage:
                 stage[k] += tm[k] / n_prof
+        r.set_profiling(False)
         # the frame just drawn is in the previous buffer after swap: swap back to read it
         r.swap_buffers()
         ids, depth, frags = r.read_ids(), r.read_depth(), r.read_fragments()

@@ -25,6 +25,7 @@ if a.world > 1:
     cfg = rrd.tile_config(s.cfg, a.world, a.rank, a.tile, halo)
 r = Renderer(cfg)
 s.upload(r)
+r.set_profiling(True)
 for i in range(a.frames):
     c_pos, c_rot = camera(s, i)
     r.frame_shadows(0)

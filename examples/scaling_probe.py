@@ -20,6 +20,7 @@ from openclrenderer_b200 import Renderer, distributed as rrd  # noqa: E402
 def run(s, cfg, frames=6):
     r = Renderer(cfg)
     s.upload(r)
+    r.set_profiling(True)
     acc = {}
     for i in range(frames):
         c_pos, c_rot = camera(s, i)

@@ -164,6 +164,9 @@ int rr_read_normals(rr_ctx*, uint16_t* dst);          /* W*H*2 ushort2, screen_n
 int rr_read_shadow(rr_ctx*, int is_static, uint32_t slab, uint32_t* dst);  /* 6*L*L uint32 of one light's cubemap */
 int rr_read_fragments(rr_ctx*, uint32_t* dst, uint32_t max_records, uint32_t* n_records);   /* 5 words each, g_tid_buf engine.cpp:601 */
 int rr_read_cutdown(rr_ctx*, float* dst, uint32_t max_tris, uint32_t* n_tris);              /* 12 floats each, g_cut_tri_mem */
+int rr_set_profiling(rr_ctx*, int on);      /* per-stage CUDA timing events (the reference's -DPROFILING, engine.hpp:625-640). Off by default: every
+                                               timing event is a timestamp write to host memory that the stream waits for, which costs ~2 % of a frame
+                                               and ~15 % while a read-back DMA occupies the PCIe link. Counts and `launches` are always available. */
 int rr_get_timings(rr_ctx*, rr_timings* out);
 
 /* ---- multi-GPU plumbing hooks ---------------------------------------------------------------------------------- */

@@ -137,6 +137,7 @@ struct rr_ctx {
     ClusterBox* d_clusters = nullptr;
     uint8_t* d_cluster_vis = nullptr;            // main view: 0 = culled this frame (k_cluster_vis)
     uint32_t *d_active = nullptr, *d_skipped = nullptr;   // k_frame_prologue: surviving setup blocks, slots skipped in front of each
+    bool stage_events = false;                   // rr_set_profiling: per-stage CUDA timing events for rr_get_timings (the reference's -DPROFILING)
     int cluster_cull = 0;                        // rr_config.cluster_cull: 0 = when the frame is split (sort-first), 1 = always, -1 = never
     uint4* d_cluster_faces = nullptr;            // face sharding: per-cluster cube-face reach of the lights of the pass
     // multi-GPU exchange over peer memory (rr_mgpu_*)
@@ -654,7 +655,8 @@ static int shadow_pass(rr_ctx* c, int only_static) {
     for (size_t first = 0; first < sel.size(); first += SHADOW_MAX_LIGHTS) {
         const int nl = (int)std::min<size_t>(SHADOW_MAX_LIGHTS, sel.size() - first);
         cudaStream_t st = c->stream2;
-        CU(cudaMemsetAsync(c->d_scounters + CTR_S_NFRAG, 0, 2 * 4, st));
+        k_zero_shadow_state<<<16, 256, 0, st>>>(c->d_scounters, c->d_sscan_lookback, c->scan_tiles);
+        c->launches++;
         ShadowSetupParams sp;
         sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
         sp.n_lights = nl;
@@ -678,7 +680,7 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         }
         k_shadow_setup<<<(c->n_tris + 127) / 128, 128, 0, st>>>(sp);
         c->launches++;
-        if ((r = scan_big(c, st, c->d_scounters, c->d_sfragcnt, c->d_sbiglist, c->d_sbigslot, c->d_sscan_lookback, CTR_S_NFRAG, sp.cap_frags))) return r;
+        if ((r = scan_big(c, st, c->d_scounters, c->d_sfragcnt, c->d_sbiglist, c->d_sbigslot, c->d_sscan_lookback, CTR_S_NFRAG, sp.cap_frags, true))) return r;
         dp.frags = c->d_sfrags; dp.cutdown = c->d_scutdown; dp.fragcnt = c->d_sfragcnt; dp.counters = c->d_scounters; dp.cap_frags = sp.cap_frags;
         dp.biglist = c->d_sbiglist; dp.bigslot = c->d_sbigslot;
         dp.n_index = CTR_S_NFRAG;
@@ -699,7 +701,7 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     // setup / depth / id kernels; rr_frame_draw joins right before shading
     CU(cudaEventRecord(c->ev_fork, c->stream));
     CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-    CU(cudaEventRecord(c->ev[EV_SH0], c->stream2));
+    if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SH0], c->stream2));
     const size_t slab = (size_t)6 * c->L * c->L;
     int mgb = 0;
     uint32_t mg_epoch = 0;
@@ -720,9 +722,9 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     if (c->n_shadow && (r = shadow_pass(c, 0))) return r;                                  // engine.cpp:1629-1697
     if (static_lights_dirty && c->n_static && (r = shadow_pass(c, 1))) return r;           // engine.cpp:1699-1784
     if (c->mg.connected && c->n_shadow && (r = mg_push(c, c->stream2, mgb, mg_epoch))) return r;
-    CU(cudaEventRecord(c->ev[EV_SH1], c->stream2));
+    if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SH1], c->stream2));
     CU(cudaEventRecord(c->ev_shadow_done, c->stream2));
-    c->have_shadow_ev = true;
+    c->have_shadow_ev = c->stage_events;
     c->shadow_pending = true;
     return RR_OK;
 }
@@ -746,7 +748,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     int band0, band1, row0, row1;
     band_rows(c, band0, band1, row0, row1);
 
-    CU(cudaEventRecord(c->ev[EV_F0], c->stream));
+    if (c->stage_events) CU(cudaEventRecord(c->ev[EV_F0], c->stream));
     // prearrange
     SetupMainParams sp;
     sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
@@ -765,13 +767,10 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     sp.rowpfx = c->d_rowpfx; sp.cull_rows = c->banded ? 1 : 0;
     sp.cluster_vis = nullptr; sp.active = nullptr; sp.skipped_before = nullptr;
     const bool cull = c->n_objs > 0 && (c->cluster_cull > 0 || (c->cluster_cull == 0 && c->banded));
-    bool scan_zeroed = false;
-    if (!cull) {                                                                           // whole frame on one GPU: nothing to cull by default
-        CU(cudaMemsetAsync(c->d_counters, 0, 4 * 4, c->stream));                           // n_cut, n_frag, overflow, ticket
-        CU(cudaMemsetAsync(c->d_counters + CTR_NSHADE, 0, 3 * 4, c->stream));              // shading list, sample list
-        CU(cudaMemsetAsync(c->d_lookback, 0, (size_t)c->lookback_blocks * 8, c->stream));
-    } else {   // one launch: zero the scan state, classify the clusters (off-screen geometry; rows rasterised elsewhere), compact the blocks
-        scan_zeroed = true;
+    const bool scan_zeroed = true;
+    {   // one launch: zero the scan state and, when culling, classify the clusters (off-screen geometry; rows rasterised elsewhere)
+        // and compact the setup blocks. No cudaMemsetAsync anywhere in the frame: memsets may be placed on the copy engine,
+        // where they wait behind the previous frame's read-back DMA.
         PrologueParams pp;
         pp.cv.boxes = c->d_clusters; pp.cv.n_clusters = c->n_clusters; pp.cv.objs = c->d_objlite; pp.cv.n_objs = c->n_objs;
         pp.cv.cam = cam; pp.cv.width = (float)c->W; pp.cv.height = (float)c->H; pp.cv.fov = c->fov; pp.cv.icut = (float)c->cfg.depth_icutoff;
@@ -779,16 +778,16 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
         pp.vis = c->d_cluster_vis; pp.n_tris = c->n_tris; pp.n_blocks = c->lookback_blocks;
         pp.active = c->d_active; pp.skipped_before = c->d_skipped; pp.counters = c->d_counters; pp.lookback = c->d_lookback;
         pp.scan_lookback = c->d_scan_lookback; pp.scan_tiles = c->scan_tiles;
-        pp.cull = 1;
+        pp.cull = cull ? 1 : 0;
         k_frame_prologue<<<std::max(1u, (c->n_clusters + PROLOGUE_THREADS - 1) / PROLOGUE_THREADS), PROLOGUE_THREADS, 0, c->stream>>>(pp);
         c->launches++;
-        sp.cluster_vis = c->d_cluster_vis; sp.active = c->d_active; sp.skipped_before = c->d_skipped;
+        if (cull) { sp.cluster_vis = c->d_cluster_vis; sp.active = c->d_active; sp.skipped_before = c->d_skipped; }
     }
     sp.sl.samples = c->d_samples; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
     sp.sl.desc = c->d_sample_desc; sp.sl.cap_desc = c->cap_frags; sp.sl.desc_count = c->d_counters + CTR_NDESC; sp.sl.fragcnt = c->d_fragcnt;
     if (c->banded) k_setup_main<true><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     else k_setup_main<false><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
-    CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
+    if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
     // kernel1 / kernel2
     if ((r = scan_big(c, c->stream, c->d_counters, c->d_fragcnt, c->d_biglist, c->d_bigslot, c->d_scan_lookback, CTR_NFRAG, c->cap_frags, scan_zeroed))) return r;
     RasterParams rp;
@@ -799,12 +798,12 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     rp.width = (float)c->W; rp.height = (float)c->H; rp.W = c->W;
     rp.row_lo = row0; rp.row_hi = row1; rp.rowmask = c->d_rowmask; rp.rowbit = ROW_NEEDED;
     if ((r = raster<RM_DEPTH>(c, c->stream, rp))) return r;
-    CU(cudaEventRecord(c->ev[EV_DEPTH], c->stream));
+    if (c->stage_events) CU(cudaEventRecord(c->ev[EV_DEPTH], c->stream));
     rp.row_lo = band0; rp.row_hi = band1; rp.rowbit = ROW_OWNED;
     k_ids_list<<<grid_for(c, 8), 256, 0, c->stream>>>(sp.sl, c->d_depth[c->cur], c->d_ids[c->cur], c->W, band0, band1, c->d_rowmask);
     c->launches++;
     if ((r = raster<RM_IDS>(c, c->stream, rp))) return r;
-    CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
+    if (c->stage_events) CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
     // kernel3
     ShadeParams hp;
     hp.tris = c->d_tris; hp.objs = c->d_objs; hp.objlite = c->d_objlite; hp.lightlite = c->d_lightlite; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
@@ -843,9 +842,9 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
         c->launches++;
     }
     if (mg_composite && c->mg.rank == 0 && (r = mg_wait(c, c->stream, false, c->mg.draw_epoch))) return r;             // composite complete
-    CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
+    if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
     c->launches += 3;
-    c->have_frame_ev = true;
+    c->have_frame_ev = c->stage_events;
     CU(cudaGetLastError());
     return RR_OK;
 }
@@ -919,6 +918,13 @@ int rr_read_cutdown(rr_ctx* c, float* dst, uint32_t max_tris, uint32_t* n_tris) 
     if (n_tris) *n_tris = n;
     uint32_t k = std::min(std::min(n, max_tris), c->cap_cut);
     if (dst && k) return read_back(c, dst, c->d_cutdown, (size_t)k * 48);
+    return RR_OK;
+}
+
+int rr_set_profiling(rr_ctx* c, int on) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    c->stage_events = on != 0;
+    if (!on) c->have_shadow_ev = c->have_frame_ev = false;
     return RR_OK;
 }
 

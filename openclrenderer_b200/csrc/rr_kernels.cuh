@@ -476,7 +476,7 @@ struct PrologueParams {
     uint32_t* active; uint32_t* skipped_before;
     uint32_t* counters; unsigned long long* lookback;
     unsigned long long* scan_lookback; uint32_t scan_tiles;   // k_scan_big's descriptors of the main pass, zeroed here too
-    int cull;                                // 0: no culling (vis = 1 everywhere, identity compaction)
+    int cull;                                // 0: zeroing only
 };
 
 __global__ void __launch_bounds__(PROLOGUE_THREADS) k_frame_prologue(const PrologueParams P) {
@@ -484,9 +484,17 @@ __global__ void __launch_bounds__(PROLOGUE_THREADS) k_frame_prologue(const Prolo
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t i = blockIdx.x * blockDim.x + tid;
-    if (i < P.cv.n_clusters) P.vis[i] = P.cull ? cluster_visible(P.cv, i) : (uint8_t)1;
     for (uint32_t j = i; j < P.n_blocks; j += gridDim.x * blockDim.x) P.lookback[j] = 0ull;
     for (uint32_t j = i; j < P.scan_tiles; j += gridDim.x * blockDim.x) P.scan_lookback[j] = 0ull;
+    if (!P.cull) {                           // whole frame, no culling: only the zeroing (cudaMemsetAsync would queue behind a
+        if (i == 0) {                        // read-back DMA on the copy engine and stall the frame)
+            P.counters[CTR_NCUT] = 0u; P.counters[CTR_NFRAG] = 0u; P.counters[CTR_OVERFLOW] = 0u; P.counters[CTR_TICKET] = 0u;
+            P.counters[CTR_NSAMPLES] = 0u; P.counters[CTR_NDESC] = 0u; P.counters[CTR_NSHADE] = 0u;
+            P.counters[CTR_SLOTS] = 0u; P.counters[CTR_SCAN_TICKET] = 0u; P.counters[CTR_NBIG] = 0u;
+        }
+        return;
+    }
+    if (i < P.cv.n_clusters) P.vis[i] = cluster_visible(P.cv, i);
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(&P.counters[CTR_PROLOGUE_TICKET], 1u) == gridDim.x - 1;
@@ -1302,6 +1310,16 @@ __global__ void __launch_bounds__(256) k_fill_faces(const MgFillParams P) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t pi = i / per_face4, k = i - pi * per_face4;
         reinterpret_cast<uint4*>(P.buffer + (size_t)P.pair[pi] * P.face_words)[k] = ones;
+    }
+}
+
+// state of one shadow pass's allocation and big-fragment scan, zeroed by a kernel (not cudaMemsetAsync: see k_frame_prologue)
+__global__ void __launch_bounds__(256) k_zero_shadow_state(uint32_t* __restrict__ counters, unsigned long long* __restrict__ lookback, uint32_t tiles) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t j = i; j < tiles; j += gridDim.x * blockDim.x) lookback[j] = 0ull;
+    if (i == 0) {
+        counters[CTR_S_NFRAG] = 0u; counters[CTR_S_NCUT] = 0u;
+        counters[CTR_SLOTS] = 0u; counters[CTR_SCAN_TICKET] = 0u; counters[CTR_NBIG] = 0u;
     }
 }
 

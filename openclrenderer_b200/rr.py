@@ -39,6 +39,8 @@ def load_library():
         _LIB.rr_shadows_done.argtypes = [_P]
         _LIB.rr_frame_e2e.restype = C.c_int
         _LIB.rr_frame_e2e.argtypes = [_P, _F4, _F4, _F4, C.c_int, _P]
+        _LIB.rr_set_profiling.restype = C.c_int
+        _LIB.rr_set_profiling.argtypes = [_P, C.c_int]
         _LIB.rr_set_pipeline_depth.restype = C.c_int
         _LIB.rr_set_pipeline_depth.argtypes = [_P, C.c_int]
         _LIB.rr_host_alloc.restype = _P
@@ -109,6 +111,10 @@ class Renderer(CApi):
         r = self._lib.rr_shadows_done(self._ctx)
         if r != RR_OK:
             raise RRError(r, self.last_error())
+
+    def set_profiling(self, on=True):
+        """per-stage CUDA events for timings() (off by default: they cost frame time, see rr.h)"""
+        self._lib.rr_set_profiling(self._ctx, int(bool(on)))
 
     def set_pipeline_depth(self, depth):
         r = self._lib.rr_set_pipeline_depth(self._ctx, int(depth))
