@@ -153,6 +153,7 @@ int rr_lights_write(rr_ctx*, const rr_light* lights, uint32_t n_active);        
 /* ---- per frame ------------------------------------------------------------------------------------------------- */
 int rr_frame_shadows(rr_ctx*, int static_lights_dirty);                                          /* engine::generate_realtime_shadowing engine.cpp:1601-1790 */
 int rr_frame_draw(rr_ctx*, const float c_pos[4], const float c_rot[4], const float clear_rgba[4]); /* engine::draw_bulk_objs_n engine.cpp:2356 -> render_tris 1794-2025 */
+int rr_post_pseudo_aa(rr_ctx*);                                                                  /* engine::do_pseudo_aa engine.cpp:1513 -> do_pseudo_aa cl2.cl:6437-6657; after rr_frame_draw, whole-frame contexts only */
 int rr_swap_buffers(rr_ctx*);                                                                    /* object_context_data::swap_buffers object_context.cpp:17-25 */
 int rr_sync(rr_ctx*);                                                                            /* cl::cqueue.finish(); reports RR_ERR_OVERFLOW */
 

@@ -102,6 +102,7 @@ _SIGS = {
     "frame_shadows": (C.c_int, [_P, C.c_int]),
     "frame_draw": (C.c_int, [_P, _F4, _F4, _F4]),
     "swap_buffers": (C.c_int, [_P]),
+    "post_pseudo_aa": (C.c_int, [_P]),
     "sync": (C.c_int, [_P]),
     "read_depth": (C.c_int, [_P, _P]),
     "read_ids": (C.c_int, [_P, _P]),
@@ -217,6 +218,10 @@ class CApi:
             v = list(v) + [0.0] * (4 - len(v))
             return _F4(*[float(x) for x in v[:4]])
         self._call("frame_draw", f4(c_pos), f4(c_rot), f4(clear))
+
+    def post_pseudo_aa(self):
+        """engine::do_pseudo_aa: edge smoothing of the frame just drawn (before swap_buffers)"""
+        self._call("post_pseudo_aa")
 
     def swap_buffers(self):
         self._call("swap_buffers")

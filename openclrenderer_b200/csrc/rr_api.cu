@@ -100,6 +100,7 @@ struct rr_ctx {
     cudaEvent_t ev_draw_done = nullptr, ev_copy_done[RR_RING_MAX] = {};
     bool copy_pending[RR_RING_MAX] = {};
     ushort2* d_normals = nullptr;
+    uchar4* d_post = nullptr;                    // second colour target of the post passes (rr_post_pseudo_aa)
     uint32_t* d_shade_list = nullptr;            // compacted covered pixels
     uint2* d_samples = nullptr;                  // covered samples of inline-rasterised triangles (pixel, depth)
     uint4* d_sample_desc = nullptr;              // {first sample, count, fragment index}
@@ -457,6 +458,7 @@ void rr_destroy(rr_ctx* c) {
     for (int i = 0; i < 2; i++) { cudaFree(c->d_depth[i]); cudaFree(c->d_ids[i]); }
     if (!c->ext_rgba8) cudaFree(c->d_rgba8);
     cudaFree(c->d_fragcnt); cudaFree(c->d_scan_lookback); cudaFree(c->d_biglist); cudaFree(c->d_bigslot);
+    cudaFree(c->d_post);
     cudaFree(c->d_normals); cudaFree(c->d_shade_list); cudaFree(c->d_samples); cudaFree(c->d_sample_desc); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
@@ -846,6 +848,31 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     c->launches += 3;
     c->have_frame_ev = c->stage_events;
     CU(cudaGetLastError());
+    return RR_OK;
+}
+
+// engine::do_pseudo_aa, engine.cpp:1513-1516 — after rr_frame_draw, before rr_swap_buffers
+int rr_post_pseudo_aa(rr_ctx* c) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    if (c->mg.connected || c->banded) return fail(RR_ERR_INVALID, "rr_post_pseudo_aa: needs the whole frame's depth and normals on one context");
+    if (c->n_tris == 0) return RR_OK;
+    const size_t P = (size_t)c->W * c->H;
+    if (!c->d_post) CU(cudaMalloc((void**)&c->d_post, P * 4));
+    const float aa_arg = 20.f * 2 * RR_PI_F / 360.f;
+    const float cosrad = (float)cos((double)aa_arg);                  // cos() pinned: double on the host, rounded to float
+    dim3 grid((c->W + 31) / 32, (c->H + 7) / 8);
+    k_pseudo_aa<<<grid, 256, 0, c->stream>>>(c->d_rgba8, c->d_post, c->d_depth[c->cur], c->d_normals, c->W, c->H, cosrad);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (c->ext_rgba8) {                                               // caller-owned target: put the result back where the caller expects it
+        k_copy_u32<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_post), reinterpret_cast<uint4*>(c->d_rgba8), P / 4,
+                                                          reinterpret_cast<const uint32_t*>(c->d_post), reinterpret_cast<uint32_t*>(c->d_rgba8), P);
+        c->launches++;
+        CU(cudaGetLastError());
+    } else {                                                          // own target: the post target becomes the colour target
+        for (int i = 0; i < RR_RING_MAX; i++) if (c->d_ring[i] == c->d_rgba8) c->d_ring[i] = c->d_post;
+        std::swap(c->d_rgba8, c->d_post);
+    }
     return RR_OK;
 }
 

@@ -1833,6 +1833,78 @@ __global__ void __launch_bounds__(128) k_shade(const ShadeParams P) {
     }
 }
 
+// =====================================================================================================================
+// k_pseudo_aa == do_pseudo_aa (cl2.cl:6437-6657): edge smoothing on the G-buffer after kernel3. A pixel whose 3x3
+// neighbourhood has exactly one horizontal and one vertical neighbour (plus at least one diagonal) on the other side of a
+// depth step (> 100 units) or of a normal crease (> 20 degrees) becomes 0.65 * mean(same side) + 0.35 * mean(other side).
+// The reference runs it in place on one image (engine.cpp:1854-1856), so its result depends on scheduling; here every read
+// sees kernel3's frame (`in`) and every pixel is written to `out`. Streaming: 12 B/pixel in, 4 B/pixel out.
+// =====================================================================================================================
+__device__ __forceinline__ float3 decode_normal(ushort2 s) {            // short_to_float + decode_normal, cl2.cl:5598-5647
+    float vx = (float)s.x, vy = (float)s.y;
+    vx = vx / 65535.f; vy = vy / 65535.f;
+    vx = vx * 2.f; vy = vy * 2.f;
+    vx = vx - 1.f; vy = vy - 1.f;
+    const float d = vx * vx + vy * vy;
+    const float z = d * 2.f - 1.f;
+    const float l = sqrtf(d);
+    const float k = sqrtf(fmaxf(1.f - z * z, 0.f));
+    return make_float3((vx / l) * k, (vy / l) * k, z);
+}
+
+__global__ void __launch_bounds__(256) k_pseudo_aa(const uchar4* __restrict__ in, uchar4* __restrict__ out, const uint32_t* __restrict__ depth_buffer,
+                                                   const ushort2* __restrict__ normals, int W, int H, float cosrad) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t px = (size_t)y * W + x;
+    const uchar4 mine = in[px];
+    uchar4 res = mine;
+    const uint32_t my_depth_raw = depth_buffer[px];
+    if (x >= 1 && y >= 1 && x < W - 1 && y < H - 1 && my_depth_raw != 0xFFFFFFFFu) {
+        const float3 my_normal = normalize3(decode_normal(normals[px]));
+        const float my_depth = ((float)my_depth_raw * RR_INV_U32MAXF) * RR_DEPTH_FAR;      // idcalc(x / mulint)
+        int num_x[2] = {0, 0}, num_y[2] = {0, 0}, num_corner[2] = {0, 0};
+        float3 my_accum[2] = {make_float3(0, 0, 0), make_float3(0, 0, 0)}, their_accum[2] = {make_float3(0, 0, 0), make_float3(0, 0, 0)};
+        float my_samples[2] = {0.f, 0.f}, their_samples[2] = {0.f, 0.f};
+#pragma unroll
+        for (int j = -1; j < 2; j++) {
+#pragma unroll
+            for (int i = -1; i < 2; i++) {
+                if (i == 0 && j == 0) continue;
+                const size_t q = (size_t)(y + j) * W + (x + i);
+                const float depth = ((float)depth_buffer[q] * RR_INV_U32MAXF) * RR_DEPTH_FAR;
+                const float3 found_normal = decode_normal(normals[q]);
+                const uchar4 cv = in[q];
+                const float3 val = make_float3((float)cv.x / 255.f, (float)cv.y / 255.f, (float)cv.z / 255.f);
+                const bool tests[2] = {fabsf(depth - my_depth) > 100.f, dot3(my_normal, found_normal) < cosrad};
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+                    if (tests[kk]) {
+                        if (i == j || i == -j) num_corner[kk]++;
+                        else if (i == 1 || i == -1) num_x[kk]++;
+                        else num_y[kk]++;
+                        their_accum[kk] = their_accum[kk] + val;
+                        their_samples[kk] += 1.f;
+                    } else {
+                        my_accum[kk] = my_accum[kk] + val;
+                        my_samples[kk] += 1.f;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+            if (num_x[kk] == 1 && num_y[kk] == 1 && num_corner[kk] >= 1) {
+                const float3 ma = my_accum[kk] / my_samples[kk], ta = their_accum[kk] / their_samples[kk];
+                const float3 accum = ma * 0.65f + ta * 0.35f;
+                res = make_uchar4(quant8(accum.x), quant8(accum.y), quant8(accum.z), 255);
+                break;
+            }
+        }
+    }
+    out[px] = res;
+}
+
 __global__ void k_lightlite(const rr_light* __restrict__ lights, uint32_t n, LightLite* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1848,6 +1920,12 @@ __global__ void __launch_bounds__(256) k_bench_atomic_min(uint32_t* buf, uint32_
         s = rand_xorshift(s);
         atomicMin(buf + (s & n_words_mask), s >> 3);
     }
+}
+
+__global__ void __launch_bounds__(256) k_copy_u32(const uint4* __restrict__ src4, uint4* __restrict__ dst4, size_t n4,
+                                                  const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) dst4[i] = src4[i];
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[n4 * 4 + threadIdx.x] = src[n4 * 4 + threadIdx.x];
 }
 
 __global__ void __launch_bounds__(256) k_bench_copy(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {

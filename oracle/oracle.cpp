@@ -1037,6 +1037,82 @@ void kernel3(orc_ctx* c, const float c_pos4[4], const rotsc& crot, const float c
     }
 }
 
+// ---- do_pseudo_aa, cl2.cl:6437-6657 (post pass on the G-buffer) ---------------------------------
+// short_to_float / decode_normal, cl2.cl:5598-5647
+inline f3 decode_normal(const uint16_t* s) {
+    f2 val = {(float)s[0], (float)s[1]};
+    val = {val.x / 65535.f, val.y / 65535.f};
+    val = {val.x * 2.f, val.y * 2.f};
+    val = {val.x - 1.f, val.y - 1.f};
+    f3 ret;
+    const float d = val.x * val.x + val.y * val.y;
+    ret.z = d * 2.f - 1.f;
+    const float l = sqrtf(d);
+    const float k = sqrtf(cl_max(1.f - ret.z * ret.z, 0.f));
+    ret.x = (val.x / l) * k;
+    ret.y = (val.y / l) * k;
+    return ret;
+}
+
+// The reference runs this in place (screen == in_screen == gl_screen[1], engine.cpp:1854-1856), so a pixel may read
+// neighbours the pass has already replaced: the outcome depends on scheduling. Canonical here: every read sees the frame
+// kernel3 produced. Input is the headless RGBA8 target (c / 255.f), output goes through the same quantiser. The id /
+// object lookups, avg_depth and avg_normal of the reference only feed code under REDUCED_AA / #if 0 and are not restated.
+void pseudo_aa(orc_ctx* c) {
+    const int W = c->W, H = c->H;
+    const uint32_t* depth_buffer = c->depth[c->cur].data();
+    const std::vector<uint8_t> in = c->rgba8;
+    const float AA_angle_degrees = 20.f;
+    const float aa_arg = AA_angle_degrees * 2 * CL_M_PI / 360.f;
+    const float AA_angle_cosrad = (float)cos((double)aa_arg);          // cos() pinned: double on the host, rounded to float
+    const float depth_bound = 100;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(c->threads)
+    for (int y = 1; y < H - 1; y++) {
+        for (int x = 1; x < W - 1; x++) {
+            const size_t px = (size_t)y * W + x;
+            f3 my_normal = fast_normalize3(decode_normal(&c->normals[px * 2]));
+            const uint32_t my_depth_raw = depth_buffer[px];
+            if (my_depth_raw == 0xFFFFFFFFu) continue;
+            const float my_depth = ((float)my_depth_raw / U32MAXF) * DEPTH_FAR;             // idcalc
+            int num_x[2] = {0, 0}, num_y[2] = {0, 0}, num_corner[2] = {0, 0};
+            f3 my_accum[2] = {{0, 0, 0}, {0, 0, 0}}, their_accum[2] = {{0, 0, 0}, {0, 0, 0}};
+            float my_samples[2] = {0, 0}, their_samples[2] = {0, 0};
+            for (int j = -1; j < 2; j++) {
+                for (int i = -1; i < 2; i++) {
+                    if (i == 0 && j == 0) continue;
+                    const size_t q = (size_t)(y + j) * W + x + i;
+                    const float depth = ((float)depth_buffer[q] / U32MAXF) * DEPTH_FAR;
+                    const f3 found_normal = decode_normal(&c->normals[q * 2]);
+                    const f3 val = {(float)in[q * 4] / 255.f, (float)in[q * 4 + 1] / 255.f, (float)in[q * 4 + 2] / 255.f};
+                    const int tests[2] = {fabsf(depth - my_depth) > depth_bound, dot3(my_normal, found_normal) < AA_angle_cosrad};
+                    for (int kk = 0; kk < 2; kk++) {
+                        if (tests[kk]) {
+                            if (i == j || i == -j) num_corner[kk]++;
+                            else if (i == 1 || i == -1) num_x[kk]++;
+                            else if (j == 1 || j == -1) num_y[kk]++;
+                            their_accum[kk] = their_accum[kk] + val;
+                            their_samples[kk] += 1.f;
+                        } else {
+                            my_accum[kk] = my_accum[kk] + val;
+                            my_samples[kk] += 1.f;
+                        }
+                    }
+                }
+            }
+            for (int kk = 0; kk < 2; kk++) {
+                if (num_x[kk] == 1 && num_y[kk] == 1 && num_corner[kk] >= 1) {
+                    const float wm = 0.65f, wt = 0.35f;
+                    const f3 ma = my_accum[kk] / my_samples[kk], ta = their_accum[kk] / their_samples[kk];
+                    const f3 accum = ma * wm + ta * wt;
+                    const float o[4] = {accum.x, accum.y, accum.z, 1.f};
+                    for (int k = 0; k < 4; k++) c->rgba8[px * 4 + k] = (uint8_t)(cl_clamp(o[k], 0.f, 1.f) * 255.f + 0.5f);
+                    break;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -1184,6 +1260,9 @@ int orc_stage_setup(orc_ctx* c, const float c_pos[4], const float c_rot[4]) {
 }
 int orc_stage_depth(orc_ctx* c) { kernel1(c); return RR_OK; }
 int orc_stage_ids(orc_ctx* c) { kernel2(c); return RR_OK; }
+
+// engine::do_pseudo_aa, engine.cpp:1513-1516: after orc_frame_draw, before orc_swap_buffers
+int orc_post_pseudo_aa(orc_ctx* c) { pseudo_aa(c); return RR_OK; }
 
 int orc_swap_buffers(orc_ctx* c) { c->cur ^= 1; return RR_OK; }        // depth_buffer.flip(), object_context.cpp:21
 int orc_sync(orc_ctx*) { return RR_OK; }
