@@ -41,6 +41,16 @@ def _worker(rank, world, port, q):
     fb = torch.from_numpy(o.read_rgba8().copy())
     rows = H // world
     rrd.gather_bands(fb, rows, rank, world, dst=0)
+    # interleaved split (the peer-memory path's row ownership): rows of foreign tiles blanked, then gather_tiles to rank 0
+    tile = 16
+    own = rrd.owned_rows(H, tile, world, rank)
+    whole = Oracle(s.cfg, threads=1)
+    s.upload(whole)
+    whole.frame_shadows(1)
+    whole.frame_draw(s.c_pos, s.c_rot, s.clear)
+    fbt = torch.from_numpy(whole.read_rgba8().copy())
+    fbt[torch.from_numpy(~own)] = 0
+    rrd.gather_tiles(fbt, tile, rank, world, dst=0)
     if rank == 0:
         ref = Oracle(s.cfg, threads=1)
         s.upload(ref)
@@ -50,7 +60,8 @@ def _worker(rank, world, port, q):
         ok_frame = np.array_equal(ref.read_rgba8(), fb.numpy())
         y0, y1 = rrd.band_rows(H, world, 0)
         ok_depth = np.array_equal(ref.read_depth(), o.read_depth())
-        q.put((ok_shadow, ok_frame, ok_depth))
+        ok_tiles = np.array_equal(ref.read_rgba8(), fbt.numpy())
+        q.put((ok_shadow, ok_frame, ok_depth, ok_tiles))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,4 +77,4 @@ def test_two_rank_band_and_face_exchange_matches_single_process():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert res == (True, True, True), res
+    assert res == (True, True, True, True), res
