@@ -140,6 +140,18 @@ int rr_scene_write_tris(rr_ctx*, uint32_t first, uint32_t count, const rr_triang
 int rr_scene_write_objs(rr_ctx*, uint32_t first, uint32_t count, const rr_obj_desc* objs);       /* alloc_object_descriptors object_context.cpp:460-484 */
 int rr_scene_patch_obj(rr_ctx*, uint32_t obj_id, uint32_t byte_off, uint32_t nbytes, const void* src); /* object::g_flush partial writes object.cpp:652-857 */
 
+/* ---- asynchronous rebuild (object_context::build(async) + flip_buffers, object_context.cpp:520-797) ------------------
+ * The reference rebuilds a changed scene into `new_gpu_dat` on a second queue while the old one keeps rendering, and flips
+ * when the uploads are done. Same here: begin sizes a BACK scene (buffers are reused when they are large enough; growing
+ * them costs one device synchronisation), the writes go to it on an upload stream, commit makes every frame enqueued
+ * afterwards use it — the render stream waits for the uploads on the device, the host never blocks. Frames already
+ * enqueued finish on the old scene, which becomes the next back scene. */
+int rr_scene_build_begin(rr_ctx*, uint32_t n_tris, uint32_t n_objs);
+int rr_scene_build_write_objs(rr_ctx*, uint32_t first, uint32_t count, const rr_obj_desc* objs);
+int rr_scene_build_write_tris(rr_ctx*, uint32_t first, uint32_t count, const rr_triangle* tris);   /* page-locked `tris` must stay valid until rr_scene_build_ready() */
+int rr_scene_build_ready(rr_ctx*);                /* 1 once the uploads have landed (object_context::ready_to_flip); commit does not need it */
+int rr_scene_build_commit(rr_ctx*);               /* flip_buffers */
+
 /* ---- texture atlas (texture_context::alloc_gpu texture_context.cpp:350-517) ------------------------------------ */
 int rr_atlas_alloc(rr_ctx*, uint32_t n_slices, const uint32_t* nums, uint32_t n_nums,
                    const uint32_t* sizes, uint32_t n_sizes, uint32_t mipmap_start);              /* g_texture_array / g_texture_nums / g_texture_sizes */

@@ -95,6 +95,11 @@ _SIGS = {
     "scene_write_objs": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
     "scene_patch_obj": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
     "atlas_alloc": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, C.c_uint32]),
+    "scene_build_begin": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "scene_build_write_objs": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
+    "scene_build_write_tris": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
+    "scene_build_ready": (C.c_int, [_P]),
+    "scene_build_commit": (C.c_int, [_P]),
     "atlas_upload": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_int]),
     "atlas_write_raw": (C.c_int, [_P, _P, C.c_size_t]),
     "atlas_read_raw": (C.c_int, [_P, _P, C.c_size_t]),
@@ -180,6 +185,23 @@ class CApi:
     def scene_patch_obj(self, obj_id, byte_off, data):
         b = np.frombuffer(bytes(data), dtype=np.uint8)
         self._call("scene_patch_obj", obj_id, byte_off, len(b), _ptr(b))
+
+    # -- asynchronous rebuild (object_context::build(async) + flip_buffers)
+    def scene_build(self, tris, objs, commit=True):
+        """upload a whole new scene into the back buffers while the current one keeps rendering; flip on commit"""
+        tris = np.ascontiguousarray(tris, dtype=TRIANGLE)
+        objs = np.ascontiguousarray(objs, dtype=OBJ_DESC)
+        self._call("scene_build_begin", len(tris), len(objs))
+        self._call("scene_build_write_objs", 0, len(objs), _ptr(objs))
+        self._call("scene_build_write_tris", 0, len(tris), _ptr(tris))
+        if commit:
+            self._call("scene_build_commit")
+
+    def scene_build_ready(self):
+        return bool(getattr(self._lib, self._prefix + "scene_build_ready")(self._ctx))
+
+    def scene_build_commit(self):
+        self._call("scene_build_commit")
 
     # -- atlas
     def atlas_alloc(self, n_slices, nums, sizes, mipmap_start):

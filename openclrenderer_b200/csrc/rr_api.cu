@@ -53,6 +53,30 @@ enum { EV_SH0, EV_SH1, EV_F0, EV_SETUP, EV_DEPTH, EV_IDS, EV_SHADE, EV_COUNT };
 
 }  // namespace
 
+// The device scene that is NOT being rendered: object_context::build(async) fills it on the upload stream while frames keep
+// coming from the front scene (the flat fields of rr_ctx), and rr_scene_build_commit swaps the two (flip_buffers,
+// object_context.cpp:520-590). Same fields as the front scene; buffers are reused when they are large enough.
+struct SceneBuf {
+    uint32_t n_tris = 0, n_objs = 0, tri_cap = 0, obj_cap = 0;
+    rr_triangle* d_tris = nullptr;
+    float4 *d_pa = nullptr, *d_pb = nullptr;
+    float2* d_pc = nullptr;
+    rr_obj_desc* d_objs = nullptr;
+    ObjLite* d_objlite = nullptr;
+    uint32_t* d_obj_r2 = nullptr;
+    int2* d_obj_rows = nullptr;
+    uint32_t n_clusters = 0;
+    ClusterBox* d_clusters = nullptr;
+    uint8_t* d_cluster_vis = nullptr;
+    uint4* d_cluster_faces = nullptr;
+    uint32_t *d_active = nullptr, *d_skipped = nullptr;
+    float4 *d_cutdown = nullptr, *d_scutdown = nullptr;
+    uint32_t cap_cut = 0;
+    unsigned long long* d_lookback = nullptr;
+    uint32_t lookback_blocks = 0;
+    rr_obj_desc* h_objs_pinned = nullptr;
+};
+
 struct rr_ctx {
     rr_config cfg;
     float fov = 0;
@@ -63,6 +87,7 @@ struct rr_ctx {
     bool have_shadow_ev = false, have_frame_ev = false;
     // scene
     uint32_t n_tris = 0, n_objs = 0;
+    uint32_t tri_cap = 0, obj_cap = 0;           // what the scene buffers were sized for (they swap with the back scene, rr_scene_build_*)
     rr_triangle* d_tris = nullptr;
     float4 *d_pa = nullptr, *d_pb = nullptr;
     float2* d_pc = nullptr;
@@ -160,10 +185,17 @@ struct rr_ctx {
         uchar4* saved_rgba8 = nullptr; bool saved_ext_rgba8 = false;
     } mg;
     int mg_target = 0;                           // which of the colour-target pair this draw goes to (rr_frame_e2e alternates)
+    // asynchronous scene rebuild (rr_scene_build_*)
+    SceneBuf back;
+    cudaStream_t stream4 = nullptr;              // upload stream of the rebuild (the reference's cqueue2)
+    cudaEvent_t ev_built = nullptr, ev_retire = nullptr;
+    bool building = false, retire_pending = false;
     // stats
     uint32_t launches = 0;
     FaceTable faces;
 };
+
+static void scene_free_fwd(rr_ctx* c);           // frees the back scene of an asynchronous rebuild (defined with rr_scene_build_*)
 
 namespace {
 
@@ -438,6 +470,10 @@ void rr_destroy(rr_ctx* c) {
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream3) cudaStreamSynchronize(c->stream3);
     rr_mgpu_disconnect(c);
+    if (c->stream4) { cudaStreamSynchronize(c->stream4); cudaStreamDestroy(c->stream4); }
+    if (c->ev_built) cudaEventDestroy(c->ev_built);
+    if (c->ev_retire) cudaEventDestroy(c->ev_retire);
+    scene_free_fwd(c);
     for (int i = 1; i < RR_RING_MAX; i++) if (c->d_ring[i]) cudaFree(c->d_ring[i]);
     if (!c->ext_rgba8 && c->d_ring[0]) c->d_rgba8 = c->d_ring[0];      // the context's own target (freed below)
     if (c->ev_draw_done) cudaEventDestroy(c->ev_draw_done);
@@ -472,7 +508,7 @@ int rr_scene_alloc(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
     if (!c) return fail(RR_ERR_INVALID, "null ctx");
     if (n_tris >= (1u << 26)) return fail(RR_ERR_INVALID, "rr_scene_alloc: %u triangles exceeds the 2^26 limit of the scan descriptor", n_tris);
     CU(cudaStreamSynchronize(c->stream));
-    c->n_tris = n_tris; c->n_objs = n_objs;
+    c->n_tris = n_tris; c->n_objs = n_objs; c->tri_cap = n_tris; c->obj_cap = n_objs;
     int r;
     if ((r = dev_alloc(c->d_tris, n_tris))) return r;
     if ((r = dev_alloc(c->d_pa, n_tris))) return r;
@@ -537,6 +573,141 @@ int rr_scene_patch_obj(rr_ctx* c, uint32_t obj_id, uint32_t byte_off, uint32_t n
     memcpy((char*)(c->h_objs_pinned + obj_id) + byte_off, src, nbytes);
     CU(cudaMemcpyAsync((char*)(c->d_objs + obj_id) + byte_off, (char*)(c->h_objs_pinned + obj_id) + byte_off, nbytes, cudaMemcpyHostToDevice, c->stream));
     c->objlite_dirty = true;
+    return RR_OK;
+}
+
+// ---- asynchronous rebuild: object_context::build(async) + flip_buffers (object_context.cpp:520-797) ------------------
+static int join_shadows_fwd(rr_ctx* c);
+namespace {
+int back_alloc_bytes(void** p, size_t bytes) {   // plain cudaMalloc: only called when the back scene has to grow
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    CU(cudaMalloc(p, std::max<size_t>(bytes, 1)));
+    return RR_OK;
+}
+#define back_alloc(ptr, count) back_alloc_bytes((void**)&(ptr), (size_t)(count) * sizeof(*(ptr)))
+
+void scene_swap(rr_ctx* c, SceneBuf& b) {
+    std::swap(c->n_tris, b.n_tris); std::swap(c->n_objs, b.n_objs); std::swap(c->tri_cap, b.tri_cap); std::swap(c->obj_cap, b.obj_cap);
+    std::swap(c->d_tris, b.d_tris); std::swap(c->d_pa, b.d_pa); std::swap(c->d_pb, b.d_pb); std::swap(c->d_pc, b.d_pc);
+    std::swap(c->d_objs, b.d_objs); std::swap(c->d_objlite, b.d_objlite); std::swap(c->d_obj_r2, b.d_obj_r2); std::swap(c->d_obj_rows, b.d_obj_rows);
+    std::swap(c->n_clusters, b.n_clusters); std::swap(c->d_clusters, b.d_clusters); std::swap(c->d_cluster_vis, b.d_cluster_vis);
+    std::swap(c->d_cluster_faces, b.d_cluster_faces); std::swap(c->d_active, b.d_active); std::swap(c->d_skipped, b.d_skipped);
+    std::swap(c->d_cutdown, b.d_cutdown); std::swap(c->d_scutdown, b.d_scutdown); std::swap(c->cap_cut, b.cap_cut);
+    std::swap(c->d_lookback, b.d_lookback); std::swap(c->lookback_blocks, b.lookback_blocks); std::swap(c->h_objs_pinned, b.h_objs_pinned);
+}
+
+void scene_free(SceneBuf& b) {
+    cudaFree(b.d_tris); cudaFree(b.d_pa); cudaFree(b.d_pb); cudaFree(b.d_pc); cudaFree(b.d_objs); cudaFree(b.d_objlite); cudaFree(b.d_obj_r2);
+    cudaFree(b.d_obj_rows); cudaFree(b.d_clusters); cudaFree(b.d_cluster_vis); cudaFree(b.d_cluster_faces); cudaFree(b.d_active); cudaFree(b.d_skipped);
+    cudaFree(b.d_cutdown); cudaFree(b.d_scutdown); cudaFree(b.d_lookback);
+    if (b.h_objs_pinned) cudaFreeHost(b.h_objs_pinned);
+    b = SceneBuf();
+}
+}  // namespace
+
+}  // extern "C"
+static void scene_free_fwd(rr_ctx* c) { scene_free(c->back); }
+extern "C" {
+
+int rr_scene_build_begin(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    if (c->building) return fail(RR_ERR_INVALID, "rr_scene_build_begin: a rebuild is already in progress (commit it first)");
+    if (n_tris >= (1u << 26)) return fail(RR_ERR_INVALID, "rr_scene_build_begin: %u triangles exceeds the 2^26 limit of the scan descriptor", n_tris);
+    if (!c->stream4) {
+        CU(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_built, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_retire, cudaEventDisableTiming));
+    }
+    // the back buffers were the front scene until the last commit: frames enqueued before it may still read them
+    if (c->retire_pending) { CU(cudaStreamWaitEvent(c->stream4, c->ev_retire, 0)); }
+    SceneBuf& b = c->back;
+    int r;
+    const uint32_t n_clusters = (n_tris + CLUSTER_TRIS - 1) / CLUSTER_TRIS, blocks = (n_tris + SETUP_THREADS - 1) / SETUP_THREADS;
+    const uint32_t cap_cut = c->cfg.max_cutdown ? c->cfg.max_cutdown : (uint32_t)std::min<uint64_t>((uint64_t)n_tris * 6 + 1024, 0x7FFFFFFFu);
+    if (n_tris > b.tri_cap || cap_cut > b.cap_cut) {                 // grow (cudaFree of the old buffers synchronises the device once)
+        if (c->retire_pending) { CU(cudaEventSynchronize(c->ev_retire)); }
+        if ((r = back_alloc(b.d_tris, n_tris))) return r;
+        if ((r = back_alloc(b.d_pa, n_tris))) return r;
+        if ((r = back_alloc(b.d_pb, n_tris))) return r;
+        if ((r = back_alloc(b.d_pc, n_tris))) return r;
+        if ((r = back_alloc(b.d_clusters, (size_t)n_clusters))) return r;
+        if ((r = back_alloc(b.d_cluster_vis, (size_t)n_clusters + 2))) return r;
+        if ((r = back_alloc(b.d_cluster_faces, (size_t)n_clusters))) return r;
+        if ((r = back_alloc(b.d_cutdown, (size_t)cap_cut * 3))) return r;
+        if ((r = back_alloc(b.d_scutdown, (size_t)cap_cut * 3))) return r;
+        if ((r = back_alloc(b.d_lookback, (size_t)blocks))) return r;
+        if ((r = back_alloc(b.d_active, (size_t)blocks))) return r;
+        if ((r = back_alloc(b.d_skipped, (size_t)blocks))) return r;
+        b.tri_cap = n_tris;
+    }
+    if (n_objs > b.obj_cap) {
+        if (c->retire_pending) { CU(cudaEventSynchronize(c->ev_retire)); }
+        if ((r = back_alloc(b.d_objs, n_objs))) return r;
+        if ((r = back_alloc(b.d_objlite, n_objs))) return r;
+        if ((r = back_alloc(b.d_obj_r2, n_objs))) return r;
+        if ((r = back_alloc(b.d_obj_rows, n_objs))) return r;
+        if (b.h_objs_pinned) cudaFreeHost(b.h_objs_pinned);
+        b.h_objs_pinned = nullptr;
+        CU(cudaMallocHost((void**)&b.h_objs_pinned, std::max<size_t>(1, n_objs) * sizeof(rr_obj_desc)));
+        b.obj_cap = n_objs;
+    }
+    b.n_tris = n_tris; b.n_objs = n_objs; b.n_clusters = n_clusters; b.lookback_blocks = blocks; b.cap_cut = cap_cut;
+    CU(cudaMemsetAsync(b.d_clusters, 0, std::max<size_t>(1, n_clusters) * sizeof(ClusterBox), c->stream4));
+    CU(cudaMemsetAsync(b.d_obj_r2, 0, std::max<size_t>(1, n_objs) * 4, c->stream4));
+    c->building = true;
+    return RR_OK;
+}
+
+int rr_scene_build_write_objs(rr_ctx* c, uint32_t first, uint32_t count, const rr_obj_desc* objs) {
+    if (!c || !objs) return fail(RR_ERR_INVALID, "null argument");
+    if (!c->building) return fail(RR_ERR_INVALID, "rr_scene_build_write_objs outside rr_scene_build_begin / commit");
+    SceneBuf& b = c->back;
+    if ((uint64_t)first + count > b.n_objs) return fail(RR_ERR_INVALID, "rr_scene_build_write_objs: range outside %u", b.n_objs);
+    if (count == 0) return RR_OK;
+    memcpy(b.h_objs_pinned + first, objs, (size_t)count * sizeof(rr_obj_desc));
+    CU(cudaMemcpyAsync(b.d_objs + first, b.h_objs_pinned + first, (size_t)count * sizeof(rr_obj_desc), cudaMemcpyHostToDevice, c->stream4));
+    return RR_OK;
+}
+
+int rr_scene_build_write_tris(rr_ctx* c, uint32_t first, uint32_t count, const rr_triangle* tris) {
+    if (!c || !tris) return fail(RR_ERR_INVALID, "null argument");
+    if (!c->building) return fail(RR_ERR_INVALID, "rr_scene_build_write_tris outside rr_scene_build_begin / commit");
+    SceneBuf& b = c->back;
+    if ((uint64_t)first + count > b.n_tris) return fail(RR_ERR_INVALID, "rr_scene_build_write_tris: range [%u,+%u) outside %u", first, count, b.n_tris);
+    if (count == 0) return RR_OK;
+    // pageable `tris`: the runtime stages the copy before returning, the caller may free it; page-locked `tris`: a true
+    // asynchronous DMA, the memory must stay valid until rr_scene_build_ready() (object.cpp:729-731 has the same rule)
+    CU(cudaMemcpyAsync(b.d_tris + first, tris, (size_t)count * sizeof(rr_triangle), cudaMemcpyHostToDevice, c->stream4));
+    k_repack<<<(count + 255) / 256, 256, 0, c->stream4>>>(b.d_tris, first, count, b.d_pa, b.d_pb, b.d_pc, b.d_obj_r2, b.n_objs);
+    const uint32_t cl0 = first / CLUSTER_TRIS, cl1 = (first + count - 1) / CLUSTER_TRIS;
+    k_cluster_bounds<<<cl1 - cl0 + 1, CLUSTER_TRIS, 0, c->stream4>>>(b.d_pa, b.d_pb, b.d_pc, b.n_tris, cl0, b.d_clusters);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return RR_OK;
+}
+
+int rr_scene_build_ready(rr_ctx* c) {
+    if (!c || !c->building) return 0;
+    cudaError_t e = cudaStreamQuery(c->stream4);
+    if (e == cudaSuccess) return 1;
+    if (e != cudaErrorNotReady) fail(RR_ERR_CUDA, "rr_scene_build_ready: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return 0;
+}
+
+int rr_scene_build_commit(rr_ctx* c) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    if (!c->building) return fail(RR_ERR_INVALID, "rr_scene_build_commit without rr_scene_build_begin");
+    // frames enqueued so far read the current front scene: it becomes reusable once they are done
+    if (c->shadow_pending) { int r = join_shadows_fwd(c); if (r) return r; }
+    CU(cudaEventRecord(c->ev_retire, c->stream));
+    c->retire_pending = true;
+    // frames enqueued from now on read the new scene, and only after its uploads have landed (no host synchronisation)
+    CU(cudaEventRecord(c->ev_built, c->stream4));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_built, 0));
+    scene_swap(c, c->back);
+    c->objlite_dirty = true;
+    c->building = false;
     return RR_OK;
 }
 
@@ -738,6 +909,7 @@ static int join_shadows(rr_ctx* c) {
     }
     return RR_OK;
 }
+static int join_shadows_fwd(rr_ctx* c) { return join_shadows(c); }
 
 int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const float clear_rgba[4]) {
     if (!c || !c_pos || !c_rot) return fail(RR_ERR_INVALID, "null argument");

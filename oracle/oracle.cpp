@@ -316,8 +316,8 @@ struct orc_ctx {
     float fov;
     int W, H, L;
     int threads;
-    std::vector<rr_triangle> tris;
-    std::vector<rr_obj_desc> objs;
+    std::vector<rr_triangle> tris, back_tris;
+    std::vector<rr_obj_desc> objs, back_objs;
     std::vector<rr_light> lights;
     std::vector<uint8_t> atlas;       // uchar4[2048*2048*slices]
     std::vector<uint32_t> nums, sizes;
@@ -1159,6 +1159,18 @@ void orc_destroy(orc_ctx* c) { delete c; }
 int orc_threads(orc_ctx* c) { return c->threads; }
 
 int orc_scene_alloc(orc_ctx* c, uint32_t n_tris, uint32_t n_objs) { c->tris.assign(n_tris, rr_triangle{}); c->objs.assign(n_objs, rr_obj_desc{}); return RR_OK; }
+// object_context::build(async) + flip_buffers: the checker rebuilds synchronously into a second scene and swaps on commit
+int orc_scene_build_begin(orc_ctx* c, uint32_t n_tris, uint32_t n_objs) { c->back_tris.assign(n_tris, rr_triangle{}); c->back_objs.assign(n_objs, rr_obj_desc{}); return RR_OK; }
+int orc_scene_build_write_tris(orc_ctx* c, uint32_t first, uint32_t count, const rr_triangle* t) {
+    if ((size_t)first + count > c->back_tris.size()) return RR_ERR_INVALID;
+    memcpy(&c->back_tris[first], t, (size_t)count * sizeof(rr_triangle)); return RR_OK;
+}
+int orc_scene_build_write_objs(orc_ctx* c, uint32_t first, uint32_t count, const rr_obj_desc* o) {
+    if ((size_t)first + count > c->back_objs.size()) return RR_ERR_INVALID;
+    memcpy(&c->back_objs[first], o, (size_t)count * sizeof(rr_obj_desc)); return RR_OK;
+}
+int orc_scene_build_ready(orc_ctx*) { return 1; }
+int orc_scene_build_commit(orc_ctx* c) { c->tris.swap(c->back_tris); c->objs.swap(c->back_objs); return RR_OK; }
 int orc_scene_write_tris(orc_ctx* c, uint32_t first, uint32_t count, const rr_triangle* t) {
     if ((size_t)first + count > c->tris.size()) return RR_ERR_INVALID;
     memcpy(&c->tris[first], t, (size_t)count * sizeof(rr_triangle)); return RR_OK;

@@ -173,6 +173,55 @@ def test_cluster_culling_keeps_records_exact(rot_y, rot_x):
     assert_frame_parity(g, o, label=f"culling rot_y={rot_y}")
 
 
+def test_async_rebuild_flips_between_scenes():
+    """object_context::build(async) + flip_buffers (object_context.cpp:520-797; SURVEY.md §8f rank 1): a new scene is uploaded
+    into the back buffers while frames keep coming from the old one; after the commit the frame equals the oracle's (and a
+    fresh context's) render of the new scene. Covers a smaller scene (buffers reused), a larger one (buffers grow) and the
+    way back."""
+    kw = dict(n_lights=2, light_dim=128, tex_sizes=(128, 64))
+    sA = scene.scene_spheres(640, 360, n_spheres=8, grid=(4, 2), seed=5, **kw)
+    sB = scene.scene_spheres(640, 360, n_spheres=5, grid=(3, 2), seed=6, **kw)
+    sC = scene.scene_spheres(640, 360, n_spheres=14, grid=(5, 3), seed=7, **kw)
+    g, o = Renderer(sA.cfg), Oracle(sA.cfg, threads=0)
+    for x in (g, o):
+        sA.upload(x)
+
+    def frame(label, dirty=0):
+        for x in (g, o):
+            x.frame_shadows(dirty)
+            x.frame_draw(sA.c_pos, sA.c_rot, sA.clear)
+            x.sync()
+        st = assert_frame_parity(g, o, label=label)
+        col = g.read_rgba8()
+        for x in (g, o):
+            x.swap_buffers()
+        return col, st
+
+    frame("A", 1)
+    cur = sA
+    for nxt, name in ((sB, "B"), (sC, "C"), (sA, "A again")):
+        for x in (g, o):
+            x.scene_build(nxt.tris, nxt.objs, commit=False)
+        before, _ = frame(f"still {cur.name} while {name} uploads")      # the old scene keeps rendering during the upload
+        for x in (g, o):
+            x.scene_build_commit()
+        after, st = frame(name)
+        assert st["covered"] > 50
+        assert not np.array_equal(before, after)
+        fresh = Renderer(sA.cfg)                                         # same atlas / lights, the new geometry
+        sA.upload(fresh)
+        fresh.scene_alloc(len(nxt.tris), len(nxt.objs))
+        fresh.scene_write_objs(nxt.objs)
+        fresh.scene_write_tris(nxt.tris)
+        fresh.frame_shadows(0)
+        fresh.frame_draw(sA.c_pos, sA.c_rot, sA.clear)
+        fresh.sync()
+        assert np.array_equal(fresh.read_rgba8(), after), f"{name}: rebuilt context differs from a fresh one"
+        fresh.close()
+        cur = nxt
+    assert g.scene_build_ready() is False                                # nothing in flight
+
+
 def test_overflow_is_reported():
     s = _soup(5, 400, 320, 200, True)
     cfg = s.cfg.copy(max_fragments=64)
