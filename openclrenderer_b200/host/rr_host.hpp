@@ -254,10 +254,25 @@ struct object_context {
     object_context_data* fetch() { return &gpu_dat; }
     void set_clear_colour(const cl_float4& col) { gpu_dat.g_clear_col = col; }
     void attach(rr_ctx* dev) { gpu_dat.dev = dev; }
-    // object_context::build (object_context.cpp:646-797): textures -> descriptors (228-339) -> triangles (346-458)
-    void build(bool /*force*/ = false) {
+    // object_context::build_request / build_tick (object_context.cpp:614-640): rebuild lazily, once per frame at most
+    bool request_dirty = false, rebuilding_async = false;
+    void build_request() { request_dirty = true; }
+    void build_tick(bool async = false) { if (request_dirty) { build(false, async); request_dirty = false; } }
+    // flip_buffers (object_context.cpp:520-590): called once per frame by the render loop; swaps in an asynchronous rebuild.
+    // The device waits for the uploads on its own, so the flip never blocks the host (the reference waits for an event callback).
+    void flip() {
+        if (!rebuilding_async) return;
+        if (rr_scene_build_commit(gpu_dat.dev)) rr_fatal("rr_scene_build_commit");
+        rebuilding_async = false;
+    }
+    // object_context::build (object_context.cpp:646-797): textures -> descriptors (228-339) -> triangles (346-458).
+    // async: the geometry goes into the device's back scene on its upload stream while frames keep rendering the current one
+    // (new_gpu_dat on cqueue2 in the reference); flip() makes it current. Textures are rebuilt synchronously either way.
+    void build(bool /*force*/ = false, bool async = false) {
         rr_ctx* dev = gpu_dat.dev;
         if (!dev) throw std::runtime_error("object_context::build before engine::load");
+        if (rebuilding_async) flip();                                                              // object_context.cpp:651-658 ("cap")
+        if (gpu_dat.tri_num == 0) async = false;                                                   // "we want there to be some valid gpu presence" (723)
         gpu_dat.tex_gpu_ctx = tex_ctx.alloc_gpu(*this, dev);
         std::vector<rr_obj_desc> desc;
         int triangle_count = 0;
@@ -281,18 +296,21 @@ struct object_context {
                 desc.push_back(d);
             }
         }
-        if (rr_scene_alloc(dev, (uint32_t)triangle_count, (uint32_t)desc.size())) rr_fatal("rr_scene_alloc");
-        if (!desc.empty() && rr_scene_write_objs(dev, 0, (uint32_t)desc.size(), desc.data())) rr_fatal("rr_scene_write_objs");
+        auto write_objs = async ? rr_scene_build_write_objs : rr_scene_write_objs;
+        auto write_tris = async ? rr_scene_build_write_tris : rr_scene_write_tris;
+        if ((async ? rr_scene_build_begin : rr_scene_alloc)(dev, (uint32_t)triangle_count, (uint32_t)desc.size())) rr_fatal("rr_scene_alloc");
+        if (!desc.empty() && write_objs(dev, 0, (uint32_t)desc.size(), desc.data())) rr_fatal("rr_scene_write_objs");
         for (auto* c : containers) {
             if (!c->isactive) continue;
             for (auto& it : c->objs) {
                 for (auto& t : it.tri_list) t.vertices[0].set_pad((cl_uint)it.object_g_id);       // object_context.cpp:427 / fill_ids
                 if (!it.tri_list.empty() &&
-                    rr_scene_write_tris(dev, (uint32_t)it.gpu_tri_start, (uint32_t)it.tri_list.size(), (const rr_triangle*)it.tri_list.data()))
+                    write_tris(dev, (uint32_t)it.gpu_tri_start, (uint32_t)it.tri_list.size(), (const rr_triangle*)it.tri_list.data()))
                     rr_fatal("rr_scene_write_tris");
             }
         }
         gpu_dat.tri_num = triangle_count; gpu_dat.obj_num = (int)desc.size();
+        rebuilding_async = async;
     }
     void flush_locations() { for (auto* c : containers) if (c->isactive) c->g_flush_objects(gpu_dat.dev); }   // object_context.cpp:819
 };
