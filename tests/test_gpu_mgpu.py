@@ -3,7 +3,8 @@ contexts in this process wired with rr_mgpu_connect_local, so the whole protocol
 flags, k_wait_flags, shading straight into rank 0's frame buffer, interleaved row tiles, per-object face reach) runs and
 is compared bit for bit with a single-context frame. The cross-process / cross-GPU variant (cudaIpc handles exchanged over
 torch.distributed) is what `bench.py --gpus N` runs; `bench.py --gpus N --verify` checks its composite against the frame one
-GPU renders alone (profiles/r1m_bench_*gpu_p2p.json: 0 pixels differ at 2, 4 and 8 GPUs)."""
+GPU renders alone (profiles/r1m_bench_*gpu_p2p.json: 0 pixels differ at 2, 4 and 8 GPUs) and tests/test_gpu_mgpu_ipc.py runs
+exactly that under pytest when two GPUs are visible."""
 import numpy as np
 import pytest
 
