@@ -315,6 +315,43 @@ struct object_context {
     void flush_locations() { for (auto* c : containers) if (c->isactive) c->g_flush_objects(gpu_dat.dev); }   // object_context.cpp:819
 };
 
+// The page planner of texture_context::alloc_gpu as a pure function (texture_context.cpp:94-261): `dims` = largest dimension
+// of every texture in gpu-id order. nums[i] = slice << 16 | index for the base levels, then nums[n + 4*i + level] for the
+// four mips of texture i; sizes[slice] = tile size of the slice. Pages are keyed by size ascending (std::map) and indices
+// count down from the page's population. Cross-checked against the Python mirror (scene.plan_atlas) on thousands of
+// textures by tests/test_host_cpp.py.
+inline void plan_texture_pages(const std::vector<int>& dims, std::vector<cl_uint>& nums, std::vector<cl_uint>& sizes) {
+    const int MIPS = 4, MAXSZ = 2048;
+    std::map<size_t, int> size_to_numbers;
+    for (int s : dims) {
+        size_to_numbers[s]++;
+        for (int j = 0; j < MIPS; j++) size_to_numbers[s / (1 << (j + 1))]++;
+    }
+    struct page { int size, n; };
+    std::vector<page> pages;
+    for (auto& kv : size_to_numbers) {
+        if (kv.first == 0) throw std::runtime_error("texture too small for 4 mip levels");
+        int per = (MAXSZ / (int)kv.first) * (MAXSZ / (int)kv.first), rem = kv.second;
+        while (rem >= per) { pages.push_back({(int)kv.first, per}); rem -= per; }
+        if (rem > 0) pages.push_back({(int)kv.first, rem});
+    }
+    std::vector<page> free_pages = pages;
+    // first page of every size, so that thousands of textures do not rescan the page list for each tile
+    std::map<int, size_t> first_of_size;
+    for (size_t sl = free_pages.size(); sl-- > 0;) first_of_size[free_pages[sl].size] = sl;
+    auto take = [&](int size) -> cl_uint {
+        auto it = first_of_size.find(size);
+        if (it != first_of_size.end())
+            for (size_t sl = it->second; sl < free_pages.size() && free_pages[sl].size == size; sl++)
+                if (free_pages[sl].n > 0) { free_pages[sl].n--; it->second = sl; return (cl_uint)((sl << 16) | (cl_uint)free_pages[sl].n); }
+        throw std::runtime_error("could not find a free texture page");
+    };
+    nums.clear(); sizes.clear();
+    for (int s : dims) nums.push_back(take(s));
+    for (int s : dims) for (int j = 0; j < MIPS; j++) nums.push_back(take(s / (1 << (j + 1))));
+    for (auto& p : pages) sizes.push_back((cl_uint)p.size);
+}
+
 // texture_context::alloc_gpu: page planner (texture_context.cpp:94-261) + uploads (texture.cpp:323-358, 465-493)
 inline texture_context_data texture_context::alloc_gpu(object_context& ctx, rr_ctx* dev) {
     std::set<texture_id_t> in_use;
@@ -330,32 +367,11 @@ inline texture_context_data texture_context::alloc_gpu(object_context& ctx, rr_c
     texture_id_orders.assign(in_use.begin(), in_use.end());
     mipmap_start = (cl_uint)in_use.size();
     for (auto id : in_use) id_to_tex(id)->load();
-    const int MIPS = 4, MAXSZ = 2048;
-    std::map<size_t, int> size_to_numbers;
-    for (auto id : in_use) {
-        int s = id_to_tex(id)->get_largest_dimension();
-        size_to_numbers[s]++;
-        for (int j = 0; j < MIPS; j++) size_to_numbers[s / (1 << (j + 1))]++;
-    }
-    struct page { int size, n; };
-    std::vector<page> pages;
-    for (auto& kv : size_to_numbers) {
-        if (kv.first == 0) throw std::runtime_error("texture too small for 4 mip levels");
-        int per = (MAXSZ / (int)kv.first) * (MAXSZ / (int)kv.first), rem = kv.second;
-        while (rem >= per) { pages.push_back({(int)kv.first, per}); rem -= per; }
-        if (rem > 0) pages.push_back({(int)kv.first, rem});
-    }
-    std::vector<page> free_pages = pages;
-    auto take = [&](int size) -> cl_uint {
-        for (size_t sl = 0; sl < free_pages.size(); sl++)
-            if (free_pages[sl].size == size && free_pages[sl].n > 0) { free_pages[sl].n--; return (cl_uint)((sl << 16) | (cl_uint)free_pages[sl].n); }
-        throw std::runtime_error("could not find a free texture page");
-    };
+    std::vector<int> dims;
+    for (auto id : in_use) dims.push_back(id_to_tex(id)->get_largest_dimension());
     std::vector<cl_uint> nums, sizes;
-    for (auto id : in_use) nums.push_back(take(id_to_tex(id)->get_largest_dimension()));
-    for (auto id : in_use) for (int j = 0; j < MIPS; j++) nums.push_back(take(id_to_tex(id)->get_largest_dimension() / (1 << (j + 1))));
-    for (auto& p : pages) sizes.push_back((cl_uint)p.size);
-    if (rr_atlas_alloc(dev, (uint32_t)pages.size(), nums.data(), (uint32_t)nums.size(), sizes.data(), (uint32_t)sizes.size(), mipmap_start)) rr_fatal("rr_atlas_alloc");
+    plan_texture_pages(dims, nums, sizes);
+    if (rr_atlas_alloc(dev, (uint32_t)sizes.size(), nums.data(), (uint32_t)nums.size(), sizes.data(), (uint32_t)sizes.size(), mipmap_start)) rr_fatal("rr_atlas_alloc");
     int c = 0;
     for (auto id : texture_id_orders) {
         texture* t = id_to_tex(id);

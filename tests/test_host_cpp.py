@@ -48,6 +48,36 @@ def test_host_layer_compiles_and_links(tmp_path):
     assert r.returncode == 2 and "usage" in r.stderr
 
 
+@pytest.mark.parametrize("n_tex,seed", [(1, 0), (9, 1), (300, 2), (4000, 3)])
+def test_page_planner_cpp_equals_python_mirror(tmp_path, n_tex, seed):
+    """texture_context::alloc_gpu's page planner (texture_context.cpp:94-261) exists twice, in the C++ host layer and in the
+    Python harness: both must produce the same nums[] / sizes[] for anything from one texture to thousands (SURVEY.md §8f
+    rank 3: atlas build at scale). 4000 textures of 16..2048 px fill dozens of 2048^2 slices."""
+    from openclrenderer_b200 import _build, scene
+    lib = _build.build_product()
+    libdir, cuda_lib = os.path.dirname(lib), "/usr/local/cuda/lib64"
+    exe = str(tmp_path / "plan_pages")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "examples", "plan_pages.cpp"), "-L" + libdir, "-lrr_b200",
+                    "-L" + cuda_lib, "-lcudart", "-lz", "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda_lib], check=True)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    dims = [int(2 ** rng.integers(4, 12)) for _ in range(n_tex)]           # 16 .. 2048, all have four mip levels >= 1
+    if n_tex >= 9:
+        dims[3] = 48                                                       # a non-power-of-two size: 48, 24, 12, 6, 3
+    r = subprocess.run([exe], input=" ".join(map(str, dims)), capture_output=True, text=True, check=True)
+    out = r.stdout.split("\n")
+    n_slices, n_nums = (int(x) for x in out[0].split())
+    nums = np.array(out[1].split(), dtype=np.uint64).astype(np.uint32)
+    sizes = np.array(out[2].split(), dtype=np.uint64).astype(np.uint32)
+    p_slices, p_nums, p_sizes, p_start = scene.plan_atlas(dims)
+    assert n_slices == p_slices and n_nums == len(p_nums) == 5 * n_tex and p_start == n_tex
+    assert np.array_equal(nums, p_nums) and np.array_equal(sizes, p_sizes)
+    # every (slice, index) is used once and fits its page
+    assert len(set(nums.tolist())) == len(nums)
+    for v in nums[:: max(1, len(nums) // 500)]:
+        sl, idx = int(v) >> 16, int(v) & 0xFFFF
+        assert idx < (2048 // int(sizes[sl])) ** 2
+
+
 def test_png_loader_roundtrip(tmp_path):
     """the host layer's zlib PNG decoder against Pillow on the reference's own texture"""
     write_obj_assets(str(tmp_path))
