@@ -21,7 +21,7 @@ enum {
     CTR_NSHADE = 10,   // covered pixels in the shading list
     CTR_NSAMPLES = 11, // entries reserved in the sample list (inline-rasterised triangles)
     CTR_NDESC = 12,    // descriptors in the sample list
-    CTR_NACTIVE = 13,  // k_block_compact: setup blocks with at least one cluster that is not culled
+    CTR_NACTIVE = 13,  // k_frame_prologue: setup blocks with at least one cluster that is not culled
     CTR_CUT_SKIPPED = 14,  // ... and the projected-triangle slots of the blocks that were skipped
     CTR_PROLOGUE_TICKET = 15,  // last-CTA detection of k_frame_prologue (self-resetting)
     CTR_COUNT = 16
@@ -564,7 +564,7 @@ struct SetupMainParams {
     const int2* obj_rows;                    // band mode: per-object row range (k_obj_rows); nullptr = no object culling
     const uint8_t* rowmask;                  // interleaved bands: per-row ownership bits (ROW_NEEDED | ROW_OWNED); nullptr = contiguous
     const uint8_t* cluster_vis;              // k_cluster_vis: 0 = the cluster's triangles take their slots but produce nothing here
-    const uint32_t* active; const uint32_t* skipped_before;   // k_block_compact (valid when cluster_vis != nullptr)
+    const uint32_t* active; const uint32_t* skipped_before;   // k_frame_prologue (valid when cluster_vis != nullptr)
     const int* rowpfx; int cull_rows;        // sort-first split: per-triangle row culling (prefix count of rasterised rows; nullptr = [row_lo, row_hi))
 };
 
