@@ -878,7 +878,7 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     const size_t slab = (size_t)6 * c->L * c->L;
     int mgb = 0;
     uint32_t mg_epoch = 0;
-    if (c->mg.connected) {
+    if (c->mg.connected && c->n_shadow) {    // (no shadow-casting light: nothing to exchange, no epoch)
         // peer-memory exchange: this epoch's cubemaps live in buffer (epoch & 1). Peers may only be written once they are
         // done with the frame that last read that buffer, which their flag for the previous epoch implies.
         mg_epoch = ++c->mg.shadow_epoch;
@@ -888,13 +888,13 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     }
     if (!c->lights.empty()) {                                                              // engine.cpp:1611-1626
         // a full clear (not only the owned faces) keeps the buffer defined for the all-gather that follows
-        if (c->mg.connected) { if (c->n_shadow && (r = mg_fill_owned(c, c->stream2, c->d_shadow_dyn))) return r; }
+        if (c->mg.connected) { if (c->n_shadow && mg_epoch && (r = mg_fill_owned(c, c->stream2, c->d_shadow_dyn))) return r; }
         else if (c->n_shadow && (r = fill_u32(c, c->stream2, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
         if (static_lights_dirty && c->n_static && (r = fill_u32(c, c->stream2, c->d_shadow_static, slab * c->n_static, 0xFFFFFFFFu))) return r;
     }
     if (c->n_shadow && (r = shadow_pass(c, 0))) return r;                                  // engine.cpp:1629-1697
     if (static_lights_dirty && c->n_static && (r = shadow_pass(c, 1))) return r;           // engine.cpp:1699-1784
-    if (c->mg.connected && c->n_shadow && (r = mg_push(c, c->stream2, mgb, mg_epoch))) return r;
+    if (c->mg.connected && c->n_shadow && mg_epoch && (r = mg_push(c, c->stream2, mgb, mg_epoch))) return r;
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SH1], c->stream2));
     CU(cudaEventRecord(c->ev_shadow_done, c->stream2));
     c->have_shadow_ev = c->stage_events;
@@ -1324,12 +1324,11 @@ int rr_mgpu_disconnect(rr_ctx* c) {
     if (c->mg.connected) {
         c->d_shadow_dyn = c->mg.saved_shadow_dyn; c->ext_shadow_dyn = c->mg.saved_ext_shadow; c->shadow_dyn_words = c->mg.saved_shadow_words;
         c->d_rgba8 = c->mg.saved_rgba8; c->ext_rgba8 = c->mg.saved_ext_rgba8;
-        if (c->mg.ipc)
-            for (int q = 0; q < MG_MAX_WORLD; q++)
-                for (int i = 0; i < 3; i++) if (c->mg.opened[q][i]) { cudaIpcCloseMemHandle(c->mg.opened[q][i]); c->mg.opened[q][i] = nullptr; }
         for (int b = 0; b < 2; b++) { cudaFree(c->mg.prev_dirty[b]); c->mg.prev_dirty[b] = nullptr; }
         c->mg.connected = false;
     }
+    for (int q = 0; q < MG_MAX_WORLD; q++)               // also after a connect that failed half-way
+        for (int i = 0; i < 3; i++) if (c->mg.opened[q][i]) { cudaIpcCloseMemHandle(c->mg.opened[q][i]); c->mg.opened[q][i] = nullptr; }
     if (c->mg.exported) {
         cudaFree(c->mg.shadow[0]); cudaFree(c->mg.fb[0]); cudaFree(c->mg.ctrl);
         c->mg.shadow[0] = c->mg.shadow[1] = nullptr; for (int i = 0; i < RR_RING_MAX; i++) c->mg.fb[i] = nullptr;
