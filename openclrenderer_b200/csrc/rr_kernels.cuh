@@ -1050,7 +1050,20 @@ __device__ __forceinline__ void warp_alloc2(uint32_t* counters, uint32_t nc, uin
     fbase = (uint32_t)(base & 0xFFFFFFFFull);
 }
 
-__global__ void __launch_bounds__(128) k_shadow_setup(const ShadowSetupParams P) {
+// Minimum resident CTAs per SM the register allocation is asked to allow. k_shadow_setup is latency-bound at 96 registers
+// (5 CTAs, 25 % of the warps resident): capped at 64 registers (8 CTAs) it spills 208 bytes per thread to L1 and the frame
+// gets 4.9 % faster (A/B on one box, ms/frame on c3: default 0.596, 6 CTAs 0.583, 8 CTAs 0.567; k_shade at 8 CTAs alone
+// 0.592 and not adopted). Build-time knobs for further A/B runs: -DRR_LB_SHADOW_SETUP=n, -DRR_LB_SHADE=n, RR_LIB=<other build>.
+#ifndef RR_LB_SHADOW_SETUP
+#define RR_LB_SHADOW_SETUP 8
+#endif
+#define RR_LB_SHADOW_SETUP_ATTR __launch_bounds__(128, RR_LB_SHADOW_SETUP)
+#ifdef RR_LB_SHADE
+#define RR_LB_SHADE_ATTR __launch_bounds__(128, RR_LB_SHADE)
+#else
+#define RR_LB_SHADE_ATTR __launch_bounds__(128)
+#endif
+__global__ void RR_LB_SHADOW_SETUP_ATTR k_shadow_setup(const ShadowSetupParams P) {
     __shared__ InlineQueue s_iq[128 / 32];
     static_assert(CLUSTER_TRIS == 128, "one k_shadow_setup block == one cluster");
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1824,7 +1837,7 @@ __global__ void __launch_bounds__(256) k_shade_pre4(const ShadeParams P) {
 
 // k_shade: the expensive part of kernel3 (~6000 instructions per covered pixel) over the compacted list — every warp
 // is dense whatever the screen coverage looks like. Persistent grid, stride over the list.
-__global__ void __launch_bounds__(128) k_shade(const ShadeParams P) {
+__global__ void RR_LB_SHADE_ATTR k_shade(const ShadeParams P) {
     const uint32_t n = *P.shade_count;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t px = __ldg(P.shade_list + i);

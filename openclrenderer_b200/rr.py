@@ -11,7 +11,8 @@ _LIB = None
 
 
 def library_path():
-    return os.path.join(_HERE, "librr_b200.so")
+    # RR_LIB: an alternative build of the same library (A/B runs of build-time knobs); the default is the in-tree product
+    return os.environ.get("RR_LIB") or os.path.join(_HERE, "librr_b200.so")
 
 
 def load_library():
