@@ -214,6 +214,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: some boxes print NCCL's version banner there unless the level is set explicitly
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     s = make_scene(args.workload)
     W, H, L = s.cfg.width, s.cfg.height, s.cfg.light_dim
