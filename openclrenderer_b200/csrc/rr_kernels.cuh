@@ -569,8 +569,11 @@ struct SetupMainParams {
 };
 
 // BANDED: sort-first split (row masks, per-triangle row culling); false compiles those paths out for the whole-frame case
+#ifndef RR_LB_SETUP_MAIN
+#define RR_LB_SETUP_MAIN 4               // 64 registers (see examples/lb_sweep.sh for the A/B harness of these knobs)
+#endif
 template <bool BANDED>
-__global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup_main(const SetupMainParams P) {
+__global__ void __launch_bounds__(SETUP_THREADS, RR_LB_SETUP_MAIN) k_setup_main(const SetupMainParams P) {
     __shared__ uint32_t s_bid;
     __shared__ uint32_t s_warp_c[SETUP_THREADS / 32], s_warp_f[SETUP_THREADS / 32];
     __shared__ uint32_t s_base_c, s_base_f, s_tot_f;
