@@ -6,8 +6,10 @@ config 3 (synthetic 1 M-triangle sphere field, texture atlas with mips, 4 shadow
   python bench.py --impl reference [...]                         the reference algorithm on the host cores (CPU oracle)
 
 A step = one whole frame: 4 shadow-cubemap passes (24 faces) + prearrange + depth + id resolve + deferred shading.
-N > 1: the same frame split sort-first into N screen bands, the 24 cubemap faces sharded over the ranks and
-all-gathered, the bands gathered to rank 0 over NCCL ("scaling": "strong").
+N > 1: the same frame split sort-first over N contexts (interleaved row tiles), the 24 cubemap faces sharded round-robin;
+faces are pushed and rows composited by the kernels themselves over peer memory (NVLink), `--exchange nccl` keeps the
+collective baseline ("scaling": "strong"). Every line carries `stages_ms` (max over ranks) and `roofline`; N > 1 lines also
+carry `verify` (composite == the frame one GPU renders alone, checked outside the timed region).
 """
 import argparse
 import json
@@ -46,7 +48,8 @@ def parse():
                     help="N>1 p2p end-to-end leg: distributed = every GPU DMAs the rows it shaded into one shared host frame over its own PCIe "
                          "link; rank0 = rows composited on GPU 0 over NVLink, GPU 0 reads the whole frame back")
     ap.add_argument("--depth", type=int, default=3, help="colour-target ring of the end-to-end leg (rr_set_pipeline_depth): frames in flight + 1")
-    ap.add_argument("--verify", action="store_true", help="N>1: rank 0 also renders the frame alone and checks the composite bit for bit")
+    ap.add_argument("--verify", action="store_true", help="(kept for compatibility) N>1 lines always carry `verify`: rank 0 also renders the frame "
+                                                          "alone, outside the timed region, and counts the pixels in which the composite differs")
     return ap.parse_args()
 
 
@@ -79,9 +82,18 @@ def camera(s, i):
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU legs (the only places bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_frame_loop(s, steps, warmup, threads=0):
+def host_cores():
+    """cores this process may run on. torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would make
+    omp_get_max_threads() 1: the CPU legs pass the count explicitly (the oracle's pragmas carry num_threads)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_frame_loop(s, steps, warmup, threads=None):
     from oracle.binding import Oracle
-    o = Oracle(s.cfg, threads=threads)
+    o = Oracle(s.cfg, threads=threads or host_cores())
     s.upload(o)
     times = []
     for i in range(warmup + steps):
@@ -430,88 +442,27 @@ def run_ours(args):
                                                                 "band_halo": args.halo if world > 1 else None}),
                 "fps": round(1e3 / ms, 2), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
 
-    # ---- stage profile + roofline + CPU baseline (rank 0, N = 1 only)
-    if world == 1:
-        stage = {k: 0.0 for k in ("shadow_depth_ms", "setup_ms", "depth_ms", "id_ms", "shade_ms", "frame_ms")}
-        n_prof = 8
-        tm = None
-        r.set_profiling(True)                  # per-stage events only for these frames: they are not free (rr.h rr_set_profiling)
-        for i in range(n_prof):
-            frame(1000 + i)
-            tm = r.timings()
-            for k in stage:
-                stage[k] += tm[k] / n_prof
-        r.set_profiling(False)
-        # the frame just drawn is in the previous buffer after swap: swap back to read it
-        r.swap_buffers()
-        ids, depth, frags = r.read_ids(), r.read_depth(), r.read_fragments()
-        r.swap_buffers()
-        cov = depth != 0xFFFFFFFF
-        P = W * H
-        V = int(len(np.unique(frags[ids[cov], 0]))) if cov.any() else 0
-        C, F = tm["n_cutdown"], tm["n_fragments"]
-        S = n_shadow
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        atom_ms = r.microbench_atomic_min(32 << 20, 1 << 30)
-        r_atomic = (1 << 30) / (atom_ms * 1e-3)
-        copy_ms = r.microbench_copy(1 << 30)
-        # algorithmic bytes per stage
-        B = {"setup": 40 * T + 48 * C + 20 * F,
-             "shadow": S * (40 * T + 2 * 4 * 6 * L * L),
-             "depth": 4 * P,
-             "id": 8 * P,
-             "shade": 8 * P + 144 * V + 144 * len(s.objs) + 5 * P + 4 * P + 4 * P + 4 * P}
-        B_lookup = S * min(P, 6 * L * L) * 4
-        ms_of = {"setup": stage["setup_ms"], "shadow": stage["shadow_depth_ms"], "depth": stage["depth_ms"], "id": stage["id_ms"], "shade": stage["shade_ms"]}
-        dom = max(ms_of, key=lambda k: ms_of[k])
-        achieved = B[dom] / (ms_of[dom] * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": {"setup": "k_setup_main (+ inline depth of small triangles)",
-                                                        "shadow": "k_fill_u32 + k_shadow_setup (all %d lights, inline raster) + k_scan_big + k_raster_*<shadow>" % S,
-                                                        "depth": "k_scan_big + k_raster_small<depth> + k_raster_big<depth>",
-                                                        "id": "k_raster_small<ids> + k_raster_big<ids>", "shade": "k_shade_pre + k_shade"}[dom],
-                            "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4), "traffic": None,
-                            "peak_source": peak_src, "algorithmic_bytes_per_launch": int(B[dom]), "avg_ms": round(ms_of[dom], 4)}
-        try:                                   # DRAM bytes of the stage's dominant kernel from the committed ncu capture (per launch)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            kname = {"setup": "k_setup_main", "shadow": "k_shadow_setup", "shade": "k_shade"}.get(dom)
-            if kname in tr:
-                line["roofline"]["traffic"] = int(tr[kname])
-                line["roofline"]["traffic_kernel"] = kname
-                line["roofline"]["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of that kernel)"
-        except Exception:
-            pass
-        line["roofline"]["note"] = ("stages are issue-bound, not HBM-bound (ncu: DRAM 3-6 %, issue-active ~50 %): the pinned IEEE arithmetic of the "
-                                    "reference's per-pixel/per-triangle math dominates; shadow stage runs concurrently with setup/depth/id on a second stream, "
-                                    "so stage times overlap and do not add up to ms_per_step")
-        line["stages_ms"] = {k: round(v, 4) for k, v in stage.items()}
-        line["counts"] = {"cutdown": int(C), "fragments": int(F), "visible_tris": V, "covered_px": int(cov.sum()), "shadow_fragments": int(tm["n_shadow_fragments"])}
-        line["microbench"] = {"atomic_min_Gops": round(r_atomic / 1e9, 2), "copy_GBs": round(2 * (1 << 30) / (copy_ms * 1e-3) / 1e9, 1)}
-        if not args.no_cpu_baseline:
-            n_cpu = 5
-            times, st = cpu_frame_loop(s, n_cpu, 1)
-            cms = 1e3 * sum(times) / len(times)
-            line["cpu_baseline"] = {"value": round(T / (cms * 1e-3) / 1e6, 4), "unit": UNIT, "cores": st["threads"], "kind": "port",
-                                    "sample": f"{n_cpu} full frames of {s.name} after 1 warm-up ({cms:.0f} ms/frame), OpenMP over reference work-groups",
-                                    "ms_per_step": round(cms, 2)}
-            A_depth, A_shadow = st["depth_samples"], st["shadow_samples"]
-            B_frame = B["setup"] + B["depth"] + B["id"] + B["shade"] + B["shadow"] + B_lookup
-            t_roof_ms = 1e3 * (B_frame / (hbm * 1e9) + (A_depth + A_shadow) / r_atomic)
-            line["roofline_frame"] = {"B_frame_bytes": int(B_frame), "atomics": int(A_depth + A_shadow), "t_roof_ms": round(t_roof_ms, 4),
-                                      "frac": round(t_roof_ms / ms, 4), "formula": "B_frame/BW_hbm + (A_depth+A_shadow)/R_atomic (SURVEY.md §8d)"}
-            line["Mfrag_per_s"] = round((A_depth + A_shadow) / (ms * 1e-3) / 1e6, 1)
-    if world == 1 and not args.no_opencl_reference:
-        try:
-            line["reference_opencl_b200"] = opencl_reference(s, min(args.steps, 20))
-        except Exception as e:                         # informative only; never fails the bench
-            line["reference_opencl_b200"] = {"unavailable": str(e)[:200]}
-    if world > 1 and args.verify:
-        # the composite on rank 0 must equal the frame one context renders alone, bit for bit
+    # ---- stage profile (every N: max over ranks), verification of the split frame (N > 1, always), roofline, CPU baseline (N = 1)
+    stage_keys = ("shadow_depth_ms", "setup_ms", "depth_ms", "id_ms", "shade_ms", "frame_ms")
+    stage = {k: 0.0 for k in stage_keys}
+    n_prof = 8
+    tm = None
+    r.set_profiling(True)                  # per-stage events only for these frames: they are not free (rr.h rr_set_profiling)
+    for i in range(n_prof):
+        frame(1000 + i)
+        tm = r.timings()
+        for k in stage:
+            stage[k] += tm[k] / n_prof
+    r.set_profiling(False)
+    barrier()
+    if world > 1:
+        tst = torch.tensor([stage[k] for k in stage_keys], dtype=torch.float64, device=dev)
+        dist.all_reduce(tst, op=dist.ReduceOp.MAX)
+        stage = {k: float(tst[i]) for i, k in enumerate(stage_keys)}
+
+    solo = None
+    if world > 1:
+        # the composite on rank 0 must equal the frame one context renders alone, bit for bit (outside the timed region)
         c_pos, c_rot = camera(s, 12345)
         r.frame_shadows(0)
         if p2p:
@@ -533,13 +484,94 @@ def run_ours(args):
             solo.sync()
             want = solo.read_rgba8()
             bad = int((got != want).any(axis=-1).sum())
-            line["verify"] = {"pixels_differing_from_single_gpu_frame": bad, "pixels": int(W * H)}
-            solo.close()
+            line["verify"] = {"pixels_differing_from_single_gpu_frame": bad, "pixels": int(W * H),
+                              "what": "composite of the N contexts vs the same frame rendered by one context on GPU 0, all four channels"}
         r.swap_buffers()
         barrier()
+
+    if rank == 0:
+        # counts of the whole frame: from this context at N = 1, from the solo context that verified the composite at N > 1
+        q = r if world == 1 else solo
+        if world == 1:
+            r.swap_buffers()               # the frame just drawn is in the previous buffer after swap: swap back to read it
+        ids, depth, frags = q.read_ids(), q.read_depth(), q.read_fragments()
+        qt = q.timings()
+        if world == 1:
+            r.swap_buffers()
+        cov = depth != 0xFFFFFFFF
+        P = W * H
+        V = int(len(np.unique(frags[ids[cov], 0]))) if cov.any() else 0
+        C, F = qt["n_cutdown"], qt["n_fragments"]
+        S = n_shadow
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        atom_ms = q.microbench_atomic_min(32 << 20, 1 << 30)
+        r_atomic = (1 << 30) / (atom_ms * 1e-3)
+        copy_ms = q.microbench_copy(1 << 30)
+        if solo is not None:
+            solo.close()
+        # algorithmic bytes per stage of the WHOLE frame
+        B = {"setup": 40 * T + 48 * C + 20 * F,
+             "shadow": S * (40 * T + 2 * 4 * 6 * L * L),
+             "depth": 4 * P,
+             "id": 8 * P,
+             "shade": 8 * P + 144 * V + 144 * len(s.objs) + 5 * P + 4 * P + 4 * P + 4 * P}
+        B_lookup = S * min(P, 6 * L * L) * 4
+        ms_of = {"setup": stage["setup_ms"], "shadow": stage["shadow_depth_ms"], "depth": stage["depth_ms"], "id": stage["id_ms"], "shade": stage["shade_ms"]}
+        dom = max(ms_of, key=lambda k: ms_of[k])
+        achieved = B[dom] / (ms_of[dom] * 1e-3) / 1e9
+        peak = hbm * world                     # N contexts: the frame's bytes over the max-over-ranks stage time against N x the measured copy bandwidth
+        line["roofline"] = {"bound": "hbm", "limiter": "instruction issue (ncu: DRAM 3-6 % of peak, issue slots 50-60 % busy; profiles/r2*_ncu_*.txt)",
+                            "kernel": {"setup": "k_setup_main (+ inline depth of small triangles)",
+                                       "shadow": "k_shadow_setup (all %d lights, inline raster) + k_raster_shadow_warp" % S,
+                                       "depth": "k_scan_big + k_raster_small<depth> + k_raster_big<depth>",
+                                       "id": "k_ids_list + k_raster_small<ids> + k_raster_big<ids>", "shade": "k_shade_pre + k_shade"}[dom],
+                            "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                            "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""), "algorithmic_bytes_per_launch": int(B[dom]), "avg_ms": round(ms_of[dom], 4)}
+        if world == 1:
+            try:                               # DRAM bytes of the stage's dominant kernel from the committed ncu capture (per launch)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                kname = {"setup": "k_setup_main", "shadow": "k_shadow_setup", "shade": "k_shade"}.get(dom)
+                if kname in tr:
+                    line["roofline"]["traffic"] = int(tr[kname])
+                    line["roofline"]["traffic_kernel"] = kname
+                    line["roofline"]["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of that kernel)"
+            except Exception:
+                pass
+        line["roofline"]["note"] = ("the HBM roofline is the hardware bound of this byte/integer path, but the stages are currently limited by instruction issue, "
+                                    "not by memory: the pinned IEEE arithmetic of the reference's per-pixel / per-triangle math dominates. The shadow stage runs "
+                                    "concurrently with setup/depth/id on a second stream, so stage times overlap and do not add up to ms_per_step"
+                                    + ("; stage times are the max over ranks" if world > 1 else ""))
+        line["stages_ms"] = {k: round(v, 4) for k, v in stage.items()}
+        line["counts"] = {"cutdown": int(C), "fragments": int(F), "visible_tris": V, "covered_px": int(cov.sum()), "shadow_fragments": int(tm["n_shadow_fragments"])}
+        line["microbench"] = {"atomic_min_Gops": round(r_atomic / 1e9, 2), "copy_GBs": round(2 * (1 << 30) / (copy_ms * 1e-3) / 1e9, 1)}
+        if world == 1 and not args.no_cpu_baseline:
+            n_cpu = 5
+            times, st = cpu_frame_loop(s, n_cpu, 1)
+            cms = 1e3 * sum(times) / len(times)
+            line["cpu_baseline"] = {"value": round(T / (cms * 1e-3) / 1e6, 4), "unit": UNIT, "cores": st["threads"], "kind": "port",
+                                    "sample": f"{n_cpu} full frames of {s.name} after 1 warm-up ({cms:.0f} ms/frame), OpenMP over reference work-groups",
+                                    "ms_per_step": round(cms, 2)}
+            A_depth, A_shadow = st["depth_samples"], st["shadow_samples"]
+            B_frame = B["setup"] + B["depth"] + B["id"] + B["shade"] + B["shadow"] + B_lookup
+            t_roof_ms = 1e3 * (B_frame / (hbm * 1e9) + (A_depth + A_shadow) / r_atomic)
+            line["roofline_frame"] = {"B_frame_bytes": int(B_frame), "atomics": int(A_depth + A_shadow), "t_roof_ms": round(t_roof_ms, 4),
+                                      "frac": round(t_roof_ms / ms, 4), "formula": "B_frame/BW_hbm + (A_depth+A_shadow)/R_atomic (SURVEY.md §8d)"}
+            line["Mfrag_per_s"] = round((A_depth + A_shadow) / (ms * 1e-3) / 1e6, 1)
+    if world == 1 and not args.no_opencl_reference:
+        try:
+            line["reference_opencl_b200"] = opencl_reference(s, min(args.steps, 20))
+        except Exception as e:                         # informative only; never fails the bench
+            line["reference_opencl_b200"] = {"unavailable": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        barrier()
         dist.destroy_process_group()
 
 

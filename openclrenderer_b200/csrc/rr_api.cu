@@ -151,8 +151,13 @@ struct rr_ctx {
     uint32_t *d_sfrags = nullptr, *d_sfragcnt = nullptr, *d_sbiglist = nullptr, *d_sbigslot = nullptr, *d_scounters = nullptr;
     float4* d_scutdown = nullptr;
     unsigned long long* d_sscan_lookback = nullptr;
-    // e2e staging (pinned)
+    // host mirror of the descriptor array (what rr_frame_e2e uploads every frame, object_context::flush_locations)
     rr_obj_desc* h_objs_pinned = nullptr;
+    // Page-locked staging for every asynchronous host-to-device upload on the main stream (patches, descriptor writes, the
+    // per-frame descriptor upload of rr_frame_e2e): two halves used alternately; a half is reused only after the event recorded
+    // behind its last copy has completed, so the host never overwrites bytes a pending DMA still has to read.
+    struct Arena { char* base = nullptr; size_t half = 0, used = 0; int cur = 0; cudaEvent_t ev[2] = {nullptr, nullptr}; bool pending[2] = {false, false}; } arena;
+    uint32_t last_overflow = 0;                  // what the last rr_sync saw (rr_get_timings reports it)
     // sort-first rows (rr_config.band_*): bounding ranges, and per-row tables in interleaved mode
     int own_lo = 0, own_hi = 0, need_lo = 0, need_hi = 0;
     bool banded = false;
@@ -208,6 +213,41 @@ int dev_alloc(T*& p, size_t count) {
 }
 
 inline int grid_for(const rr_ctx* c, int per_sm) { return c->sm_count * per_sm; }
+
+// n bytes of page-locked staging that stay untouched until the copies enqueued on `st` so far plus the one the caller is about
+// to enqueue have executed. May block the host when both halves are still in flight (two arena halves of uploads ahead of the GPU).
+int arena_take(rr_ctx* c, size_t n, cudaStream_t st, void** out) {
+    rr_ctx::Arena& a = c->arena;
+    n = (n + 15) & ~(size_t)15;
+    if (!a.base || n > a.half) {                                  // first use, or an upload larger than a half: (re)allocate
+        if (a.base) { CU(cudaStreamSynchronize(st)); cudaFreeHost(a.base); a.base = nullptr; }
+        a.half = std::max<size_t>(n * 2, (size_t)1 << 20);
+        CU(cudaMallocHost((void**)&a.base, a.half * 2));
+        for (int i = 0; i < 2; i++) { if (!a.ev[i]) CU(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming)); a.pending[i] = false; }
+        a.used = 0; a.cur = 0;
+    }
+    if (a.used + n > a.half) {                                    // this half is full: everything staged in it is in the stream already
+        CU(cudaEventRecord(a.ev[a.cur], st));
+        a.pending[a.cur] = true;
+        a.cur ^= 1;
+        if (a.pending[a.cur]) { CU(cudaEventSynchronize(a.ev[a.cur])); a.pending[a.cur] = false; }
+        a.used = 0;
+    }
+    *out = a.base + (size_t)a.cur * a.half + a.used;
+    a.used += n;
+    return RR_OK;
+}
+
+// host bytes -> device, asynchronously on the main stream, through the staging arena (the caller may reuse `src` on return)
+int upload_staged(rr_ctx* c, void* dst_dev, const void* src, size_t n) {
+    if (!n) return RR_OK;
+    void* h = nullptr;
+    int r = arena_take(c, n, c->stream, &h);
+    if (r) return r;
+    memcpy(h, src, n);
+    CU(cudaMemcpyAsync(dst_dev, h, n, cudaMemcpyHostToDevice, c->stream));
+    return RR_OK;
+}
 
 int fill_u32(rr_ctx* c, cudaStream_t st, uint32_t* p, size_t n, uint32_t v) {
     if (n == 0) return RR_OK;
@@ -498,6 +538,8 @@ void rr_destroy(rr_ctx* c) {
     cudaFree(c->d_normals); cudaFree(c->d_shade_list); cudaFree(c->d_samples); cudaFree(c->d_sample_desc); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
+    if (c->arena.base) cudaFreeHost(c->arena.base);
+    for (int i = 0; i < 2; i++) if (c->arena.ev[i]) cudaEventDestroy(c->arena.ev[i]);
     for (int i = 0; i < EV_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -561,8 +603,9 @@ int rr_scene_write_objs(rr_ctx* c, uint32_t first, uint32_t count, const rr_obj_
     if (!c || !objs) return fail(RR_ERR_INVALID, "null argument");
     if ((uint64_t)first + count > c->n_objs) return fail(RR_ERR_INVALID, "rr_scene_write_objs: range outside %u", c->n_objs);
     if (count == 0) return RR_OK;
-    memcpy(c->h_objs_pinned + first, objs, (size_t)count * sizeof(rr_obj_desc));
-    CU(cudaMemcpyAsync(c->d_objs + first, c->h_objs_pinned + first, (size_t)count * sizeof(rr_obj_desc), cudaMemcpyHostToDevice, c->stream));
+    memcpy(c->h_objs_pinned + first, objs, (size_t)count * sizeof(rr_obj_desc));          // host mirror (rr_frame_e2e uploads it every frame)
+    int r = upload_staged(c, c->d_objs + first, objs, (size_t)count * sizeof(rr_obj_desc));
+    if (r) return r;
     c->objlite_dirty = true;
     return RR_OK;
 }
@@ -571,7 +614,8 @@ int rr_scene_patch_obj(rr_ctx* c, uint32_t obj_id, uint32_t byte_off, uint32_t n
     if (!c || !src) return fail(RR_ERR_INVALID, "null argument");
     if (obj_id >= c->n_objs || (uint64_t)byte_off + nbytes > sizeof(rr_obj_desc)) return fail(RR_ERR_INVALID, "rr_scene_patch_obj: out of range");
     memcpy((char*)(c->h_objs_pinned + obj_id) + byte_off, src, nbytes);
-    CU(cudaMemcpyAsync((char*)(c->d_objs + obj_id) + byte_off, (char*)(c->h_objs_pinned + obj_id) + byte_off, nbytes, cudaMemcpyHostToDevice, c->stream));
+    int r = upload_staged(c, (char*)(c->d_objs + obj_id) + byte_off, src, nbytes);
+    if (r) return r;
     c->objlite_dirty = true;
     return RR_OK;
 }
@@ -624,7 +668,7 @@ int rr_scene_build_begin(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
     int r;
     const uint32_t n_clusters = (n_tris + CLUSTER_TRIS - 1) / CLUSTER_TRIS, blocks = (n_tris + SETUP_THREADS - 1) / SETUP_THREADS;
     const uint32_t cap_cut = c->cfg.max_cutdown ? c->cfg.max_cutdown : (uint32_t)std::min<uint64_t>((uint64_t)n_tris * 6 + 1024, 0x7FFFFFFFu);
-    if (n_tris > b.tri_cap || cap_cut > b.cap_cut) {                 // grow (cudaFree of the old buffers synchronises the device once)
+    if (n_tris > b.tri_cap || cap_cut > b.cap_cut || !b.d_tris) {    // grow (or first use: an empty scene still gets one element each) (cudaFree of the old buffers synchronises the device once)
         if (c->retire_pending) { CU(cudaEventSynchronize(c->ev_retire)); }
         if ((r = back_alloc(b.d_tris, n_tris))) return r;
         if ((r = back_alloc(b.d_pa, n_tris))) return r;
@@ -640,7 +684,7 @@ int rr_scene_build_begin(rr_ctx* c, uint32_t n_tris, uint32_t n_objs) {
         if ((r = back_alloc(b.d_skipped, (size_t)blocks))) return r;
         b.tri_cap = n_tris;
     }
-    if (n_objs > b.obj_cap) {
+    if (n_objs > b.obj_cap || !b.d_objs) {
         if (c->retire_pending) { CU(cudaEventSynchronize(c->ev_retire)); }
         if ((r = back_alloc(b.d_objs, n_objs))) return r;
         if ((r = back_alloc(b.d_objlite, n_objs))) return r;
@@ -922,6 +966,18 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     int band0, band1, row0, row1;
     band_rows(c, band0, band1, row0, row1);
 
+    const bool mg_composite = c->mg.connected && !c->mg.local_readback;      // rows of all contexts meet in rank 0's colour target
+    if (c->mg.connected) ++c->mg.draw_epoch;
+    if (mg_composite && c->mg.rank == 0 && c->mg.world > 1) {
+        // Rank 0 owns the composite target. Everything that still reads the target this frame goes to (a synchronous read-back
+        // of the previous frame, or — rr_frame_e2e — the copy of the frame that used this ring slot D frames ago, which the main
+        // stream has just waited for) is ordered before this point of rank 0's stream: tell the peers they may store into it.
+        MgFlagList fl;
+        fl.n = 0; fl.value = c->mg.draw_epoch;
+        for (int q = 1; q < c->mg.world; q++) fl.flag[fl.n++] = &c->mg.peer_ctrl[q]->fb_free;
+        k_signal_flags<<<1, 32, 0, c->stream>>>(fl);
+        c->launches++;
+    }
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_F0], c->stream));
     // prearrange
     SetupMainParams sp;
@@ -961,6 +1017,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     sp.sl.desc = c->d_sample_desc; sp.sl.cap_desc = c->cap_frags; sp.sl.desc_count = c->d_counters + CTR_NDESC; sp.sl.fragcnt = c->d_fragcnt;
     if (c->banded) k_setup_main<true><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     else k_setup_main<false><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
+    c->launches++;
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
     // kernel1 / kernel2
     if ((r = scan_big(c, c->stream, c->d_counters, c->d_fragcnt, c->d_biglist, c->d_bigslot, c->d_scan_lookback, CTR_NFRAG, c->cap_frags, scan_zeroed))) return r;
@@ -983,7 +1040,6 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     hp.tris = c->d_tris; hp.objs = c->d_objs; hp.objlite = c->d_objlite; hp.lightlite = c->d_lightlite; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
     hp.depth = c->d_depth[c->cur]; hp.ids = c->d_ids[c->cur];
     hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
-    const bool mg_composite = c->mg.connected && !c->mg.local_readback;      // rows of all contexts meet in rank 0's colour target
     if (c->mg.connected) c->d_rgba8 = (c->mg.rank == 0 || c->mg.local_readback) ? c->mg.fb[c->mg_target] : c->mg.fb0[c->mg_target];
     hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
     hp.atlas.texels = c->d_atlas; hp.atlas.nums = c->d_nums; hp.atlas.sizes = c->d_sizes; hp.atlas.mip_start = c->mipmap_start;
@@ -998,26 +1054,35 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     hp.linear = (c->cfg.test_linear && c->cfg.use_linear_rendering) ? 1 : 0;
     hp.no_ssao = c->cfg.no_ssao;
     hp.row0 = row0; hp.row1 = row1; hp.band_y0 = band0; hp.band_y1 = band1; hp.rowmask = c->d_rowmask;
-    if (c->mg.connected) ++c->mg.draw_epoch;
     if (hp.n_lights > 0 && (!c->d_lights)) return fail(RR_ERR_INVALID, "lights not written");
     hp.shade_list = c->d_shade_list; hp.shade_count = c->d_counters + CTR_NSHADE;
+    if (mg_composite && c->mg.rank != 0) {
+        // first store of this frame into rank 0's colour target (the clear colour of k_shade_pre): not before rank 0 says the
+        // target is free — the shadow-epoch wait further down comes too late for it and does not exist without shadow lights
+        MgWait w;
+        w.n = 1; w.flag[0] = &c->mg.ctrl->fb_free; w.value = c->mg.draw_epoch; w.error = &c->mg.ctrl->error; w.timeout_ns = mg_timeout_ns();
+        k_wait_flags<<<1, 32, 0, c->stream>>>(w);
+        c->launches++;
+    }
     if (c->W % 4 == 0) {
         dim3 grid4((c->W + 127) / 128, (row1 - row0 + 7) / 8);
         k_shade_pre4<<<grid4, 256, 0, c->stream>>>(hp);
+        c->launches++;
     } else {
         dim3 grid((c->W + 31) / 32, (row1 - row0 + 7) / 8);
         k_shade_pre<<<grid, 256, 0, c->stream>>>(hp);
+        c->launches++;
     }
     if ((r = join_shadows(c))) return r;                                                   // the cubemaps must be complete before shading
     if (c->mg.connected && c->mg.shadow_epoch && (r = mg_wait(c, c->stream, true, c->mg.shadow_epoch))) return r;   // ... the peers' faces too
     k_shade<<<grid_for(c, 48), 128, 0, c->stream>>>(hp);      // 4x more CTAs than fit: the tail of the stride loop balances better (0.232 -> 0.219 ms on c3)
+    c->launches++;
     if (mg_composite && c->mg.rank != 0) {                     // this context's rows are in rank 0's colour target
         k_signal_flag<<<1, 1, 0, c->stream>>>(&c->mg.peer_ctrl[0]->draw_flag[c->mg.rank], c->mg.draw_epoch);
         c->launches++;
     }
     if (mg_composite && c->mg.rank == 0 && (r = mg_wait(c, c->stream, false, c->mg.draw_epoch))) return r;             // composite complete
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
-    c->launches += 3;
     c->have_frame_ev = c->stage_events;
     CU(cudaGetLastError());
     return RR_OK;
@@ -1069,7 +1134,15 @@ int rr_sync(rr_ctx* c) {
         CU(cudaMemcpy(&perr, &c->mg.ctrl->error, 4, cudaMemcpyDeviceToHost));
         if (perr) return fail(RR_ERR_PEER, "multi-GPU exchange: a peer context did not deliver its faces / rows within the time limit (rank %d of %d)", c->mg.rank, c->mg.world);
     }
-    const uint32_t ovf = c->h_counters[CTR_OVERFLOW] | c->h_counters[CTR_COUNT + CTR_OVERFLOW];
+    const uint32_t ovf = c->h_counters[CTR_OVERFLOW] | c->h_counters[CTR_STICKY] | c->h_counters[CTR_COUNT + CTR_OVERFLOW] | c->h_counters[CTR_COUNT + CTR_STICKY];
+    c->last_overflow = ovf;
+    if (ovf) {                                             // reported once: clear the current and the sticky words of both workspaces
+        CU(cudaMemsetAsync(c->d_counters + CTR_OVERFLOW, 0, 4, c->stream));
+        CU(cudaMemsetAsync(c->d_counters + CTR_STICKY, 0, 4, c->stream));
+        CU(cudaMemsetAsync(c->d_scounters + CTR_OVERFLOW, 0, 4, c->stream));
+        CU(cudaMemsetAsync(c->d_scounters + CTR_STICKY, 0, 4, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
     if (ovf)
         return fail(RR_ERR_OVERFLOW, "raster storage exhausted (flags %u): fragments cap %u, projected-triangle cap %u", ovf, c->cap_frags, c->cap_cut);
     return RR_OK;
@@ -1143,7 +1216,7 @@ int rr_get_timings(rr_ctx* c, rr_timings* t) {
     t->n_cutdown = c->h_counters[CTR_NCUT];
     t->n_fragments = c->h_counters[CTR_NFRAG];
     t->n_shadow_fragments = c->h_counters[CTR_COUNT + CTR_S_NFRAG];    // stored (non-inlined) fragments of the last shadow pass
-    t->overflow = c->h_counters[CTR_OVERFLOW] | c->h_counters[CTR_COUNT + CTR_OVERFLOW];
+    t->overflow = c->last_overflow;
     t->launches = c->launches;
     return RR_OK;
 }
@@ -1157,7 +1230,19 @@ int rr_bind_external(rr_ctx* c, int which, void* p, size_t nbytes) {
     switch (which) {
         case RR_BUF_RGBA8:
             if (nbytes < P * 4) return fail(RR_ERR_INVALID, "external RGBA8 buffer too small");
-            if (!c->ext_rgba8) cudaFree(c->d_rgba8);
+            CU(cudaStreamSynchronize(c->stream3));
+            for (int i = 0; i < RR_RING_MAX; i++) c->copy_pending[i] = false;
+            if (!c->ext_rgba8) {                           // own target(s): the ring of rr_frame_e2e may hold the current one
+                bool in_ring = false;
+                for (int i = 0; i < RR_RING_MAX; i++) {
+                    if (!c->d_ring[i]) continue;
+                    if (c->d_ring[i] == c->d_rgba8) in_ring = true;
+                    cudaFree(c->d_ring[i]);
+                    c->d_ring[i] = nullptr;
+                }
+                if (!in_ring) cudaFree(c->d_rgba8);
+            }
+            c->ring_pos = 0;
             c->d_rgba8 = (uchar4*)p; c->ext_rgba8 = true; return RR_OK;
         case RR_BUF_SHADOW_DYNAMIC:
             if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
@@ -1379,8 +1464,10 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     if (!c || !host_rgba8) return fail(RR_ERR_INVALID, "null argument");
     int r;
     // per-frame input: the object descriptors (object_context::flush_locations, object_context.cpp:819) from pinned memory
+    // (snapshotted into the staging arena: the caller may patch the mirror for the next frame as soon as this call returns,
+    // while this frame's copy has not executed yet — the ring keeps several frames in flight)
     if (c->n_objs) {
-        CU(cudaMemcpyAsync(c->d_objs, c->h_objs_pinned, (size_t)c->n_objs * sizeof(rr_obj_desc), cudaMemcpyHostToDevice, c->stream));
+        if ((r = upload_staged(c, c->d_objs, c->h_objs_pinned, (size_t)c->n_objs * sizeof(rr_obj_desc)))) return r;
         c->objlite_dirty = true;
     }
     // Pipelined read-back over a ring of D colour targets (the reference keeps a ring of host buffers for the same reason,
@@ -1397,8 +1484,9 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
         if (!c->d_ring[k]) CU(cudaMalloc((void**)&c->d_ring[k], P * 4));
         c->d_rgba8 = c->d_ring[k];
     }
-    // target k is free again once the copy of frame n - D is done. Multi-GPU: rank 0's main stream waits for that before it
-    // forks this frame's shadow work, and no peer can shade this frame before rank 0 has delivered its faces.
+    // target k is free again once the copy of frame n - D is done. Multi-GPU composite: rank 0's main stream waits for that and
+    // then publishes the draw epoch in every peer's control block (fb_free, rr_frame_draw); a peer's first store into rank 0's
+    // target waits for it.
     if (pipelined && c->copy_pending[k]) CU(cudaStreamWaitEvent(c->stream, c->ev_copy_done[k], 0));
     if (with_shadows && (r = rr_frame_shadows(c, 0))) return r;
     if ((r = rr_frame_draw(c, c_pos, c_rot, clear_rgba))) return r;

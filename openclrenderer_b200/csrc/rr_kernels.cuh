@@ -24,7 +24,9 @@ enum {
     CTR_NACTIVE = 13,  // k_frame_prologue: setup blocks with at least one cluster that is not culled
     CTR_CUT_SKIPPED = 14,  // ... and the projected-triangle slots of the blocks that were skipped
     CTR_PROLOGUE_TICKET = 15,  // last-CTA detection of k_frame_prologue (self-resetting)
-    CTR_COUNT = 16
+    CTR_STICKY = 16,   // overflow flags of earlier frames / passes: the per-frame zeroing ORs CTR_OVERFLOW in here before clearing it,
+                       // so a pipelined caller still sees an overflow at its next rr_sync (which reads and clears both words)
+    CTR_COUNT = 17
 };
 
 // per-row ownership bits of the sort-first split (rr_config.band_tile): built on the host at rr_create
@@ -488,6 +490,7 @@ __global__ void __launch_bounds__(PROLOGUE_THREADS) k_frame_prologue(const Prolo
     for (uint32_t j = i; j < P.scan_tiles; j += gridDim.x * blockDim.x) P.scan_lookback[j] = 0ull;
     if (!P.cull) {                           // whole frame, no culling: only the zeroing (cudaMemsetAsync would queue behind a
         if (i == 0) {                        // read-back DMA on the copy engine and stall the frame)
+            P.counters[CTR_STICKY] |= P.counters[CTR_OVERFLOW];
             P.counters[CTR_NCUT] = 0u; P.counters[CTR_NFRAG] = 0u; P.counters[CTR_OVERFLOW] = 0u; P.counters[CTR_TICKET] = 0u;
             P.counters[CTR_NSAMPLES] = 0u; P.counters[CTR_NDESC] = 0u; P.counters[CTR_NSHADE] = 0u;
             P.counters[CTR_SLOTS] = 0u; P.counters[CTR_SCAN_TICKET] = 0u; P.counters[CTR_NBIG] = 0u;
@@ -539,6 +542,7 @@ __global__ void __launch_bounds__(PROLOGUE_THREADS) k_frame_prologue(const Prolo
     }
     if (tid == 0) {
         P.counters[CTR_PROLOGUE_TICKET] = 0u;
+        P.counters[CTR_STICKY] |= P.counters[CTR_OVERFLOW];
         P.counters[CTR_NCUT] = ta == 0 ? ts : 0u;                 // nothing survives: k_setup_main's blocks all leave at once
         P.counters[CTR_NFRAG] = 0u; P.counters[CTR_OVERFLOW] = 0u; P.counters[CTR_TICKET] = 0u;
         P.counters[CTR_NSAMPLES] = 0u; P.counters[CTR_NDESC] = 0u; P.counters[CTR_NSHADE] = 0u;
@@ -1233,7 +1237,9 @@ struct MgCtrl {
     uint32_t draw_flag[MG_MAX_WORLD];       // [q] = last draw epoch rank q has finished storing into this context's colour target
     uint32_t push_done, shade_done;         // last-CTA counters of the local producing kernels
     uint32_t error;                         // bit 0: a wait timed out
-    uint32_t _pad[13];
+    uint32_t fb_free;                       // written by rank 0: last draw epoch whose colour target on rank 0 may be stored into (the copy of
+                                            // the frame that used the ring slot before has left it); peers wait for it before their first store
+    uint32_t _pad[12];
 };
 
 struct MgSignal {                           // raised by the last CTA of a kernel; n == 0: nothing to do
@@ -1263,6 +1269,13 @@ __device__ __forceinline__ void mg_signal_tail(const MgSignal& S) {
 __global__ void k_signal_flag(uint32_t* flag, uint32_t value) {
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t*>(flag) = value;
+}
+
+// same for several flags at once (rank 0 -> every peer's fb_free), one lane per flag
+struct MgFlagList { uint32_t* flag[MG_MAX_WORLD]; int n; uint32_t value; };
+__global__ void __launch_bounds__(32) k_signal_flags(const MgFlagList S) {
+    __threadfence_system();
+    if ((int)threadIdx.x < S.n) *reinterpret_cast<volatile uint32_t*>(S.flag[threadIdx.x]) = S.value;
 }
 
 struct MgWait { const uint32_t* flag[MG_MAX_WORLD]; int n; uint32_t value; uint32_t* error; unsigned long long timeout_ns; };
@@ -1334,6 +1347,8 @@ __global__ void __launch_bounds__(256) k_zero_shadow_state(uint32_t* __restrict_
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t j = i; j < tiles; j += gridDim.x * blockDim.x) lookback[j] = 0ull;
     if (i == 0) {
+        counters[CTR_STICKY] |= counters[CTR_OVERFLOW];           // one pass's overflow stays visible until rr_sync has reported it
+        counters[CTR_OVERFLOW] = 0u;
         counters[CTR_S_NFRAG] = 0u; counters[CTR_S_NCUT] = 0u;
         counters[CTR_SLOTS] = 0u; counters[CTR_SCAN_TICKET] = 0u; counters[CTR_NBIG] = 0u;
     }

@@ -160,6 +160,12 @@ struct texture_context {
         return -1;
     }
     texture_context_data alloc_gpu(object_context& ctx, rr_ctx* dev);      // texture_context.cpp:350-517, defined below
+    // textures referenced by the active objects (+ force_load ones), ascending id: what alloc_gpu would lay out
+    std::vector<texture_id_t> ids_in_use(object_context& ctx);
+    std::vector<texture_id_t> built_ids;            // the set the live atlas was planned for
+    std::vector<int> built_dims;
+    bool built = false;
+    bool should_realloc(object_context& ctx);        // texture_context.cpp should_realloc: the atlas no longer matches the scene
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -175,6 +181,7 @@ struct object {
     int feature_flag = 0, buffer_offset = 0;
     bool isactive = false, isloaded = false;
     int object_g_id = -1, gpu_tri_start = 0, gpu_tri_end = 0;
+    int object_g_id_next = -1;     // descriptor slot in the scene being built asynchronously; becomes object_g_id at flip()
     std::string object_name;
     void set_active(bool a) { isactive = a; }
     void set_pos(cl_float4 p) { pos = p; }
@@ -263,6 +270,9 @@ struct object_context {
     void flip() {
         if (!rebuilding_async) return;
         if (rr_scene_build_commit(gpu_dat.dev)) rr_fatal("rr_scene_build_commit");
+        // only now do g_flush / flush_locations address the new descriptor array (until here they patched the front scene
+        // with the ids it was built with); objects that moved while the upload was in flight are re-sent by the next flush
+        for (auto* c : containers) for (auto& it : c->objs) it.object_g_id = c->isactive ? it.object_g_id_next : -1;
         rebuilding_async = false;
     }
     // object_context::build (object_context.cpp:646-797): textures -> descriptors (228-339) -> triangles (346-458).
@@ -273,14 +283,22 @@ struct object_context {
         if (!dev) throw std::runtime_error("object_context::build before engine::load");
         if (rebuilding_async) flip();                                                              // object_context.cpp:651-658 ("cap")
         if (gpu_dat.tri_num == 0) async = false;                                                   // "we want there to be some valid gpu presence" (723)
-        gpu_dat.tex_gpu_ctx = tex_ctx.alloc_gpu(*this, dev);
+        // Textures are rebuilt only when the set in use changed (texture_context::should_realloc, object_context.cpp:670-707). The
+        // atlas is a single live device resource here: re-planning it moves tiles under the frames that still render the front
+        // scene, so a build that changes the texture set is done synchronously as a whole (atlas and geometry switch together);
+        // a build that keeps the texture set stays asynchronous and never touches the atlas.
+        if (tex_ctx.should_realloc(*this)) {
+            async = false;
+            gpu_dat.tex_gpu_ctx = tex_ctx.alloc_gpu(*this, dev);
+        }
         std::vector<rr_obj_desc> desc;
         int triangle_count = 0;
         for (auto* c : containers) {
             if (!c->isactive) continue;
             for (auto& it : c->objs) {
                 rr_obj_desc d{};
-                it.object_g_id = (int)desc.size();
+                it.object_g_id_next = (int)desc.size();
+                if (!async) it.object_g_id = it.object_g_id_next;
                 d.tid = (cl_uint)tex_ctx.get_gpu_position_id((int)it.tid);
                 d.rid = (cl_uint)tex_ctx.get_gpu_position_id((int)it.rid);
                 d.ssid = (cl_uint)tex_ctx.get_gpu_position_id((int)it.ssid);
@@ -303,7 +321,7 @@ struct object_context {
         for (auto* c : containers) {
             if (!c->isactive) continue;
             for (auto& it : c->objs) {
-                for (auto& t : it.tri_list) t.vertices[0].set_pad((cl_uint)it.object_g_id);       // object_context.cpp:427 / fill_ids
+                for (auto& t : it.tri_list) t.vertices[0].set_pad((cl_uint)it.object_g_id_next);  // object_context.cpp:427 / fill_ids
                 if (!it.tri_list.empty() &&
                     write_tris(dev, (uint32_t)it.gpu_tri_start, (uint32_t)it.tri_list.size(), (const rr_triangle*)it.tri_list.data()))
                     rr_fatal("rr_scene_write_tris");
@@ -353,7 +371,7 @@ inline void plan_texture_pages(const std::vector<int>& dims, std::vector<cl_uint
 }
 
 // texture_context::alloc_gpu: page planner (texture_context.cpp:94-261) + uploads (texture.cpp:323-358, 465-493)
-inline texture_context_data texture_context::alloc_gpu(object_context& ctx, rr_ctx* dev) {
+inline std::vector<texture_id_t> texture_context::ids_in_use(object_context& ctx) {
     std::set<texture_id_t> in_use;
     for (auto* c : ctx.containers) {
         if (!c->isactive) continue;
@@ -364,6 +382,23 @@ inline texture_context_data texture_context::alloc_gpu(object_context& ctx, rr_c
         }
     }
     for (auto* t : all_textures) if (t->force_load) in_use.insert(t->id);
+    return std::vector<texture_id_t>(in_use.begin(), in_use.end());
+}
+
+inline bool texture_context::should_realloc(object_context& ctx) {
+    if (!built) return true;
+    const std::vector<texture_id_t> ids = ids_in_use(ctx);
+    if (ids != built_ids) return true;
+    for (size_t i = 0; i < ids.size(); i++) {
+        texture* t = id_to_tex(ids[i]);
+        t->load();
+        if (t->get_largest_dimension() != built_dims[i]) return true;
+    }
+    return false;
+}
+
+inline texture_context_data texture_context::alloc_gpu(object_context& ctx, rr_ctx* dev) {
+    const std::vector<texture_id_t> in_use = ids_in_use(ctx);
     texture_id_orders.assign(in_use.begin(), in_use.end());
     mipmap_start = (cl_uint)in_use.size();
     for (auto id : in_use) id_to_tex(id)->load();
@@ -378,6 +413,7 @@ inline texture_context_data texture_context::alloc_gpu(object_context& ctx, rr_c
         t->gpu_id = c++;
         if (rr_atlas_upload(dev, (uint32_t)t->gpu_id, t->c_image.data(), (uint32_t)t->w, (uint32_t)t->h, 1)) rr_fatal("rr_atlas_upload");
     }
+    built_ids = in_use; built_dims = dims; built = true;
     texture_context_data d; d.mipmap_start = mipmap_start;
     return d;
 }

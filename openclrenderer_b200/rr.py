@@ -68,20 +68,30 @@ def load_library():
     return _LIB
 
 
+class _PinnedBlock:
+    """owner of one rr_host_alloc block; numpy keeps it alive as the base of every view and it frees the block when collected"""
+
+    def __init__(self, lib, ptr, nbytes):
+        self._lib, self._ptr = lib, ptr
+        self.__array_interface__ = {"data": (ptr, False), "shape": (nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self._lib.rr_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
 def host_alloc(shape, dtype=np.uint8):
-    """numpy array over page-locked memory from rr_host_alloc (freed when the array's base is collected)."""
+    """numpy array over page-locked memory from rr_host_alloc (rr_host_free runs when the last view of it is collected)."""
     lib = load_library()
-    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    n = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
     p = lib.rr_host_alloc(n)
     if not p:
         raise RRError(-3, "rr_host_alloc failed")
-    buf = (C.c_uint8 * n).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    _PINNED[id(buf)] = (buf, p)
-    return arr
-
-
-_PINNED = {}
+    return np.asarray(_PinnedBlock(lib, p, n)).view(dtype)[:int(np.prod(shape))].reshape(shape)
 
 
 def fov_const_from_hfov(hfov_deg, width):
