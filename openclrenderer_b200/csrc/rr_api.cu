@@ -403,6 +403,31 @@ int mg_push(rr_ctx* c, cudaStream_t st, int b, uint32_t epoch) {
 
 }  // namespace
 
+// Every kernel of the library is loaded when the first context is created. With CUDA's default lazy module loading the first
+// launch of a kernel loads it, and that load can wait for running kernels to finish: a k_wait_flags spinning on a flag whose
+// writer (k_signal_flags, k_push_faces ...) has never been launched before would then never be released. Loading up front
+// makes the spin-wait protocols independent of launch history.
+static int preload_kernels() {
+    static bool done = false;
+    if (done) return RR_OK;
+    const void* fns[] = {
+        (const void*)k_repack, (const void*)k_objlite, (const void*)k_lightlite, (const void*)k_obj_rows, (const void*)k_cluster_bounds,
+        (const void*)k_frame_prologue, (const void*)k_setup_main<false>, (const void*)k_setup_main<true>,
+        (const void*)k_raster_small<RM_DEPTH>, (const void*)k_raster_small<RM_IDS>, (const void*)k_raster_small<RM_SHADOW>,
+        (const void*)k_raster_big<RM_DEPTH>, (const void*)k_raster_big<RM_IDS>, (const void*)k_raster_big<RM_SHADOW>,
+        (const void*)k_ids_list, (const void*)k_scan_big, (const void*)k_shadow_setup, (const void*)k_cluster_faces,
+        (const void*)k_signal_flag, (const void*)k_signal_flags, (const void*)k_wait_flags, (const void*)k_push_faces, (const void*)k_fill_faces,
+        (const void*)k_zero_shadow_state, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip,
+        (const void*)k_shade_pre, (const void*)k_shade_pre4, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_copy_u32,
+    };
+    for (const void* f : fns) {
+        cudaFuncAttributes a;
+        CU(cudaFuncGetAttributes(&a, f));
+    }
+    done = true;
+    return RR_OK;
+}
+
 extern "C" {
 
 const char* rr_last_error(void) { return g_err; }
@@ -444,6 +469,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { fail(RR_ERR_CUDA, "cudaGetDeviceProperties failed"); return nullptr; }
     if (prop.major < 10) { fail(RR_ERR_CUDA, "rr_create: device is sm_%d%d; this build carries only sm_100a code", prop.major, prop.minor); return nullptr; }
+    if (preload_kernels() != RR_OK) return nullptr;
     rr_ctx* c = new (std::nothrow) rr_ctx();
     if (!c) { fail(RR_ERR_OOM, "host alloc"); return nullptr; }
     c->cfg = *cfg;
