@@ -49,6 +49,14 @@ FaceTable make_face_table() {                         // r_struct, cl2.cl:4487-4
     return t;
 }
 
+// largest float t with sqrtf(t) <= depth_far (IEEE sqrt is monotone, so sqrtf(d2) > depth_far <=> d2 > t)
+float far2_threshold() {
+    float t = RR_DEPTH_FAR * RR_DEPTH_FAR;
+    while (sqrtf(t) > RR_DEPTH_FAR) t = nextafterf(t, 0.f);
+    while (sqrtf(nextafterf(t, INFINITY)) <= RR_DEPTH_FAR) t = nextafterf(t, INFINITY);
+    return t;
+}
+
 enum { EV_SH0, EV_SH1, EV_F0, EV_SETUP, EV_DEPTH, EV_IDS, EV_SHADE, EV_COUNT };
 
 }  // namespace
@@ -109,6 +117,10 @@ struct rr_ctx {
     LightLite* d_lightlite = nullptr;
     uint32_t n_shadow = 0, n_static = 0;
     uint32_t *d_shadow_dyn = nullptr, *d_shadow_static = nullptr;
+    // second dynamic cubemap buffer (context-owned buffers only): while frame n shades from one, the other — last read by frame
+    // n-1 — is cleared behind frame n's shadow pass on the shadow stream, so the clear (engine.cpp:1615) is off the critical path
+    uint32_t* d_shadow_alt = nullptr;
+    bool alt_clean = false;
     bool ext_shadow_dyn = false, ext_shadow_static = false;
     size_t shadow_dyn_words = 0, shadow_static_words = 0;
     // frame targets
@@ -169,6 +181,7 @@ struct rr_ctx {
     uint8_t* d_cluster_vis = nullptr;            // main view: 0 = culled this frame (k_cluster_vis)
     uint32_t *d_active = nullptr, *d_skipped = nullptr;   // k_frame_prologue: surviving setup blocks, slots skipped in front of each
     bool stage_events = false;                   // rr_set_profiling: per-stage CUDA timing events for rr_get_timings (the reference's -DPROFILING)
+    int shadow_pretest = 1;                      // k_shadow_setup's early back-face cull (RR_SHADOW_PRETEST=0 turns it off for A/B runs)
     int cluster_cull = 0;                        // rr_config.cluster_cull: 0 = when the frame is split (sort-first), 1 = always, -1 = never
     uint4* d_cluster_faces = nullptr;            // face sharding: per-cluster cube-face reach of the lights of the pass
     // multi-GPU exchange over peer memory (rr_mgpu_*)
@@ -417,7 +430,7 @@ static int preload_kernels() {
         (const void*)k_raster_big<RM_DEPTH>, (const void*)k_raster_big<RM_IDS>, (const void*)k_raster_big<RM_SHADOW>,
         (const void*)k_ids_list, (const void*)k_scan_big, (const void*)k_shadow_setup, (const void*)k_cluster_faces,
         (const void*)k_signal_flag, (const void*)k_signal_flags, (const void*)k_wait_flags, (const void*)k_push_faces, (const void*)k_fill_faces,
-        (const void*)k_zero_shadow_state, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip,
+        (const void*)k_raster_shadow_warp, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip,
         (const void*)k_shade_pre, (const void*)k_shade_pre4, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_copy_u32,
     };
     for (const void* f : fns) {
@@ -478,6 +491,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     c->sm_count = prop.multiProcessorCount;
     c->faces = make_face_table();
     c->cluster_cull = cfg->cluster_cull;
+    if (const char* e = getenv("RR_SHADOW_PRETEST")) c->shadow_pretest = atoi(e) != 0;
     auto bail = [&](const char* what) { fail(RR_ERR_CUDA, "rr_create: %s: %s", what, cudaGetErrorString(cudaGetLastError())); rr_destroy(c); return (rr_ctx*)nullptr; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
     for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail("event");
@@ -556,6 +570,7 @@ void rr_destroy(rr_ctx* c) {
     cudaFree(c->d_atlas); cudaFree(c->d_nums); cudaFree(c->d_sizes); cudaFree(c->d_upload);
     cudaFree(c->d_lights); cudaFree(c->d_lightlite);
     if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
+    cudaFree(c->d_shadow_alt);
     if (!c->ext_shadow_static) cudaFree(c->d_shadow_static);
     for (int i = 0; i < 2; i++) { cudaFree(c->d_depth[i]); cudaFree(c->d_ids[i]); }
     if (!c->ext_rgba8) cudaFree(c->d_rgba8);
@@ -859,6 +874,9 @@ int rr_lights_write(rr_ctx* c, const rr_light* lights, uint32_t n_active) {
         c->shadow_dyn_words = std::max<size_t>(slab * ns, 4);
         if ((r = dev_alloc(c->d_shadow_dyn, c->shadow_dyn_words))) return r;
         if ((r = fill_u32(c, c->stream, c->d_shadow_dyn, c->shadow_dyn_words, 0xFFFFFFFFu))) return r;
+        if ((r = dev_alloc(c->d_shadow_alt, c->shadow_dyn_words))) return r;
+        if ((r = fill_u32(c, c->stream, c->d_shadow_alt, c->shadow_dyn_words, 0xFFFFFFFFu))) return r;
+        c->alt_clean = true;
     }
     if (!c->ext_shadow_static && (nst != c->n_static || !c->d_shadow_static)) {
         c->shadow_static_words = std::max<size_t>(slab * nst, 4);
@@ -894,12 +912,9 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         slab++;
     }
     if (sel.empty() || c->n_tris == 0) return RR_OK;
-    int r;
     for (size_t first = 0; first < sel.size(); first += SHADOW_MAX_LIGHTS) {
         const int nl = (int)std::min<size_t>(SHADOW_MAX_LIGHTS, sel.size() - first);
         cudaStream_t st = c->stream2;
-        k_zero_shadow_state<<<16, 256, 0, st>>>(c->d_scounters, c->d_sscan_lookback, c->scan_tiles);
-        c->launches++;
         ShadowSetupParams sp;
         sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
         sp.n_lights = nl;
@@ -908,28 +923,30 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         sp.faces = c->faces;
         sp.L = (float)c->L; sp.icut = (float)c->cfg.depth_icutoff;
         sp.only_static = only_static;
+        sp.pretest = c->shadow_pretest;
+        sp.far2_max = far2_threshold();
         sp.frags = c->d_sfrags; sp.cap_frags = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS) / RR_SFRAG_WORDS);
         sp.fragcnt = c->d_sfragcnt;
         sp.cutdown = c->d_scutdown; sp.cap_cut = c->cap_cut; sp.counters = c->d_scounters;
         sp.buffer = buffer;
-        sp.cluster_faces = nullptr;
-        if (sharded && c->n_objs && c->n_clusters) {   // clusters whose bounding box cannot reach a face rendered here are skipped whole
+        {   // per-cluster cube-face reach of this pass's lights (a block of k_shadow_setup == one cluster): clusters that cannot reach a
+            // face rendered here leave at once, clusters that reach a single face skip ret_cubeface; also zeroes the pass's counters
             ObjFacesParams fp;
             fp.n_lights = nl;
             for (int k = 0; k < nl; k++) fp.lights[k] = sel[first + k];
-            k_cluster_faces<<<(c->n_clusters + 127) / 128, 128, 0, st>>>(c->d_clusters, c->n_clusters, c->d_objlite, c->n_objs, fp, c->d_cluster_faces);
+            k_cluster_faces<<<(c->n_clusters + 127) / 128, 128, 0, st>>>(c->d_clusters, c->n_clusters, c->d_objlite, c->n_objs, fp, c->d_cluster_faces, c->d_scounters);
             c->launches++;
             sp.cluster_faces = c->d_cluster_faces;
         }
         k_shadow_setup<<<(c->n_tris + 127) / 128, 128, 0, st>>>(sp);
         c->launches++;
-        if ((r = scan_big(c, st, c->d_scounters, c->d_sfragcnt, c->d_sbiglist, c->d_sbigslot, c->d_sscan_lookback, CTR_S_NFRAG, sp.cap_frags, true))) return r;
         dp.frags = c->d_sfrags; dp.cutdown = c->d_scutdown; dp.fragcnt = c->d_sfragcnt; dp.counters = c->d_scounters; dp.cap_frags = sp.cap_frags;
-        dp.biglist = c->d_sbiglist; dp.bigslot = c->d_sbigslot;
+        dp.biglist = nullptr; dp.bigslot = nullptr;
         dp.n_index = CTR_S_NFRAG;
         dp.depth = buffer; dp.ids = nullptr; dp.width = (float)c->L; dp.height = (float)c->L; dp.W = c->L;
         dp.row_lo = 0; dp.row_hi = c->L; dp.rowmask = nullptr; dp.rowbit = 0;
-        if ((r = raster<RM_SHADOW>(c, st, dp))) return r;
+        k_raster_shadow_warp<<<grid_for(c, 4), 256, 0, st>>>(dp);                         // the stored fragments (triangles larger than one small chunk)
+        c->launches++;
     }
     CU(cudaGetLastError());
     return RR_OK;
@@ -959,7 +976,10 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     if (!c->lights.empty()) {                                                              // engine.cpp:1611-1626
         // a full clear (not only the owned faces) keeps the buffer defined for the all-gather that follows
         if (c->mg.connected) { if (c->n_shadow && mg_epoch && (r = mg_fill_owned(c, c->stream2, c->d_shadow_dyn))) return r; }
-        else if (c->n_shadow && (r = fill_u32(c, c->stream2, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
+        else if (c->n_shadow) {
+            if (!c->ext_shadow_dyn && c->d_shadow_alt && c->alt_clean) { std::swap(c->d_shadow_dyn, c->d_shadow_alt); c->alt_clean = false; }   // cleared behind the previous pass
+            else if ((r = fill_u32(c, c->stream2, c->d_shadow_dyn, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
+        }
         if (static_lights_dirty && c->n_static && (r = fill_u32(c, c->stream2, c->d_shadow_static, slab * c->n_static, 0xFFFFFFFFu))) return r;
     }
     if (c->n_shadow && (r = shadow_pass(c, 0))) return r;                                  // engine.cpp:1629-1697
@@ -967,6 +987,12 @@ int rr_frame_shadows(rr_ctx* c, int static_lights_dirty) {
     if (c->mg.connected && c->n_shadow && mg_epoch && (r = mg_push(c, c->stream2, mgb, mg_epoch))) return r;
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SH1], c->stream2));
     CU(cudaEventRecord(c->ev_shadow_done, c->stream2));
+    if (!c->mg.connected && !c->ext_shadow_dyn && c->d_shadow_alt && c->n_shadow && !c->lights.empty()) {
+        // the other buffer was last read by the previous frame's shading, which the fork above is ordered after: clear it now, behind
+        // this frame's pass, for the next frame (it runs beside the main view's kernels and the shading, which are not memory-bound)
+        if ((r = fill_u32(c, c->stream2, c->d_shadow_alt, slab * c->n_shadow, 0xFFFFFFFFu))) return r;
+        c->alt_clean = true;
+    }
     c->have_shadow_ev = c->stage_events;
     c->shadow_pending = true;
     return RR_OK;
@@ -1272,6 +1298,7 @@ int rr_bind_external(rr_ctx* c, int which, void* p, size_t nbytes) {
             c->d_rgba8 = (uchar4*)p; c->ext_rgba8 = true; return RR_OK;
         case RR_BUF_SHADOW_DYNAMIC:
             if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
+            cudaFree(c->d_shadow_alt); c->d_shadow_alt = nullptr; c->alt_clean = false;
             c->d_shadow_dyn = (uint32_t*)p; c->ext_shadow_dyn = true; c->shadow_dyn_words = nbytes / 4; return RR_OK;
         case RR_BUF_SHADOW_STATIC:
             if (!c->ext_shadow_static) cudaFree(c->d_shadow_static);

@@ -1032,14 +1032,16 @@ struct ShadowSetupParams {
     ShadowLight lights[SHADOW_MAX_LIGHTS];
     FaceTable faces;
     float L, icut;
+    float far2_max;                          // largest float t with sqrtf(t) <= depth_far: length(v) > depth_far <=> dot(v, v) > far2_max (sqrt.rn is monotone)
     int only_static;
+    int pretest;                             // 1: cull clearly back-facing triangles before they are transformed (see shadow_clearly_back)
     uint32_t* frags; uint32_t cap_frags;
     uint32_t* fragcnt;
     float4* cutdown; uint32_t cap_cut;
     uint32_t* counters;
     uint32_t* buffer;                        // cubemap buffer of this pass (inline raster of small triangles)
-    const uint4* cluster_faces;              // face sharding: byte li of cluster_faces[block] = cube faces of light li the cluster's
-                                             // bounding box can reach (k_cluster_faces); nullptr = every face
+    const uint4* cluster_faces;              // byte li of cluster_faces[block] = cube faces of light li the cluster's bounding box can
+                                             // reach (k_cluster_faces); nullptr = every face
 };
 
 // reserve `nc` projected-triangle slots and `nf` fragment records for this lane; one atomic per warp
@@ -1057,12 +1059,10 @@ __device__ __forceinline__ void warp_alloc2(uint32_t* counters, uint32_t nc, uin
     fbase = (uint32_t)(base & 0xFFFFFFFFull);
 }
 
-// Minimum resident CTAs per SM the register allocation is asked to allow. k_shadow_setup is latency-bound at 96 registers
-// (5 CTAs, 25 % of the warps resident): capped at 64 registers (8 CTAs) it spills 208 bytes per thread to L1 and the frame
-// gets 4.9 % faster (A/B on one box, ms/frame on c3: default 0.596, 6 CTAs 0.583, 8 CTAs 0.567; k_shade at 8 CTAs alone
-// 0.592 and not adopted). Build-time knobs for further A/B runs: -DRR_LB_SHADOW_SETUP=n, -DRR_LB_SHADE=n, RR_LIB=<other build>.
+// Minimum resident CTAs per SM the register allocation is asked to allow (build-time knobs for A/B runs:
+// -DRR_LB_SHADOW_SETUP=n, -DRR_LB_SHADE=n, RR_LIB=<other build>; examples/lb_sweep.sh).
 #ifndef RR_LB_SHADOW_SETUP
-#define RR_LB_SHADOW_SETUP 8
+#define RR_LB_SHADOW_SETUP 6
 #endif
 #define RR_LB_SHADOW_SETUP_ATTR __launch_bounds__(128, RR_LB_SHADOW_SETUP)
 #ifdef RR_LB_SHADE
@@ -1070,26 +1070,156 @@ __device__ __forceinline__ void warp_alloc2(uint32_t* counters, uint32_t nc, uin
 #else
 #define RR_LB_SHADE_ATTR __launch_bounds__(128)
 #endif
-__global__ void RR_LB_SHADOW_SETUP_ATTR k_shadow_setup(const ShadowSetupParams P) {
-    __shared__ InlineQueue s_iq[128 / 32];
-    static_assert(CLUSTER_TRIS == 128, "one k_shadow_setup block == one cluster");
-    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t light_reach = 0xFFFFFFFFu;      // bit li: the cluster can reach a face of light li that is rendered here (block-uniform)
-    if (P.cluster_faces) {                   // face sharding: none of this context's faces can see the cluster -> the block is done
-        const uint4 m = __ldg(P.cluster_faces + blockIdx.x);
-        light_reach = 0u;
-        for (int li = 0; li < P.n_lights; li++) {
-            const uint32_t word = li < 4 ? m.x : (li < 8 ? m.y : (li < 12 ? m.z : m.w));
-            if ((((word >> ((li & 3) * 8)) & 0x3Fu) & P.lights[li].face_mask) != 0) light_reach |= 1u << li;
+
+// Per-warp work queues of k_shadow_setup (shared memory). The kernel is a three-stage pipeline inside each warp, with a
+// compaction between the stages so that every stage runs with (nearly) all 32 lanes busy:
+//   A  per (triangle, light): which cube faces does the triangle mark, is it clearly back-facing   -> items (lane, face, light)
+//   B  per item: rotate into the face's camera, clip, project, cull, classify                      -> small triangles / records
+//   C  per small triangle: rasterise its box straight into the cubemap (kernel1_realtime_shadowing's work for it)
+#define SQ_ITEMS 128            // stage A -> B: up to 3 faces x 32 lanes arrive at once on top of < 32 waiting items
+#define SR_SLOTS 64             // stage B -> C: 32 arrive on top of < 32 waiting
+#define SR_FIELDS 11            // rounded x of the 3 vertices, rounded y, camera z, rconst, face slab index
+struct ShadowWarpQueue {
+    float f[SR_FIELDS][SR_SLOTS];
+    unsigned short item[SQ_ITEMS];          // src lane (5 bits) | face << 5 (3) | light << 8 (4) | two_sided << 12 | second clip half << 13
+};
+
+// Stage A's early cull. A triangle that is not two-sided is dropped by prearrange_realtime_shadowing when its projection is
+// not front-facing, i.e. when cross(p1 - p0, p2 - p0).z >= 0 (cl2.cl:491-494, 4571). For an unclipped triangle that sign is
+// the sign of det(q0, q1, q2) (camera-space vertices, all z > 0), every face camera is a proper rotation about the light, so
+// it is the sign of D = (w0 - light) . n with n = (w1 - w0) x (w2 - w0) — the same for all six faces. The cull fires only
+// when the sign is far from being decided by rounding and the triangle cannot be clipped in any face it marks:
+//   * D > 0 and D^2 > 0.0025 |w0 - light|^2 |n|^2      (the view ray is more than ~2.9 degrees off the triangle's plane)
+//   * longest edge <= 0.1 |w0 - light|                  (then every vertex has z >= 0.32 |w0 - light| in a face that holds one of them)
+//   * 10 (icut + 1)^2 <= |w0 - light|^2 <= 0.8 far^2    (so 0.32 |w0 - light| > icut and z < far: no near / far clipping)
+//   * |n| fov >= 0.22 longest edge |w0 - light|         (projected height >= 5e-3 px at that angle: far above the ~5e-4 px noise
+//                                                        of the projected coordinates the reference decides with)
+// Everything else goes through the exact test of stage B. emax2 = squared longest edge, nn = |n|^2, fov2 = (L/2)^2.
+__device__ __forceinline__ bool shadow_clearly_back(float3 rel0, float3 n, float nn, float emax2, float fov2, float r2lo, float r2hi) {
+    const float D = dot3(rel0, n), r2 = dot3(rel0, rel0);
+    return D > 0.f && D * D > 0.0025f * r2 * nn && emax2 <= 0.01f * r2 && r2 >= r2lo && r2 <= r2hi && nn * fov2 >= 0.0484f * emax2 * r2;
+}
+
+// The literal path of stage C: replays the reference's walk (scan_chunk) with point_in_tri. Only taken by triangles the exact
+// fast path below cannot take (coordinates beyond 2047, a clamped box, a lagging row counter); kept out of line so that its
+// registers do not count against the kernel.
+__device__ __noinline__ void shadow_raster_small_literal(float3 xr, float3 yr, float3 zc, float rconst, float L, uint32_t* __restrict__ target) {
+    const float4 mm = calc_min_max(xr, yr, L, L);
+    float3 d = make_float3(zc.x / RR_DEPTH_FAR, zc.y / RR_DEPTH_FAR, zc.z / RR_DEPTH_FAR);     // dcalc
+    d = make_float3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);                                     // native_recip
+    float A, B, C;
+    interpolate_get_const(d, xr, yr, rconst, A, B, C);
+    scan_chunk(mm, RR_OP_SIZE_LIGHT, 0u, [&](float x, float y) {
+        if (point_in_tri(x, y, xr.x, yr.x, xr.y, yr.y, xr.z, yr.z)) {
+            const float fd = fmaf(A, x, fmaf(B, y, C));
+            atomicMin(target + ((int)(y * L) + (int)x), sat_u32(RR_U32MAXF / fd));
         }
-        if (!light_reach) return;
+    });
+}
+
+#define SR_EXACT 0x80000000u    // flag in a queued triangle's face word: stage B found its coordinates small enough for exact arithmetic
+
+// Stage C for one queued small triangle (single chunk, box of at most RASTER_SMALL_MAX pixel slots).
+// Fast path — every operation below is exact in fp32, so it yields bit for bit what the reference's walk + point_in_tri do:
+//   * SR_EXACT: the rounded vertex coordinates are integers with |v| <= 2047 and extents <= 64, so every product and partial
+//     sum of point_in_tri (cl2.cl:4798-4807) is an integer below 2^24: the edge functions can be stepped incrementally, and
+//     "inside" means inside the CLOSED rounded triangle (s >= 0, t >= 0, s + t <= 2|A|; 2.0001f * |A| < 2|A| + 1 at this size).
+//     Hence only pixels of the vertices' own bounding box can be covered: the walk's extra first row and column
+//     (bbox = [round(min) - 1, round(max)), cl2.cl:420-441) are skipped, the last ones it never visits are left out as well.
+//   * no row of the walk lags: its float row counter floor(fma(k, 1/width, min_y)) is exact at a row start r * width when
+//     r <= min_y (the error r * 2^-24 stays below half an ulp of min_y + r); the few boxes within `rows` of the top edge are
+//     checked row by row. Without a lagging row the walk visits exactly the box (rr_math.cuh scan_chunk).
+// Covered pixels are collected in a bit mask first; the depth plane (six IEEE divisions) is only paid for triangles with a hit.
+__device__ __forceinline__ void shadow_raster_small(const ShadowWarpQueue& Q, int slot, bool valid, float L, uint32_t* __restrict__ buffer) {
+    if (!valid) return;
+    const float* f = &Q.f[0][slot];
+    const float3 xr = make_float3(f[0], f[SR_SLOTS], f[2 * SR_SLOTS]), yr = make_float3(f[3 * SR_SLOTS], f[4 * SR_SLOTS], f[5 * SR_SLOTS]);
+    const uint32_t fw = __float_as_uint(f[10 * SR_SLOTS]);
+    uint32_t* target = buffer + (size_t)(fw & ~SR_EXACT) * (size_t)(L * L);
+    const float4 mm = calc_min_max(xr, yr, L, L);
+    // tight box: the vertices' own bounding box inside the walk's box
+    const float x0 = fmaxf(mm.x, fminf(fminf(xr.x, xr.y), xr.z)), y0 = fmaxf(mm.z, fminf(fminf(yr.x, yr.y), yr.z));
+    const int wt = (int)(mm.y - x0), ht = (int)(mm.w - y0), rows = (int)(mm.w - mm.z);
+    bool fast = (fw & SR_EXACT) && wt * ht <= 32;
+    if (fast && (float)(rows - 1) > mm.z) {                 // a box at the very top of the face: look for a lagging row
+        const int width = (int)(mm.y - mm.x);
+        const float iw = 1.f / (float)width;
+        for (int r = 1; r < rows; r++) fast = fast && walk_row(r * width, iw, mm.z) == mm.z + (float)r;
     }
+    if (!fast) {
+        shadow_raster_small_literal(xr, yr, make_float3(f[6 * SR_SLOTS], f[7 * SR_SLOTS], f[8 * SR_SLOTS]), f[9 * SR_SLOTS], L, target);
+        return;
+    }
+    if (wt <= 0 || ht <= 0) return;
+    const float Ah = 0.5f * (-yr.y * xr.z + yr.x * (-xr.y + xr.z) + xr.x * (yr.y - yr.z) + xr.y * yr.z);
+    const float sign = Ah < 0 ? -1.f : 1.f;
+    const float lim = 2.0001f * Ah * sign;
+    const float as = (yr.z - yr.x) * sign, bs = (xr.x - xr.z) * sign, at = (yr.x - yr.y) * sign, bt = (xr.y - xr.x) * sign;
+    float s_row = (yr.x * xr.z - xr.x * yr.z) * sign + as * x0 + bs * y0;
+    float t_row = (xr.x * yr.y - yr.x * xr.y) * sign + at * x0 + bt * y0;
+    uint32_t mask = 0u, bit = 1u;
+    for (int r = 0; r < ht; r++) {
+        float s = s_row, t = t_row;
+        for (int c = 0; c < wt; c++) {
+            if (s > -0.0001f && t > -0.0001f && (s + t) < lim) mask |= bit;
+            bit <<= 1;
+            s += as; t += at;
+        }
+        s_row += bs; t_row += bt;
+    }
+    if (!mask) return;
+    float3 d = make_float3(f[6 * SR_SLOTS] / RR_DEPTH_FAR, f[7 * SR_SLOTS] / RR_DEPTH_FAR, f[8 * SR_SLOTS] / RR_DEPTH_FAR);     // dcalc, cl2.cl:5029-5040
+    d = make_float3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);                                                                        // native_recip
+    float A, B, C;
+    interpolate_get_const(d, xr, yr, f[9 * SR_SLOTS], A, B, C);
+    const float iwt = __fdividef(1.f, (float)wt);
+    while (mask) {
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const int r = (int)(((float)i + 0.5f) * iwt);       // i / wt: i < 32, wt <= 32, so (i + 0.5) / wt is at least 1/64 away from an integer
+        const float x = x0 + (float)(i - r * wt), y = y0 + (float)r;
+        const float fd = fmaf(A, x, fmaf(B, y, C));
+        atomicMin(target + ((int)(y * L) + (int)x), sat_u32(RR_U32MAXF / fd));
+    }
+}
+
+// =====================================================================================================================
+// shadow passes: k_shadow_setup == prearrange_realtime_shadowing (cl2.cl:4420-4636) for ALL lights of a pass in one launch,
+// plus kernel1_realtime_shadowing (cl2.cl:5130-5246) for every triangle whose walk is one small chunk (97 % of config 3's).
+// The reference launches prearrange once per light and re-reads / re-transforms every triangle each time. Here a thread
+// loads its triangle once and brings it to world space once (bit-identical: that part of full_rotate_quat does not depend
+// on the light); the per-light, per-face work then flows through the warp's queues (ShadowWarpQueue). Slot numbers of a
+// shadow pass are never observable (only the atomic_min result is), so the few triangles that need records get them from
+// ONE warp-aggregated 64-bit atomicAdd that reserves projected-triangle slots and fragment records together.
+// Records: {light << 8 | face, chunk, c_id, bits(rconst)} (cl2.cl:4626-4631 with the light folded into word 0); they are
+// rasterised by k_raster_shadow_warp.
+// =====================================================================================================================
+__global__ void RR_LB_SHADOW_SETUP_ATTR k_shadow_setup(const ShadowSetupParams P) {
+    __shared__ ShadowWarpQueue s_q[128 / 32];
+    __shared__ RotSC s_face[6];
+    __shared__ float4 s_light[SHADOW_MAX_LIGHTS];    // position, w = bits of (slab << 8 | face_mask)
+    static_assert(CLUSTER_TRIS == 128, "one k_shadow_setup block == one cluster");
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tri = blockIdx.x * blockDim.x + tid;
+    uint4 reach4 = make_uint4(0x3F3F3F3Fu, 0x3F3F3F3Fu, 0x3F3F3F3Fu, 0x3F3F3F3Fu);
+    if (P.cluster_faces) reach4 = __ldg(P.cluster_faces + blockIdx.x);
+    auto reach_of = [&](int li) -> uint32_t {
+        const uint32_t word = li < 4 ? reach4.x : (li < 8 ? reach4.y : (li < 12 ? reach4.z : reach4.w));
+        return (word >> ((li & 3) * 8)) & 0x3Fu;
+    };
+    uint32_t light_reach = 0u;               // bit li: the cluster can reach a face of light li that is rendered here (block-uniform)
+    for (int li = 0; li < P.n_lights; li++) if (reach_of(li) & P.lights[li].face_mask) light_reach |= 1u << li;
+    if (!light_reach) return;                // none of this context's faces can see the cluster
+    if (tid < 6) s_face[tid] = P.faces.r[tid];
+    if (tid < P.n_lights) s_light[tid] = make_float4(P.lights[tid].x, P.lights[tid].y, P.lights[tid].z, __uint_as_float((P.lights[tid].slab << 8) | P.lights[tid].face_mask));
+    __syncthreads();
+
+    ShadowWarpQueue& Q = s_q[tid >> 5];
+    const float L = P.L, half = P.L / 2.f;
     bool active = tri < P.n_tris;
-    float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0, gpos = w0;
+    float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0, gpos = w0, nrm = w0;
+    float nn = 0.f, emax2 = 0.f;
     bool two_sided = false;
-    InlineRaster<false> ir;
-    ir.q = &s_iq[threadIdx.x >> 5]; ir.count = 0; ir.op = RR_OP_SIZE_LIGHT; ir.width = P.L; ir.height = P.L; ir.base = P.buffer;
-    ir.face_stride = (size_t)(P.L * P.L); ir.row_lo = 0; ir.row_hi = 0x7FFFFFFF; ir.rowmask = nullptr;
     if (active) {
         const float4 a = __ldg(P.pa + tri), b = __ldg(P.pb + tri);
         const float2 c = __ldg(P.pc + tri);
@@ -1103,64 +1233,190 @@ __global__ void RR_LB_SHADOW_SETUP_ATTR k_shadow_setup(const ShadowSetupParams P
             w1 = rot_quat_n(make_float3(a.w, b.x, b.y) * sc, G.nquat) + gpos;
             w2 = rot_quat_n(make_float3(b.z, b.w, c.x) * sc, G.nquat) + gpos;
             two_sided = (G.feature_flag & RR_FEATURE_TWO_SIDED) > 0;
+            const float3 e1 = w1 - w0, e2 = w2 - w0, e3 = w2 - w1;
+            nrm = cross3(e1, e2);
+            nn = dot3(nrm, nrm);
+            emax2 = fmaxf(fmaxf(dot3(e1, e1), dot3(e2, e2)), dot3(e3, e3));
         }
     }
-    for (int li = 0; li < P.n_lights; li++) {
-        if (!((light_reach >> li) & 1u)) continue;
-        const float3 lpos = make_float3(P.lights[li].x, P.lights[li].y, P.lights[li].z);
-        uint32_t faces = 0;
-        if (active && !(length3(gpos - lpos) > RR_DEPTH_FAR)) {                                  // cl2.cl:4472
-            faces = (1u << ret_cubeface(w0, lpos)) | (1u << ret_cubeface(w1, lpos)) | (1u << ret_cubeface(w2, lpos));   // cl2.cl:4520-4539
-            faces &= P.lights[li].face_mask;
-        }
-        // warp-uniform loop over the six faces so the warp-level allocation stays converged
-        for (int kk = 0; kk < 6; kk++) {
-            const bool mine = (faces >> kk) & 1u;
-            if (!__any_sync(0xffffffffu, mine)) continue;
-            SubTri st0, st1;
-            subtri_clear(st0); subtri_clear(st1);
-            if (mine) {
-                const RotSC& fr = P.faces.r[kk];
-                const int num = clip_project(rot(w0, lpos, fr), rot(w1, lpos, fr), rot(w2, lpos, fr), P.icut, P.L / 2.f, P.L / 2.f, P.L / 2.0f, st0, st1);
-                if (num > 0) classify(st0, two_sided, P.L, P.L, (float)RR_OP_SIZE_LIGHT);
-                if (num > 1) classify(st1, two_sided, P.L, P.L, (float)RR_OP_SIZE_LIGHT);
+    const bool pretest = P.pretest && active && !two_sided && isfinite(nn) && isfinite(emax2);
+    const float r2lo = 10.f * (P.icut + 1.f) * (P.icut + 1.f), r2hi = 0.8f * RR_DEPTH_FAR * RR_DEPTH_FAR, fov2 = half * half;
+    const unsigned lt = (1u << lane) - 1u;
+
+    int qa = 0, qr = 0;                      // items waiting for stage B / small triangles waiting for stage C (warp-uniform)
+    for (int li = 0; li <= P.n_lights; li++) {
+        const bool last = li == P.n_lights;
+        if (!last) {
+            if (!((light_reach >> li) & 1u)) continue;
+            // ---- stage A
+            const float4 l4 = s_light[li];
+            const float3 lpos = make_float3(l4.x, l4.y, l4.z);
+            const uint32_t face_mask = __float_as_uint(l4.w) & 0x3Fu, reach = reach_of(li);
+            uint32_t faces = 0;
+            const float3 gl = gpos - lpos;
+            if (active && !(dot3(gl, gl) > P.far2_max)) {                                        // length(...) > depth_far, cl2.cl:4472 (far2_max: see ShadowSetupParams)
+                // a cluster whose box reaches a single face: every vertex is assigned that face (the reach is a superset)
+                if ((reach & (reach - 1u)) == 0u) faces = reach;
+                else faces = (1u << ret_cubeface(w0, lpos)) | (1u << ret_cubeface(w1, lpos)) | (1u << ret_cubeface(w2, lpos));   // cl2.cl:4520-4539
+                faces &= face_mask;
+                if (faces && pretest && shadow_clearly_back(w0 - lpos, nrm, nn, emax2, fov2, r2lo, r2hi)) faces = 0;
             }
-            // small triangles: queued for the warp to rasterise with all lanes busy; nothing is stored for them
-            const uint32_t face_index = P.lights[li].slab * 6 + (uint32_t)kk;
-            const bool small0 = inline_candidate(st0), small1 = inline_candidate(st1);
-            ir.push(small0, st0, face_index, 0u);
-            ir.push(small1, st1, face_index, 0u);
-            if (small0) st0.keep = false;
-            if (small1) st1.keep = false;
-            if (!__any_sync(0xffffffffu, st0.keep || st1.keep)) continue;
-            const uint32_t nk = (st0.keep ? 1u : 0u) + (st1.keep ? 1u : 0u);
-            const uint32_t nf0 = st0.keep ? (uint32_t)st0.n_frag : 0u, nf1 = st1.keep ? (uint32_t)st1.n_frag : 0u;
-            uint32_t cid, fbase;
-            warp_alloc2(P.counters, nk, nf0 + nf1, cid, fbase);
-            if (nk == 0) continue;
-            if (cid + nk > P.cap_cut) { atomicOr(&P.counters[CTR_OVERFLOW], 2u); continue; }
-            if ((unsigned long long)fbase + nf0 + nf1 > (unsigned long long)P.cap_frags) { atomicOr(&P.counters[CTR_OVERFLOW], 1u); continue; }
-            const uint32_t word0 = ((uint32_t)li << 8) | (uint32_t)kk;
+            const int cnt = __popc(faces);
+            const unsigned m1 = __ballot_sync(0xffffffffu, cnt > 0);
+            if (m1) {
+                const unsigned m2 = __ballot_sync(0xffffffffu, cnt > 1);
+                const unsigned short base_item = (unsigned short)(lane | (li << 8) | (two_sided ? 1 << 12 : 0));
+                if (!m2) {                   // the usual case: at most one face per triangle
+                    if (cnt) Q.item[qa + __popc(m1 & lt)] = (unsigned short)(base_item | ((__ffs(faces) - 1) << 5));
+                    qa += __popc(m1);
+                } else {
+                    int inc = cnt;
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const SubTri& st = i ? st1 : st0;
-                if (!st.keep) continue;
-                float4* dst = P.cutdown + (size_t)cid * 3;
-                dst[0] = make_float4(st.p0.x, st.p0.y, st.p0.z, 0.f);
-                dst[1] = make_float4(st.p1.x, st.p1.y, st.p1.z, 0.f);
-                dst[2] = make_float4(st.p2.x, st.p2.y, st.p2.z, 0.f);
-                const int kend = subtri_walk_end(st, P.L, P.L);
-                uint4* rec = reinterpret_cast<uint4*>(P.frags) + fbase;
-                for (int a = 0; a < st.n_frag; a++) {
-                    rec[a] = make_uint4(word0, (uint32_t)a, cid, __float_as_uint(st.rconst));
-                    P.fragcnt[fbase + a] = chunk_slots(kend, a, RR_OP_SIZE_LIGHT);
+                    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+                    int at = qa + inc - cnt;
+                    for (uint32_t fm = faces; fm; fm &= fm - 1u) Q.item[at++] = (unsigned short)(base_item | ((__ffs(fm) - 1) << 5));
+                    qa += __shfl_sync(0xffffffffu, inc, 31);
                 }
-                fbase += (uint32_t)st.n_frag;
-                cid++;
+            }
+            __syncwarp();
+        }
+        // ---- stage B: 32 items at a time (whatever is left after the last light)
+        while (qa >= 32 || (last && qa > 0)) {
+            const int take = min(qa, 32);
+            qa -= take;
+            const bool have = lane < take;
+            const uint32_t item = have ? Q.item[qa + lane] : 0u;
+            __syncwarp();
+            const int src = item & 31, kk = (item >> 5) & 7, l = (item >> 8) & 15;
+            const bool ts = (item >> 12) & 1u, second = (item >> 13) & 1u;
+            float3 v0, v1, v2;               // the source lane's world-space triangle
+            v0.x = __shfl_sync(0xffffffffu, w0.x, src); v0.y = __shfl_sync(0xffffffffu, w0.y, src); v0.z = __shfl_sync(0xffffffffu, w0.z, src);
+            v1.x = __shfl_sync(0xffffffffu, w1.x, src); v1.y = __shfl_sync(0xffffffffu, w1.y, src); v1.z = __shfl_sync(0xffffffffu, w1.z, src);
+            v2.x = __shfl_sync(0xffffffffu, w2.x, src); v2.y = __shfl_sync(0xffffffffu, w2.y, src); v2.z = __shfl_sync(0xffffffffu, w2.z, src);
+            bool requeue = false, small = false, big = false;
+            float3 p0, p1, p2, xr, yr;       // (only read by lanes that set them: no defaults, so no moves at the branch joins)
+            float rconst, area;
+            uint32_t faceword;
+            if (have) {
+                const float4 l4 = s_light[l];
+                const float3 lpos = make_float3(l4.x, l4.y, l4.z);
+                faceword = (__float_as_uint(l4.w) >> 8) * 6u + (uint32_t)kk;
+                const RotSC fr = s_face[kk];
+                float3 a0, a1, a2;
+                const int num = clip_near_one(rot(v0, lpos, fr), rot(v1, lpos, fr), rot(v2, lpos, fr), P.icut, second, a0, a1, a2);
+                requeue = !second && num > 1;                                                    // the other half of a clipped triangle: same item again
+                if (num > (second ? 1 : 0)) {
+                    p0 = project(a0, half, half, half); p1 = project(a1, half, half, half); p2 = project(a2, half, half, half);
+                    // cull + bbox + fragment count, cl2.cl:4571-4597 (classify() with the bookkeeping stage C needs)
+                    const bool valid = ts || front_facing(p0, p1, p2);
+                    // all three on one outer side of the viewport (cl2.cl:4583-4586): min / max form unless a coordinate is NaN
+                    // (fminf / fmaxf skip NaNs, the reference's comparisons do not); a NaN survives the sum, inf - inf makes one
+                    const float chk = ((p0.x + p1.x) + (p2.x + p0.y)) + (p1.y + p2.y);
+                    bool cond;
+                    if (chk == chk) {
+                        const float xmax = fmaxf(fmaxf(p0.x, p1.x), p2.x), xmin = fminf(fminf(p0.x, p1.x), p2.x);
+                        const float ymax = fmaxf(fmaxf(p0.y, p1.y), p2.y), ymin = fminf(fminf(p0.y, p1.y), p2.y);
+                        cond = xmax < 0 || xmin >= L || ymax < 0 || ymin >= L;
+                    } else {
+                        cond = (p0.x < 0 && p1.x < 0 && p2.x < 0) || (p0.x >= L && p1.x >= L && p2.x >= L) || (p0.y < 0 && p1.y < 0 && p2.y < 0) || (p0.y >= L && p1.y >= L && p2.y >= L);
+                    }
+                    if (valid && !cond) {
+                        xr = make_float3(roundf(p0.x), roundf(p1.x), roundf(p2.x));
+                        yr = make_float3(roundf(p0.y), roundf(p1.y), roundf(p2.y));
+                        const float det = xr.y * yr.z + xr.x * (yr.y - yr.z) - xr.z * yr.y + (xr.z - xr.y) * yr.x;      // calc_rconstant_v
+                        rconst = recip_or_inf(det);
+                        const float4 mm = calc_min_max(xr, yr, L, L);
+                        area = (mm.y - mm.x) * (mm.w - mm.z);
+                        small = area >= 1.f && area <= (float)RASTER_SMALL_MAX;                  // one chunk (ceil(area / 300) == 1) of at most 48 slots
+                        big = area > (float)RASTER_SMALL_MAX;                                    // (an empty or NaN box produces nothing)
+                        if (small) {
+                            const float cmax = fmaxf(fmaxf(fmaxf(fabsf(xr.x), fabsf(xr.y)), fmaxf(fabsf(xr.z), fabsf(yr.x))), fmaxf(fabsf(yr.y), fabsf(yr.z)));
+                            const float ext = fmaxf(fmaxf(fmaxf(xr.x, xr.y), xr.z) - fminf(fminf(xr.x, xr.y), xr.z), fmaxf(fmaxf(yr.x, yr.y), yr.z) - fminf(fminf(yr.x, yr.y), yr.z));
+                            if (cmax <= 2047.f && ext <= 64.f) {                                  // exact arithmetic from here on (finite: passed the test above)
+                                faceword |= SR_EXACT;
+                                if (det == 0.f) small = false;                                   // collinear after rounding: point_in_tri's s + t < 0 can never hold
+                            }
+                        }
+                    }
+                }
+            }
+            const unsigned mq = __ballot_sync(0xffffffffu, requeue);
+            if (mq) {
+                if (requeue) Q.item[qa + __popc(mq & lt)] = (unsigned short)(item | (1u << 13));
+                qa += __popc(mq);
+            }
+            // small triangles: queued for stage C, nothing is stored for them
+            const unsigned ms = __ballot_sync(0xffffffffu, small);
+            if (small) {
+                float* f = &Q.f[0][qr + __popc(ms & lt)];
+                f[0] = xr.x; f[SR_SLOTS] = xr.y; f[2 * SR_SLOTS] = xr.z;
+                f[3 * SR_SLOTS] = yr.x; f[4 * SR_SLOTS] = yr.y; f[5 * SR_SLOTS] = yr.z;
+                f[6 * SR_SLOTS] = p0.z; f[7 * SR_SLOTS] = p1.z; f[8 * SR_SLOTS] = p2.z;
+                f[9 * SR_SLOTS] = rconst; f[10 * SR_SLOTS] = __uint_as_float(faceword);
+            }
+            qr += __popc(ms);
+            // the rest gets records
+            if (__any_sync(0xffffffffu, big)) {
+                const int n_frag = big ? (int)ceilf(area / (float)RR_OP_SIZE_LIGHT) : 0;
+                uint32_t cid, fbase;
+                warp_alloc2(P.counters, big ? 1u : 0u, (uint32_t)n_frag, cid, fbase);
+                if (big) {
+                    if (cid + 1u > P.cap_cut) atomicOr(&P.counters[CTR_OVERFLOW], 2u);
+                    else if ((unsigned long long)fbase + (uint32_t)n_frag > (unsigned long long)P.cap_frags) atomicOr(&P.counters[CTR_OVERFLOW], 1u);
+                    else {
+                        float4* dst = P.cutdown + (size_t)cid * 3;
+                        dst[0] = make_float4(p0.x, p0.y, p0.z, 0.f);
+                        dst[1] = make_float4(p1.x, p1.y, p1.z, 0.f);
+                        dst[2] = make_float4(p2.x, p2.y, p2.z, 0.f);
+                        const float4 mm = calc_min_max(xr, yr, L, L);
+                        const int width = (int)(mm.y - mm.x), nrows = (int)(mm.w - mm.z);
+                        const int kend = walk_end(width, nrows, 1.f / (float)width, mm.z, mm.w);
+                        const uint32_t word0 = ((uint32_t)l << 8) | (uint32_t)kk;
+                        uint4* rec = reinterpret_cast<uint4*>(P.frags) + fbase;
+                        for (int a = 0; a < n_frag; a++) {
+                            rec[a] = make_uint4(word0, (uint32_t)a, cid, __float_as_uint(rconst));
+                            P.fragcnt[fbase + a] = chunk_slots(kend, a, RR_OP_SIZE_LIGHT);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- stage C
+            if (qr >= 32) {
+                qr -= 32;
+                shadow_raster_small(Q, qr + lane, true, L, P.buffer);
+                __syncwarp();
             }
         }
+        if (last) break;
     }
-    ir.flush();
+    if (qr > 0) shadow_raster_small(Q, lane, lane < qr, L, P.buffer);
+}
+
+// kernel1_realtime_shadowing (cl2.cl:5130-5246) for the fragments k_shadow_setup stored: one warp per fragment, the lanes
+// take the chunk's pixel slots 32 at a time through the closed form of the walk (walk_pixel). A chunk has at most 301
+// slots, so the work per warp is bounded and no prefix sum over slot counts is needed; config 3 stores about a thousand
+// fragments per frame, shadow-heavy scenes (a ground plane seen from a light at L = 2048) tens of thousands.
+__global__ void __launch_bounds__(256) k_raster_shadow_warp(const RasterParams P) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = min(P.counters[CTR_S_NFRAG], P.cap_frags);
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < n; f += warps) {
+        const uint32_t cnt = __ldg(P.fragcnt + f) & FRAGCNT_MASK;
+        if (cnt == 0) continue;
+        uint32_t face, distance;
+        FragGeom g;
+        load_fragment<RM_SHADOW>(P, f, face, distance, g);      // the same record for every lane: broadcast loads
+        const int width = (int)(g.mm.y - g.mm.x), k0 = RR_OP_SIZE_LIGHT * (int)distance;
+        if (width <= 0) continue;
+        const float iw = 1.f / (float)width;
+        for (uint32_t s = lane; s < cnt; s += 32u) {
+            float x, y;
+            if (!walk_pixel(k0 + (int)s, k0, width, iw, g.mm, x, y)) continue;
+            if (!point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) continue;
+            emit_sample<RM_SHADOW>(P, x, y, g.A, g.B, g.C, face, 0u);
+        }
+    }
 }
 
 // Per-cluster cube-face reach for the face-sharded shadow pass: the faces of each light that ANY point of the cluster's
@@ -1174,8 +1430,13 @@ __device__ __forceinline__ float iv_min_abs(float lo, float hi) { return (lo <= 
 __device__ __forceinline__ float iv_max_abs(float lo, float hi) { return fmaxf(fabsf(lo), fabsf(hi)); }
 
 __global__ void __launch_bounds__(128) k_cluster_faces(const ClusterBox* __restrict__ boxes, uint32_t n_clusters, const ObjLite* __restrict__ objs, uint32_t n_objs,
-                                                       const ObjFacesParams P, uint4* __restrict__ out) {
+                                                       const ObjFacesParams P, uint4* __restrict__ out, uint32_t* __restrict__ counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {                            // first launch of a shadow pass: its allocation state (no cudaMemsetAsync inside a frame, see k_frame_prologue)
+        counters[CTR_STICKY] |= counters[CTR_OVERFLOW];           // one pass's overflow stays visible until rr_sync has reported it
+        counters[CTR_OVERFLOW] = 0u;
+        counters[CTR_S_NFRAG] = 0u; counters[CTR_S_NCUT] = 0u;
+    }
     if (i >= n_clusters) return;
     const ClusterBox b = boxes[i];
     const uint32_t oid = __float_as_uint(b.lo.w);
@@ -1342,18 +1603,6 @@ __global__ void __launch_bounds__(256) k_fill_faces(const MgFillParams P) {
     }
 }
 
-// state of one shadow pass's allocation and big-fragment scan, zeroed by a kernel (not cudaMemsetAsync: see k_frame_prologue)
-__global__ void __launch_bounds__(256) k_zero_shadow_state(uint32_t* __restrict__ counters, unsigned long long* __restrict__ lookback, uint32_t tiles) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t j = i; j < tiles; j += gridDim.x * blockDim.x) lookback[j] = 0ull;
-    if (i == 0) {
-        counters[CTR_STICKY] |= counters[CTR_OVERFLOW];           // one pass's overflow stays visible until rr_sync has reported it
-        counters[CTR_OVERFLOW] = 0u;
-        counters[CTR_S_NFRAG] = 0u; counters[CTR_S_NCUT] = 0u;
-        counters[CTR_SLOTS] = 0u; counters[CTR_SCAN_TICKET] = 0u; counters[CTR_NBIG] = 0u;
-    }
-}
-
 // =====================================================================================================================
 // fills (clEnqueueFillBuffer, engine.cpp:1615-1624) — 128-bit stores, grid-stride
 // =====================================================================================================================
@@ -1482,7 +1731,7 @@ struct ShadeParams {
 __device__ __forceinline__ float4 read_tex_pre(float cx, float cy, int which, int slice, float width, const uchar4* __restrict__ atlas) {
     const float ihnum = width * (1.f / 2048);
     float tnumy = floorf((float)which * ihnum);
-    float tnumx = (float)which - tnumy / ihnum;
+    float tnumx = (float)which - ((tnumy == 0.f && ihnum > 0.f) ? tnumy : tnumy / ihnum);   // first tile row: 0 / x == 0 without the division's slow path
     cx = clampf(cx, 0.001f, width - 0.001f);
     cy = clampf(cy, 0.001f, width - 0.001f);
     int ix = (int)fmaf(tnumx, width, cx), iy = (int)fmaf(tnumy, width, cy);
@@ -1549,8 +1798,13 @@ __device__ __forceinline__ float generate_ssao(int sx, int sy, const uint32_t* _
         }
     }
     float acc = (float)cnt;
+#ifdef RR_SHADE_EXACT
     acc = div_pos(acc, 125.f);          // pow(samples*2+1, 3)
     return 1.f - (1.f - acc) / ssao_div;
+#else
+    acc = acc * (1.f / 125.f);          // the occlusion factor only scales the colour sums (colour-only arithmetic, rr_math.cuh)
+    return 1.f - div_c(1.f - acc, ssao_div);
+#endif
 }
 
 // generate_hard_occlusion, cl2.cl:2536-2701 (SMOOTH_SHADOWS)
@@ -1577,6 +1831,7 @@ __device__ __forceinline__ float hard_occlusion(float3 lpos, float3 normal, floa
             float ldp1 = ((float)__ldg(ldepth_map + (ipy + y) * L + ipx + x) * RR_INV_U32MAXF) * RR_DEPTH_FAR;
             cnd[(y + 1) * 4 + x + 1] = dpth > ldp1 + bias ? 1.f : 0.f;
         }
+#ifdef RR_SHADE_EXACT
     float shadow = 0.f;
 #pragma unroll
     for (int y = -1; y <= 1; y++)
@@ -1585,6 +1840,16 @@ __device__ __forceinline__ float hard_occlusion(float3 lpos, float3 normal, floa
             shadow += bilinear_interpolate(pp.x + 0.5f + (float)x, pp.y + 0.5f + (float)y, cnd[(y + 1) * 4 + x + 1], cnd[(y + 1) * 4 + x + 2],
                                            cnd[(y + 2) * 4 + x + 1], cnd[(y + 2) * 4 + x + 2]);
     return div_pos(shadow, 9.f);
+#else
+    // The nine 2x2 blends share their weights up to rounding (the fraction of pp + k is the fraction of pp), so their sum is a
+    // separable 4x4 kernel with weights (1 - u, 1, 1, u) per axis. The 16 compare results above are exact; only the blend of
+    // those 0 / 1 values is evaluated differently (colour-only arithmetic, rr_math.cuh).
+    const float ux = pp.x - floorf(pp.x), uy = pp.y - floorf(pp.y), bx = 1.f - ux, by = 1.f - uy;
+    float rowsum[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++) rowsum[y] = fmaf(bx, cnd[y * 4], fmaf(ux, cnd[y * 4 + 3], cnd[y * 4 + 1] + cnd[y * 4 + 2]));
+    return fmaf(by, rowsum[0], fmaf(uy, rowsum[3], rowsum[1] + rowsum[2])) * (1.f / 9.f);
+#endif
 }
 
 __device__ __forceinline__ unsigned short to_ushort_sat(float v) {
@@ -1678,7 +1943,7 @@ __device__ __forceinline__ void shade_pixel(const ShadeParams& P, const int x, c
     rseed = make_float3((rseed.x - 0.5f) * 2, (rseed.y - 0.5f) * 2, (rseed.z - 0.5f) * 2);
 
     float3 diffuse_sum = zero3, specular_sum = zero3;
-    float3 l2p = normalize3(P.cam.pos - global_position);
+    float3 l2p = normalize3_c(P.cam.pos - global_position);
     const int feature_flag = __ldg(&G->feature_flag);
     const bool is_two_sided = (feature_flag & RR_FEATURE_TWO_SIDED) > 0;
     const bool receives_dynamic_shadows = !((feature_flag & RR_FEATURE_NO_DYNAMIC_SHADOWS) > 0);
@@ -1686,7 +1951,11 @@ __device__ __forceinline__ void shade_pixel(const ShadeParams& P, const int x, c
     if (!is_front && is_two_sided) normal = -normal;
     const float ssao = P.no_ssao ? 1.f : generate_ssao(x, y, P.depth, W, H, fov, P.ssao_rad, P.ssao_div);
     normal = normalize3(normal);
+#ifdef RR_SHADE_EXACT
     const float3 lighting_normal = normalize3(normal + rseed / 100.f);
+#else
+    const float3 lighting_normal = normalize3_c(mad3(rseed, 0.01f, normal));
+#endif
     const float ambient = P.linear ? gamma_fwd(P.ambient) : P.ambient;
     const float Gdiffuse = __ldg(&G->diffuse), Gspecular = __ldg(&G->specular), Gspec_mult = __ldg(&G->spec_mult);
 
@@ -1719,13 +1988,13 @@ __device__ __forceinline__ void shade_pixel(const ShadeParams& P, const int x, c
             occlusion = fminf(occlusion, dyn);
             shnum++;
         }
-        point_to_light = normalize3(point_to_light);
+        point_to_light = normalize3_c(point_to_light);
         float light = dot3(point_to_light, lighting_normal);
         light *= occlusion;
         light = fmaxf(light, 0.f);
         float diffuse = (1.0f - ambient) * light;
         diffuse_sum = diffuse_sum + light_col * ((diffuse + ambient) * __ldg(&l->diffuse) * Gdiffuse * illumination);
-        float3 Hh = normalize3(l2p + point_to_light);
+        float3 Hh = normalize3_c(l2p + point_to_light);
         const float kS = 0.4f;
         float ndh = fmaxf(0.f, dot3(normal, Hh));
         float ndv = fmaxf(0.f, dot3(normal, l2p));
@@ -1735,13 +2004,22 @@ __device__ __forceinline__ void shade_pixel(const ShadeParams& P, const int x, c
         const float omv = 1.f - vdh, omv2 = omv * omv;
         float fresnel = F0 + (1 - F0) * (omv2 * omv2 * omv);                                  // native_powr(x, 5)
         float rough = clampf(1.f - Gspecular, 0.001f, 10.f);
-        float alpha = rational_acos(ndh);
-        float microfacet = 0.8346f * expf(-alpha * alpha / (rough * rough));
-        float sv = 2 * ndh / vdh;
+        float alpha = rational_acos_c(ndh);
+        float microfacet = 0.8346f * exp_c(div_c(-alpha * alpha, rough * rough));
+        const float sv_num = 2 * ndh;
+#ifdef RR_SHADE_EXACT
+        float sv = (sv_num == 0.f && vdh > 0.f) ? sv_num : sv_num / vdh;                       // 0 / positive == 0 (0 / 0 stays NaN, q17)
+#else
+        float sv = div_c(sv_num, vdh);
+#endif
         float c1 = sv * ndv, c2 = sv * ndl;
         float geometric = fminf(fminf(1.f, c1), c2);
         const float spec_num = fresnel * microfacet * geometric, spec_den = RR_PI_F * ndv;
+#ifdef RR_SHADE_EXACT
         float spec = (spec_num == 0.f && spec_den > 0.f) ? spec_num : spec_num / spec_den;   // 0 / positive == 0 without the division's slow path
+#else
+        float spec = div_c(spec_num, spec_den);
+#endif
         specular_sum = specular_sum + light_col * (spec * kS * illumination) * Gspec_mult;
         specular_sum = make_float3(fmaxf(specular_sum.x, 0.f), fmaxf(specular_sum.y, 0.f), fmaxf(specular_sum.z, 0.f));
         specular_sum = specular_sum * occlusion;
@@ -1752,7 +2030,7 @@ __device__ __forceinline__ void shade_pixel(const ShadeParams& P, const int x, c
     float3 colclamp = make_float3(col.x, col.y, col.z) + zero3 + specular_sum * rsc;
     float3 fc = make_float3(fmaf(colclamp.x, diffuse_sum.x, specular_sum.x * (1.f - rsc)), fmaf(colclamp.y, diffuse_sum.y, specular_sum.y * (1.f - rsc)),
                             fmaf(colclamp.z, diffuse_sum.z, specular_sum.z * (1.f - rsc)));
-    if (P.linear) fc = make_float3(gamma_inv(fc.x), gamma_inv(fc.y), gamma_inv(fc.z));
+    if (P.linear) fc = make_float3(gamma_inv_c(fc.x), gamma_inv_c(fc.y), gamma_inv_c(fc.z));
     P.rgba8[px] = make_uchar4(quant8(clampf(fc.x, 0.f, 1.f)), quant8(clampf(fc.y, 0.f, 1.f)), quant8(clampf(fc.z, 0.f, 1.f)), quant8(col.w));
 
     // encode_normal + float_to_short, cl2.cl:5588-5628

@@ -102,8 +102,12 @@ __device__ __forceinline__ float4 back_quat(float4 quat) {          // the norma
 }
 
 // cl2.cl:408-411
+// 1.0f / d for a d that is often exactly +-0 (rounded vertices of a sub-pixel triangle are collinear): 1 / +-0 == +-inf, and
+// skipping the division avoids the IEEE slow path a zero divisor takes (bit-identical result)
+__device__ __forceinline__ float recip_or_inf(float d) { return d == 0.f ? __int_as_float(0x7f800000u | (__float_as_uint(d) & 0x80000000u)) : 1.0f / d; }
+
 __device__ __forceinline__ float calc_rconstant_v(float3 x, float3 y) {
-    return 1.0f / (x.y * y.z + x.x * (y.y - y.z) - x.z * y.y + (x.z - x.y) * y.x);
+    return recip_or_inf(x.y * y.z + x.x * (y.y - y.z) - x.z * y.y + (x.z - x.y) * y.x);
 }
 
 // cl2.cl:413-418
@@ -171,6 +175,38 @@ __device__ __forceinline__ int clip_near(float3 q0, float3 q1, float3 q2, float 
     return 1;
 }
 
+// clip_near for callers that take the (at most two) output triangles one at a time: returns how many triangles the clip
+// produces and writes triangle number `which` (0 or 1) to a0..a2 when it exists. Same arithmetic as clip_near.
+__device__ __forceinline__ int clip_near_one(float3 q0, float3 q1, float3 q2, float icut, bool which, float3& a0, float3& a1, float3& a2) {
+    const bool h0 = q0.z <= icut || q0.z > RR_DEPTH_FAR, h1 = q1.z <= icut || q1.z > RR_DEPTH_FAR, h2 = q2.z <= icut || q2.z > RR_DEPTH_FAR;
+    if (!(h0 || h1 || h2)) { a0 = q0; a1 = q1; a2 = q2; return 1; }
+    const int n_behind = (int)h0 + (int)h1 + (int)h2;
+    if (n_behind > 2) return 0;
+    int g1, g2, g3;
+    if (n_behind == 1) {
+        const int id = h0 ? 0 : (h1 ? 1 : 2);
+        g1 = id;
+        g2 = (id + 1) >= 3 ? id - 2 : id + 1;
+        g3 = (id + 2) >= 3 ? id - 1 : id + 2;
+    } else {
+        g2 = h0 ? 0 : 1;
+        g3 = h2 ? 2 : 1;
+        g1 = !h0 ? 0 : (!h1 ? 1 : 2);
+    }
+    const float3 P1 = sel3(g1, q0, q1, q2), P2 = sel3(g2, q0, q1, q2), P3 = sel3(g3, q0, q1, q2);
+    const float3 p1 = P2 + ((icut - P2.z) * (P1 - P2)) / (P1.z - P2.z);
+    const float3 p2 = P3 + ((icut - P3.z) * (P1 - P3)) / (P1.z - P3.z);
+    if (n_behind == 1) {
+        if (!which) { a0 = p1; a1 = P2; a2 = P3; }
+        else { a0 = p1; a1 = P3; a2 = p2; }
+        return 2;
+    }
+    a0 = (0 == g2) ? p1 : ((0 == g3) ? p2 : P1);
+    a1 = (1 == g2) ? p1 : ((1 == g3) ? p2 : P1);
+    a2 = (2 == g2) ? p1 : ((2 == g3) ? p2 : P1);
+    return 1;
+}
+
 // cl2.cl:4798-4807
 __device__ __forceinline__ bool point_in_tri(float px, float py, float p0x, float p0y, float p1x, float p1y, float p2x, float p2y) {
     float A = 0.5f * (-p1y * p2x + p0y * (-p1x + p2x) + p0x * (p1y - p2y) + p1x * p2y);
@@ -205,7 +241,35 @@ __device__ __forceinline__ uint32_t rand_xorshift(uint32_t s) { s ^= (s << 13); 
 __device__ __forceinline__ float rational_acos(float x) {
     const float a = -0.939115566365855f, b = 0.9217841528914573f, c = -1.2845906244690837f, d = 0.295624144969963174f;
     const float x2 = x * x;
-    return RR_PI_F / 2.f + (a * x + b * x * x * x) / (1.f + c * x * x + d * (x2 * x2));      // pow(x, 4)
+    const float num = a * x + b * x * x * x, den = 1.f + c * x * x + d * (x2 * x2);      // pow(x, 4)
+    return RR_PI_F / 2.f + ((num == 0.f && den > 0.f) ? num : num / den);                // +-0 / positive == +-0 without the slow path
+}
+
+// ---- colour-only arithmetic ------------------------------------------------------------------------------------------
+// kernel3's lighting sums feed nothing but the RGBA8 colour, which is compared at +-1 LSB (the shipped reference itself builds
+// them with -cl-fast-relaxed-math, FP_CONTRACT ON and native_* / fast_* calls). Everything that feeds a DISCRETE decision —
+// texel and shadow-texel addresses, mip level, depth compares, the shadow bias, the illumination cut-off, the stored normal —
+// keeps the pinned IEEE arithmetic; the smooth terms below use the SFU approximations (<= 2 ulp) and fused multiply-adds.
+// Define RR_SHADE_EXACT to build the fully pinned variant for A/B runs.
+#ifdef RR_SHADE_EXACT
+__device__ __forceinline__ float3 normalize3_c(float3 a) { return normalize3(a); }
+__device__ __forceinline__ float div_c(float a, float b) { return a / b; }
+__device__ __forceinline__ float exp_c(float x) { return expf(x); }
+__device__ __forceinline__ float sqrt_c(float x) { return sqrtf(x); }
+#else
+__device__ __forceinline__ float3 normalize3_c(float3 a) { const float r = rsqrtf(fmaf(a.x, a.x, fmaf(a.y, a.y, a.z * a.z))); return make_float3(a.x * r, a.y * r, a.z * r); }   // 0 -> NaN like 0 / 0
+__device__ __forceinline__ float div_c(float a, float b) { return __fdividef(a, b); }       // 0 / 0 -> NaN, x / 0 -> inf (q17 semantics kept)
+__device__ __forceinline__ float exp_c(float x) { return __expf(x); }
+__device__ __forceinline__ float sqrt_c(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
+__device__ __forceinline__ float rational_acos_c(float x) {           // rational_acos for the specular lobe
+    const float a = -0.939115566365855f, b = 0.9217841528914573f, c = -1.2845906244690837f, d = 0.295624144969963174f;
+    const float x2 = x * x;
+    return RR_PI_F / 2.f + div_c(a * x + b * x * x * x, 1.f + c * x * x + d * (x2 * x2));
+}
+__device__ __forceinline__ float gamma_inv_c(float c) {
+    const float S1 = sqrt_c(c), S2 = sqrt_c(S1), S3 = sqrt_c(S2);
+    return 0.585122381f * S1 + 0.783140355f * S2 - 0.368262736f * S3;
 }
 
 // cl2.cl:5372-5384
