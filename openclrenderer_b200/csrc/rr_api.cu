@@ -140,7 +140,7 @@ struct rr_ctx {
     uchar4* d_post = nullptr;                    // second colour target of the post passes (rr_post_pseudo_aa)
     uint32_t* d_shade_list = nullptr;            // compacted covered pixels
     uint2* d_samples = nullptr;                  // covered samples of inline-rasterised triangles (pixel, depth)
-    uint4* d_sample_desc = nullptr;              // {first sample, count, fragment index}
+    uint32_t* d_sample_frag = nullptr;           // ... and the fragment index of each sample
     uint32_t cap_samples = 0;
     // raster storage
     uint32_t* d_frags = nullptr;
@@ -151,18 +151,15 @@ struct rr_ctx {
     unsigned long long* d_lookback = nullptr;
     uint32_t lookback_blocks = 0;
     uint32_t* d_fragcnt = nullptr;               // per-fragment pixel-slot counts
-    uint32_t *d_biglist = nullptr, *d_bigslot = nullptr;   // compacted big fragments + exclusive prefix of their slots (k_scan_big)
-    unsigned long long* d_scan_lookback = nullptr;
-    uint32_t scan_tiles = 0;
+    uint32_t *d_worklist = nullptr, *d_extra = nullptr;    // fragments kernel1 / kernel2 still have to walk (k_setup_main -> k_raster_warp)
     uint32_t* h_counters = nullptr;      // pinned (main counters, then shadow counters)
     // second raster workspace + stream: the shadow passes of a frame run concurrently with the main view's setup / depth /
     // id kernels (they only meet at shading). The reference shares g_tid_buf / g_cut_tri_mem between them and serialises.
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_shadow_done = nullptr;
     bool shadow_pending = false;
-    uint32_t *d_sfrags = nullptr, *d_sfragcnt = nullptr, *d_sbiglist = nullptr, *d_sbigslot = nullptr, *d_scounters = nullptr;
+    uint32_t *d_sfrags = nullptr, *d_sfragcnt = nullptr, *d_scounters = nullptr;
     float4* d_scutdown = nullptr;
-    unsigned long long* d_sscan_lookback = nullptr;
     // host mirror of the descriptor array (what rr_frame_e2e uploads every frame, object_context::flush_locations)
     rr_obj_desc* h_objs_pinned = nullptr;
     // Page-locked staging for every asynchronous host-to-device upload on the main stream (patches, descriptor writes, the
@@ -279,24 +276,10 @@ int ensure_objlite(rr_ctx* c) {
     return RR_OK;
 }
 
-// compact the big fragments of the list whose length is counters[n_index] and prefix-sum their slot counts
-int scan_big(rr_ctx* c, cudaStream_t st, uint32_t* counters, const uint32_t* fragcnt, uint32_t* biglist, uint32_t* bigslot,
-             unsigned long long* lookback, int n_index, uint32_t cap, bool zeroed = false) {
-    if (!zeroed) {                                                                         // the main pass has k_frame_prologue do this
-        CU(cudaMemsetAsync(counters + CTR_SLOTS, 0, 3 * 4, st));                           // CTR_SLOTS, CTR_SCAN_TICKET, CTR_NBIG
-        CU(cudaMemsetAsync(lookback, 0, (size_t)c->scan_tiles * 8, st));
-    }
-    k_scan_big<<<grid_for(c, 2), SCAN_THREADS, 0, st>>>(fragcnt, counters + n_index, cap, biglist, bigslot, counters, lookback);
-    c->launches++;
-    CU(cudaGetLastError());
-    return RR_OK;
-}
-
 template <int MODE>
 int raster(rr_ctx* c, cudaStream_t st, const RasterParams& rp) {
-    k_raster_small<MODE><<<grid_for(c, 8), 256, 0, st>>>(rp);
-    k_raster_big<MODE><<<grid_for(c, 4), RASTER_THREADS, 0, st>>>(rp);
-    c->launches += 2;
+    k_raster_warp<MODE><<<grid_for(c, 4), 256, 0, st>>>(rp);
+    c->launches++;
     CU(cudaGetLastError());
     return RR_OK;
 }
@@ -426,9 +409,8 @@ static int preload_kernels() {
     const void* fns[] = {
         (const void*)k_repack, (const void*)k_objlite, (const void*)k_lightlite, (const void*)k_obj_rows, (const void*)k_cluster_bounds,
         (const void*)k_frame_prologue, (const void*)k_setup_main<false>, (const void*)k_setup_main<true>,
-        (const void*)k_raster_small<RM_DEPTH>, (const void*)k_raster_small<RM_IDS>, (const void*)k_raster_small<RM_SHADOW>,
-        (const void*)k_raster_big<RM_DEPTH>, (const void*)k_raster_big<RM_IDS>, (const void*)k_raster_big<RM_SHADOW>,
-        (const void*)k_ids_list, (const void*)k_scan_big, (const void*)k_shadow_setup, (const void*)k_cluster_faces,
+        (const void*)k_raster_warp<RM_DEPTH>, (const void*)k_raster_warp<RM_IDS>,
+        (const void*)k_ids_list, (const void*)k_shadow_setup, (const void*)k_cluster_faces,
         (const void*)k_signal_flag, (const void*)k_signal_flags, (const void*)k_wait_flags, (const void*)k_push_faces, (const void*)k_fill_faces,
         (const void*)k_raster_shadow_warp, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip,
         (const void*)k_shade_pre, (const void*)k_shade_pre4, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_copy_u32,
@@ -507,12 +489,10 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaMalloc((void**)&c->d_samples, (size_t)c->cap_samples * 8) != cudaSuccess) return bail("sample list");
     c->cap_frags = cfg->max_fragments ? cfg->max_fragments : (16u << 20);
     if (cudaMalloc((void**)&c->d_frags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("fragment buffer");
-    if (cudaMalloc((void**)&c->d_sample_desc, (size_t)c->cap_frags * 16) != cudaSuccess) return bail("sample descriptors");
+    if (cudaMalloc((void**)&c->d_sample_frag, (size_t)c->cap_samples * 4) != cudaSuccess) return bail("sample list");
     if (cudaMalloc((void**)&c->d_fragcnt, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("slot counts");
-    if (cudaMalloc((void**)&c->d_biglist, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("big list");
-    if (cudaMalloc((void**)&c->d_bigslot, (size_t)c->cap_frags * RR_FRAG_WORDS * 4 / RR_SFRAG_WORDS + 16) != cudaSuccess) return bail("big slots");
-    c->scan_tiles = (uint32_t)(((uint64_t)c->cap_frags * RR_FRAG_WORDS / RR_SFRAG_WORDS + SCAN_TILE - 1) / SCAN_TILE) + 1;
-    if (cudaMalloc((void**)&c->d_scan_lookback, (size_t)c->scan_tiles * 8) != cudaSuccess) return bail("scan descriptors");
+    if (cudaMalloc((void**)&c->d_worklist, (size_t)c->cap_frags * 4 + 16) != cudaSuccess) return bail("work list");
+    if (cudaMalloc((void**)&c->d_extra, (size_t)c->cap_frags * 4 + 16) != cudaSuccess) return bail("extra list");
     if (cudaMalloc((void**)&c->d_counters, CTR_COUNT * 4) != cudaSuccess) return bail("counters");
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail("stream2");
     if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail("stream3");
@@ -524,9 +504,6 @@ rr_ctx* rr_create(const rr_config* cfg) {
         const size_t srec = (size_t)c->cap_frags * RR_FRAG_WORDS / RR_SFRAG_WORDS;     // shadow records are 4 words
         if (cudaMalloc((void**)&c->d_sfrags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("shadow fragment buffer");
         if (cudaMalloc((void**)&c->d_sfragcnt, srec * 4 + 16) != cudaSuccess) return bail("shadow slot counts");
-        if (cudaMalloc((void**)&c->d_sbiglist, srec * 4 + 16) != cudaSuccess) return bail("shadow big list");
-        if (cudaMalloc((void**)&c->d_sbigslot, srec * 4 + 16) != cudaSuccess) return bail("shadow big slots");
-        if (cudaMalloc((void**)&c->d_sscan_lookback, (size_t)c->scan_tiles * 8) != cudaSuccess) return bail("shadow scan descriptors");
         if (cudaMalloc((void**)&c->d_scounters, CTR_COUNT * 4) != cudaSuccess) return bail("shadow counters");
         cudaMemsetAsync(c->d_scounters, 0, CTR_COUNT * 4, c->stream);
     }
@@ -559,8 +536,8 @@ void rr_destroy(rr_ctx* c) {
     if (c->ev_draw_done) cudaEventDestroy(c->ev_draw_done);
     for (int i = 0; i < RR_RING_MAX; i++) if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
     if (c->stream3) cudaStreamDestroy(c->stream3);
-    cudaFree(c->d_sfrags); cudaFree(c->d_sfragcnt); cudaFree(c->d_sbiglist); cudaFree(c->d_sbigslot); cudaFree(c->d_scounters);
-    cudaFree(c->d_scutdown); cudaFree(c->d_sscan_lookback);
+    cudaFree(c->d_sfrags); cudaFree(c->d_sfragcnt); cudaFree(c->d_scounters);
+    cudaFree(c->d_scutdown);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_shadow_done) cudaEventDestroy(c->ev_shadow_done);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -574,9 +551,9 @@ void rr_destroy(rr_ctx* c) {
     if (!c->ext_shadow_static) cudaFree(c->d_shadow_static);
     for (int i = 0; i < 2; i++) { cudaFree(c->d_depth[i]); cudaFree(c->d_ids[i]); }
     if (!c->ext_rgba8) cudaFree(c->d_rgba8);
-    cudaFree(c->d_fragcnt); cudaFree(c->d_scan_lookback); cudaFree(c->d_biglist); cudaFree(c->d_bigslot);
+    cudaFree(c->d_fragcnt); cudaFree(c->d_worklist); cudaFree(c->d_extra);
     cudaFree(c->d_post);
-    cudaFree(c->d_normals); cudaFree(c->d_shade_list); cudaFree(c->d_samples); cudaFree(c->d_sample_desc); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
+    cudaFree(c->d_normals); cudaFree(c->d_shade_list); cudaFree(c->d_samples); cudaFree(c->d_sample_frag); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
     if (c->arena.base) cudaFreeHost(c->arena.base);
@@ -941,7 +918,7 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         k_shadow_setup<<<(c->n_tris + 127) / 128, 128, 0, st>>>(sp);
         c->launches++;
         dp.frags = c->d_sfrags; dp.cutdown = c->d_scutdown; dp.fragcnt = c->d_sfragcnt; dp.counters = c->d_scounters; dp.cap_frags = sp.cap_frags;
-        dp.biglist = nullptr; dp.bigslot = nullptr;
+        dp.worklist = nullptr; dp.extra = nullptr;
         dp.n_index = CTR_S_NFRAG;
         dp.depth = buffer; dp.ids = nullptr; dp.width = (float)c->L; dp.height = (float)c->L; dp.W = c->L;
         dp.row_lo = 0; dp.row_hi = c->L; dp.rowmask = nullptr; dp.rowbit = 0;
@@ -1049,7 +1026,6 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     sp.rowpfx = c->d_rowpfx; sp.cull_rows = c->banded ? 1 : 0;
     sp.cluster_vis = nullptr; sp.active = nullptr; sp.skipped_before = nullptr;
     const bool cull = c->n_objs > 0 && (c->cluster_cull > 0 || (c->cluster_cull == 0 && c->banded));
-    const bool scan_zeroed = true;
     {   // one launch: zero the scan state and, when culling, classify the clusters (off-screen geometry; rows rasterised elsewhere)
         // and compact the setup blocks. No cudaMemsetAsync anywhere in the frame: memsets may be placed on the copy engine,
         // where they wait behind the previous frame's read-back DMA.
@@ -1059,23 +1035,21 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
         pp.cv.rowpfx = c->d_rowpfx; pp.cv.row_lo = row0; pp.cv.row_hi = row1;
         pp.vis = c->d_cluster_vis; pp.n_tris = c->n_tris; pp.n_blocks = c->lookback_blocks;
         pp.active = c->d_active; pp.skipped_before = c->d_skipped; pp.counters = c->d_counters; pp.lookback = c->d_lookback;
-        pp.scan_lookback = c->d_scan_lookback; pp.scan_tiles = c->scan_tiles;
         pp.cull = cull ? 1 : 0;
         k_frame_prologue<<<std::max(1u, (c->n_clusters + PROLOGUE_THREADS - 1) / PROLOGUE_THREADS), PROLOGUE_THREADS, 0, c->stream>>>(pp);
         c->launches++;
         if (cull) { sp.cluster_vis = c->d_cluster_vis; sp.active = c->d_active; sp.skipped_before = c->d_skipped; }
     }
-    sp.sl.samples = c->d_samples; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
-    sp.sl.desc = c->d_sample_desc; sp.sl.cap_desc = c->cap_frags; sp.sl.desc_count = c->d_counters + CTR_NDESC; sp.sl.fragcnt = c->d_fragcnt;
+    sp.sl.samples = c->d_samples; sp.sl.frag = c->d_sample_frag; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
+    sp.sl.extra = c->d_extra; sp.sl.extra_count = c->d_counters + CTR_NEXTRA; sp.worklist = c->d_worklist;
     if (c->banded) k_setup_main<true><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     else k_setup_main<false><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     c->launches++;
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
     // kernel1 / kernel2
-    if ((r = scan_big(c, c->stream, c->d_counters, c->d_fragcnt, c->d_biglist, c->d_bigslot, c->d_scan_lookback, CTR_NFRAG, c->cap_frags, scan_zeroed))) return r;
     RasterParams rp;
     rp.frags = c->d_frags; rp.cutdown = c->d_cutdown; rp.fragcnt = c->d_fragcnt; rp.counters = c->d_counters; rp.cap_frags = c->cap_frags;
-    rp.biglist = c->d_biglist; rp.bigslot = c->d_bigslot;
+    rp.worklist = c->d_worklist; rp.extra = c->d_extra;
     rp.n_index = CTR_NFRAG;
     rp.depth = c->d_depth[c->cur]; rp.ids = c->d_ids[c->cur];
     rp.width = (float)c->W; rp.height = (float)c->H; rp.W = c->W;

@@ -15,9 +15,9 @@ enum {
     CTR_S_NFRAG = 4,   // shadow pass allocation counter, one 64-bit word at [4..5]: (projected triangles << 32) | fragments,
     CTR_S_NCUT = 5,    //   i.e. word 4 = fragment count, word 5 = projected-triangle count (little endian)
     CTR_S_TOTAL = 6,   // running total of shadow fragments in this frame (statistics)
-    CTR_SLOTS = 7,     // total pixel slots of the fragment list last scanned (k_scan_slots)
-    CTR_SCAN_TICKET = 8,
-    CTR_NBIG = 9,      // number of big fragments (more than RASTER_SMALL_MAX slots) in the list last scanned
+    CTR_NEXTRA = 7,    // fragments rasterised inline whose samples did not fit the sample list: kernel2 walks them (k_raster_warp<RM_IDS>)
+    CTR_UNUSED8 = 8,
+    CTR_NWORK = 9,     // fragments k_setup_main did not rasterise inline: the work list of k_raster_warp
     CTR_NSHADE = 10,   // covered pixels in the shading list
     CTR_NSAMPLES = 11, // entries reserved in the sample list (inline-rasterised triangles)
     CTR_NDESC = 12,    // descriptors in the sample list
@@ -287,125 +287,190 @@ __device__ __forceinline__ int clip_project(float3 q0, float3 q1, float3 q2, flo
 __device__ __forceinline__ void subtri_clear(SubTri& s) { s.keep = false; s.n_frag = 0; s.box = 0; s.rconst = 0.f; }
 
 // ---- inline rasterisation of a small single-chunk triangle from the setup kernels --------------------------------------
-// A triangle whose whole walk is one chunk of at most RASTER_SMALL_MAX slots is rasterised by the thread that set it up:
-// same frag_geom / scan_chunk / depth arithmetic as the raster kernels, but no trip through the record and
-// projected-triangle buffers and no second kernel. `target` is the depth buffer (or cubemap face) it lands in.
+// A triangle whose whole walk is one chunk of at most RASTER_SMALL_MAX slots is rasterised by the warp that set it up
+// (kernel1's work for it): no trip through the record and projected-triangle buffers and no second kernel.
 #define RASTER_SMALL_MAX 48
 #define FRAGCNT_DEPTH_DONE 0x80000000u      // flag in the per-fragment slot count: depth already written inline
-#define FRAGCNT_IDS_LISTED 0x40000000u      // ... and its covered samples are in the sample list (k_ids_list resolves its ids)
 #define FRAGCNT_MASK 0x3FFFFFFFu
 
 __device__ __forceinline__ bool inline_candidate(const SubTri& s) { return s.keep && s.n_frag == 1 && s.box <= RASTER_SMALL_MAX; }
 
-// Per-warp queue in shared memory that compacts the small triangles of a warp (warp ballot + prefix) so that the walk is
-// always executed by 32 busy lanes: roughly half of a warp's triangles are culled and the survivors need different
-// numbers of steps, so rasterising them in place would leave most lanes idle.
-// REC (main view only): the covered samples (pixel, depth) of every triangle are appended to a sample list with one
-// descriptor {first sample, count, fragment index} per triangle, so that kernel2's work for these triangles is a
-// stream over that list (k_ids_list) instead of a second walk. Space is reserved per drain with one warp-aggregated
-// atomicAdd (box-many entries per triangle); if the list is full the triangle is simply left to the re-walk path.
+// Exactness test shared by the inline rasterisers: rounded vertex coordinates (integers) for which every product and partial
+// sum of point_in_tri (cl2.cl:4798-4807) and of calc_rconstant_v (cl2.cl:408-411) is an integer below 2^24, hence exact in
+// fp32 whatever the evaluation order: max|x| * max|y| + 64 (max|x| + max|y|) < 2^24 with extents of at most 64.
+// (Always true at 4K and in a 2048^2 cube face; at 8K only towards the top-left of the screen.)
+__device__ __forceinline__ bool tri_exact_arith(float3 xr, float3 yr) {
+    const float mx = fmaxf(fmaxf(fabsf(xr.x), fabsf(xr.y)), fabsf(xr.z)), my = fmaxf(fmaxf(fabsf(yr.x), fabsf(yr.y)), fabsf(yr.z));
+    const float ext = fmaxf(fmaxf(fmaxf(xr.x, xr.y), xr.z) - fminf(fminf(xr.x, xr.y), xr.z), fmaxf(fmaxf(yr.x, yr.y), yr.z) - fminf(fminf(yr.x, yr.y), yr.z));
+    const float chk = ((xr.x + xr.y) + (xr.z + yr.x)) + (yr.y + yr.z);           // NaN / inf - inf guard (fmaxf skips NaNs)
+    return chk == chk && ext <= 64.f && mx * my + 64.f * (mx + my) < 16000000.f;
+}
+
+// Per-warp queue in shared memory that compacts the small triangles of a warp (warp ballot + prefix) so that they are
+// rasterised by 32 busy lanes: roughly half of a warp's triangles are culled and the survivors need different numbers of
+// steps, so rasterising them in place would leave most lanes idle.
+// The covered samples (pixel, depth, fragment index) of every triangle are appended to a sample list so that kernel2's work
+// for these triangles is a stream over that list (k_ids_list) instead of a second walk. Coverage is determined first (a bit
+// mask per triangle), so exactly popc(mask) entries are reserved, with one warp-aggregated atomicAdd per drain; a triangle
+// whose samples do not fit goes to the `extra` list and is walked again by k_raster_warp<RM_IDS>.
 #define IQ_SLOTS 64
-#define IQ_FIELDS 12            // p0.xyz p1.xyz p2.xyz rconst target-index fragment-index
+#define IQ_FIELDS 12            // rounded x of the 3 vertices, rounded y, camera z, rconst, fragment index, flags
+#define IQ_EXACT 1u
 struct InlineQueue { float f[IQ_FIELDS][IQ_SLOTS]; };
 
-struct SampleList { uint2* samples; uint32_t cap; uint32_t* count; uint4* desc; uint32_t cap_desc; uint32_t* desc_count; uint32_t* fragcnt; };
+struct SampleList { uint2* samples; uint32_t* frag; uint32_t cap; uint32_t* count;      // (pixel, depth), fragment index
+                    uint32_t* extra; uint32_t* extra_count; };                              // fragments whose samples did not fit
 
-template <bool REC, bool MASKED = false>
+struct RowFilter { int lo, hi; const uint8_t* mask; };     // rows rasterised here: [lo, hi), and bit 0 of mask[y] when mask != nullptr
+__device__ __forceinline__ bool row_wanted(const RowFilter& rf, int y) { return y >= rf.lo && y < rf.hi && (!rf.mask || (rf.mask[y] & 1)); }
+
+// The literal path of the inline rasteriser (triangles that fail tri_exact_arith, have a lagging row counter or a tight box of
+// more than 32 pixels): the reference's walk (scan_chunk) with point_in_tri, in two passes over the same state machine —
+// first the coverage as a bit per walk step (a chunk of at most 48 slots takes at most 49 steps), then the emission.
+__device__ __noinline__ unsigned long long inline_literal_mask(float3 xr, float3 yr, float width, float height, int op, RowFilter rf) {
+    const float4 mm = calc_min_max(xr, yr, width, height);
+    unsigned long long mask = 0ull, bit = 1ull;
+    scan_chunk(mm, op, 0u, [&](float x, float y) {
+        if (row_wanted(rf, (int)y) && point_in_tri(x, y, xr.x, yr.x, xr.y, yr.y, xr.z, yr.z)) mask |= bit;
+        bit <<= 1;
+    });
+    return mask;
+}
+__device__ __noinline__ void inline_literal_emit(float3 xr, float3 yr, float A, float B, float C, float width, float height, int op, unsigned long long mask,
+                                                 uint32_t* __restrict__ target, uint2* __restrict__ samples, uint32_t* __restrict__ sfrag, uint32_t fidx) {
+    const float4 mm = calc_min_max(xr, yr, width, height);
+    uint32_t n = 0;
+    scan_chunk(mm, op, 0u, [&](float x, float y) {
+        if (mask & 1ull) {
+            const float fd = fmaf(A, x, fmaf(B, y, C));
+            const uint32_t d = sat_u32(RR_U32MAXF / fd);
+            const uint32_t px = (uint32_t)((int)(y * width) + (int)x);
+            atomicMin(target + px, d);
+            if (samples) { samples[n] = make_uint2(px, d); sfrag[n] = fidx; n++; }
+        }
+        mask >>= 1;
+    });
+}
+
+template <bool MASKED>
 struct InlineRaster {
     InlineQueue* q; int count;  // count is warp-uniform
-    int op; float width, height; uint32_t* base; size_t face_stride; int row_lo, row_hi;
-    const uint8_t* rowmask;     // interleaved sort-first ownership: bit 0 = row rasterised here (nullptr: every row of [row_lo, row_hi))
+    int op; float width, height; uint32_t* target; RowFilter rf;
     SampleList sl;
 
-    // executed by all 32 lanes; lanes with !valid only take part in the warp collectives
+    // executed by all 32 lanes; lanes with !valid only take part in the warp collectives.
+    // Fast path: see shadow_raster_small (k_shadow_setup's stage C) — exact integer edge functions stepped over the vertices' own
+    // bounding box; here the covered samples are also recorded.
     __device__ __forceinline__ void run(int slot, bool valid) const {
         const int lane = threadIdx.x & 31;
         const float* f = &q->f[0][valid ? slot : 0];
-        FragGeom g;
-        uint32_t* target = base;
-        uint32_t fidx = 0;
-        int need = 0;
-        if (valid) {
-            g = frag_geom(make_float3(f[0], f[IQ_SLOTS], f[2 * IQ_SLOTS]), make_float3(f[3 * IQ_SLOTS], f[4 * IQ_SLOTS], f[5 * IQ_SLOTS]),
-                          make_float3(f[6 * IQ_SLOTS], f[7 * IQ_SLOTS], f[8 * IQ_SLOTS]), f[9 * IQ_SLOTS], width, height);
-            target = base + (size_t)__float_as_uint(f[10 * IQ_SLOTS]) * face_stride;
-            fidx = __float_as_uint(f[11 * IQ_SLOTS]);
-            need = (int)((g.mm.y - g.mm.x) * (g.mm.w - g.mm.z));
+        const float3 xr = make_float3(f[0], f[IQ_SLOTS], f[2 * IQ_SLOTS]), yr = make_float3(f[3 * IQ_SLOTS], f[4 * IQ_SLOTS], f[5 * IQ_SLOTS]);
+        const uint32_t fidx = __float_as_uint(f[10 * IQ_SLOTS]), flags = __float_as_uint(f[11 * IQ_SLOTS]);
+        const float4 mm = calc_min_max(xr, yr, width, height);
+        const float x0 = fmaxf(mm.x, fminf(fminf(xr.x, xr.y), xr.z)), y0 = fmaxf(mm.z, fminf(fminf(yr.x, yr.y), yr.z));
+        const int wt = (int)(mm.y - x0), ht = (int)(mm.w - y0), rows = (int)(mm.w - mm.z);
+        bool fast = valid && (flags & IQ_EXACT) && wt * ht <= 32;
+        if (fast && (float)(rows - 1) > mm.z) {             // a box at the very top of the screen: look for a lagging row (rr_math.cuh walk_row)
+            const int bw = (int)(mm.y - mm.x);
+            const float iw = 1.f / (float)bw;
+            for (int r = 1; r < rows; r++) fast = fast && walk_row(r * bw, iw, mm.z) == mm.z + (float)r;
         }
-        uint32_t first = 0;
-        bool rec = false;
-        if (REC) {              // reserve `need` sample entries per lane with one atomic per warp
-            int inc = need;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-            const int total = __shfl_sync(0xffffffffu, inc, 31);
-            uint32_t b0 = 0;
-            if (lane == 31 && total) b0 = atomicAdd(sl.count, (uint32_t)total);
-            b0 = __shfl_sync(0xffffffffu, b0, 31);
-            first = b0 + (uint32_t)(inc - need);
-            rec = valid && ((unsigned long long)b0 + (unsigned long long)total <= (unsigned long long)sl.cap);
-        }
-        uint32_t n = 0;
-        if (valid) {
-            const float w = width;
-            const int rlo = row_lo, rhi = row_hi;
-            const uint8_t* rm = rowmask;
-            scan_chunk(g.mm, op, 0u, [&](float x, float y) {
-                if ((int)y < rlo || (int)y >= rhi) return;
-                if (MASKED && rm && !(rm[(int)y] & 1)) return;
-                if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) {
-                    const float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
-                    const uint32_t d = sat_u32(RR_U32MAXF / fd);
-                    const uint32_t px = (uint32_t)((int)(y * w) + (int)x);
-                    atomicMin(target + px, d);
-                    if (REC && rec) sl.samples[first + n++] = make_uint2(px, d);
-                }
-            });
-        }
-        if (REC) {              // one descriptor per recorded triangle
-            const unsigned m = __ballot_sync(0xffffffffu, rec);
-            if (m) {
-                uint32_t d0 = 0;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) d0 = atomicAdd(sl.desc_count, (uint32_t)__popc(m));
-                d0 = __shfl_sync(0xffffffffu, d0, leader);
-                if (rec) {
-                    const uint32_t at = d0 + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                    if (at < sl.cap_desc) {
-                        sl.desc[at] = make_uint4(first, n, fidx, 0u);
-                        sl.fragcnt[fidx] |= FRAGCNT_IDS_LISTED;      // only this lane touches fragcnt[fidx] now (the block synchronised after the record phase)
+        uint32_t mask = 0u;
+        unsigned long long lmask = 0ull;
+        if (fast) {
+            if (wt > 0 && ht > 0) {
+                const float Ah = 0.5f * (-yr.y * xr.z + yr.x * (-xr.y + xr.z) + xr.x * (yr.y - yr.z) + xr.y * yr.z);
+                const float sign = Ah < 0 ? -1.f : 1.f;
+                const float lim = 2.0001f * Ah * sign;
+                const float as = (yr.z - yr.x) * sign, bs = (xr.x - xr.z) * sign, at = (yr.x - yr.y) * sign, bt = (xr.y - xr.x) * sign;
+                float s_row = (yr.x * xr.z - xr.x * yr.z) * sign + as * x0 + bs * y0;
+                float t_row = (xr.x * yr.y - yr.x * xr.y) * sign + at * x0 + bt * y0;
+                uint32_t bit = 1u;
+                for (int r = 0; r < ht; r++) {
+                    float s = s_row, t = t_row;
+                    const bool row_ok = !MASKED || row_wanted(rf, (int)y0 + r);
+                    for (int c = 0; c < wt; c++) {
+                        if (row_ok && s > -0.0001f && t > -0.0001f && (s + t) < lim) mask |= bit;
+                        bit <<= 1;
+                        s += as; t += at;
                     }
+                    s_row += bs; t_row += bt;
                 }
             }
+        } else if (valid) {
+            lmask = inline_literal_mask(xr, yr, width, height, op, MASKED ? rf : RowFilter{0, 0x7FFFFFFF, nullptr});
+        }
+        const int n = fast ? __popc(mask) : __popcll(lmask);
+        // reserve n sample entries per lane with one atomic per warp
+        int inc = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (total == 0) return;
+        uint32_t b0 = 0;
+        if (lane == 31) b0 = atomicAdd(sl.count, (uint32_t)total);
+        b0 = __shfl_sync(0xffffffffu, b0, 31);
+        const bool rec = (unsigned long long)b0 + (unsigned long long)total <= (unsigned long long)sl.cap;
+        if (n == 0) return;
+        const uint32_t first = b0 + (uint32_t)(inc - n);
+        if (!rec) sl.extra[atomicAdd(sl.extra_count, 1u)] = fidx;                 // sample list full: kernel2 walks this fragment again
+        // plane of 1 / (z / far), cl2.cl:5029-5040
+        float3 d = make_float3(f[6 * IQ_SLOTS] / RR_DEPTH_FAR, f[7 * IQ_SLOTS] / RR_DEPTH_FAR, f[8 * IQ_SLOTS] / RR_DEPTH_FAR);     // dcalc
+        d = make_float3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);                                                                        // native_recip
+        float A, B, C;
+        interpolate_get_const(d, xr, yr, f[9 * IQ_SLOTS], A, B, C);
+        if (fast) {
+            const float iwt = __fdividef(1.f, (float)wt);
+            uint32_t at = first;
+            while (mask) {
+                const int i = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const int r = (int)(((float)i + 0.5f) * iwt);   // i / wt: i < 32, wt <= 32, so (i + 0.5) / wt is at least 1/64 away from an integer
+                const float x = x0 + (float)(i - r * wt), y = y0 + (float)r;
+                const float fd = fmaf(A, x, fmaf(B, y, C));
+                const uint32_t dd = sat_u32(RR_U32MAXF / fd);
+                const uint32_t px = (uint32_t)((int)(y * width) + (int)x);
+                atomicMin(target + px, dd);
+                if (rec) { sl.samples[at] = make_uint2(px, dd); sl.frag[at] = fidx; at++; }
+            }
+        } else {
+            inline_literal_emit(xr, yr, A, B, C, width, height, op, lmask, target, rec ? sl.samples + first : nullptr, sl.frag + first, fidx);
         }
     }
-    // called by all 32 lanes
-    __device__ __forceinline__ void push(bool has, const SubTri& s, uint32_t target_index, uint32_t fidx) {
+    // called by all 32 lanes: queue the triangle (rounded here), unless it provably covers nothing
+    __device__ __forceinline__ void push(bool has, const SubTri& s, uint32_t fidx) {
         const int lane = threadIdx.x & 31;
+        float3 xr, yr;
+        uint32_t flags = 0;
+        if (has) {
+            xr = make_float3(roundf(s.p0.x), roundf(s.p1.x), roundf(s.p2.x));
+            yr = make_float3(roundf(s.p0.y), roundf(s.p1.y), roundf(s.p2.y));
+            if (tri_exact_arith(xr, yr)) {
+                flags = IQ_EXACT;
+                if (isinf(s.rconst)) has = false;       // collinear after rounding (determinant exactly 0): point_in_tri's s + t < 0 can never hold
+            }
+        }
         const unsigned m = __ballot_sync(0xffffffffu, has);
         if (!m) return;
         if (has) {
-            const int at = count + __popc(m & ((1u << lane) - 1u));
-            float* f = &q->f[0][at];
-            f[0] = s.p0.x; f[IQ_SLOTS] = s.p0.y; f[2 * IQ_SLOTS] = s.p0.z;
-            f[3 * IQ_SLOTS] = s.p1.x; f[4 * IQ_SLOTS] = s.p1.y; f[5 * IQ_SLOTS] = s.p1.z;
-            f[6 * IQ_SLOTS] = s.p2.x; f[7 * IQ_SLOTS] = s.p2.y; f[8 * IQ_SLOTS] = s.p2.z;
-            f[9 * IQ_SLOTS] = s.rconst; f[10 * IQ_SLOTS] = __uint_as_float(target_index); f[11 * IQ_SLOTS] = __uint_as_float(fidx);
+            float* f = &q->f[0][count + __popc(m & ((1u << lane) - 1u))];
+            f[0] = xr.x; f[IQ_SLOTS] = xr.y; f[2 * IQ_SLOTS] = xr.z;
+            f[3 * IQ_SLOTS] = yr.x; f[4 * IQ_SLOTS] = yr.y; f[5 * IQ_SLOTS] = yr.z;
+            f[6 * IQ_SLOTS] = s.p0.z; f[7 * IQ_SLOTS] = s.p1.z; f[8 * IQ_SLOTS] = s.p2.z;
+            f[9 * IQ_SLOTS] = s.rconst; f[10 * IQ_SLOTS] = __uint_as_float(fidx); f[11 * IQ_SLOTS] = __uint_as_float(flags);
         }
         count += __popc(m);
         __syncwarp();
-        if (count >= 32) {                      // drain a full warp's worth
-            count -= 32;
-            run(count + lane, true);
+    }
+    // called by all 32 lanes: rasterise full warps' worth; with `all`, whatever is left as well
+    __device__ __forceinline__ void drain(bool all) {
+        const int lane = threadIdx.x & 31;
+        while (count >= 32 || (all && count > 0)) {
+            const int n = min(count, 32);
+            count -= n;
+            run(count + lane, lane < n);
             __syncwarp();
         }
-    }
-    __device__ __forceinline__ void flush() {
-        const int lane = threadIdx.x & 31;
-        __syncwarp();
-        if (count > 0) run(lane, lane < count);
-        count = 0;
-        __syncwarp();
     }
 };
 
@@ -477,7 +542,6 @@ struct PrologueParams {
     uint32_t n_tris, n_blocks;
     uint32_t* active; uint32_t* skipped_before;
     uint32_t* counters; unsigned long long* lookback;
-    unsigned long long* scan_lookback; uint32_t scan_tiles;   // k_scan_big's descriptors of the main pass, zeroed here too
     int cull;                                // 0: zeroing only
 };
 
@@ -487,13 +551,12 @@ __global__ void __launch_bounds__(PROLOGUE_THREADS) k_frame_prologue(const Prolo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t i = blockIdx.x * blockDim.x + tid;
     for (uint32_t j = i; j < P.n_blocks; j += gridDim.x * blockDim.x) P.lookback[j] = 0ull;
-    for (uint32_t j = i; j < P.scan_tiles; j += gridDim.x * blockDim.x) P.scan_lookback[j] = 0ull;
     if (!P.cull) {                           // whole frame, no culling: only the zeroing (cudaMemsetAsync would queue behind a
         if (i == 0) {                        // read-back DMA on the copy engine and stall the frame)
             P.counters[CTR_STICKY] |= P.counters[CTR_OVERFLOW];
             P.counters[CTR_NCUT] = 0u; P.counters[CTR_NFRAG] = 0u; P.counters[CTR_OVERFLOW] = 0u; P.counters[CTR_TICKET] = 0u;
             P.counters[CTR_NSAMPLES] = 0u; P.counters[CTR_NDESC] = 0u; P.counters[CTR_NSHADE] = 0u;
-            P.counters[CTR_SLOTS] = 0u; P.counters[CTR_SCAN_TICKET] = 0u; P.counters[CTR_NBIG] = 0u;
+            P.counters[CTR_NEXTRA] = 0u; P.counters[CTR_NWORK] = 0u;
         }
         return;
     }
@@ -546,7 +609,7 @@ __global__ void __launch_bounds__(PROLOGUE_THREADS) k_frame_prologue(const Prolo
         P.counters[CTR_NCUT] = ta == 0 ? ts : 0u;                 // nothing survives: k_setup_main's blocks all leave at once
         P.counters[CTR_NFRAG] = 0u; P.counters[CTR_OVERFLOW] = 0u; P.counters[CTR_TICKET] = 0u;
         P.counters[CTR_NSAMPLES] = 0u; P.counters[CTR_NDESC] = 0u; P.counters[CTR_NSHADE] = 0u;
-        P.counters[CTR_SLOTS] = 0u; P.counters[CTR_SCAN_TICKET] = 0u; P.counters[CTR_NBIG] = 0u;
+        P.counters[CTR_NEXTRA] = 0u; P.counters[CTR_NWORK] = 0u;
         P.counters[CTR_NACTIVE] = ta;
         P.counters[CTR_CUT_SKIPPED] = ts;
     }
@@ -560,6 +623,7 @@ struct SetupMainParams {
     float width, height, fov, icut;
     uint32_t* frags; uint32_t cap_frags;
     uint32_t* fragcnt;                       // pixel slots per fragment (+ FRAGCNT_DEPTH_DONE)
+    uint32_t* worklist;                      // fragments that are not rasterised inline (count: CTR_NWORK)
     float4* cutdown; uint32_t cap_cut;
     uint32_t* counters;
     unsigned long long* lookback;
@@ -719,39 +783,40 @@ __global__ void __launch_bounds__(SETUP_THREADS, RR_LB_SETUP_MAIN) k_setup_main(
         out[w] = val;
         if (field == 1) {
             const uint32_t ke = (uint32_t)s_kend[slot];
-            P.fragcnt[base_f + r] = chunk_slots((int)(ke & ~FRAGCNT_DEPTH_DONE), (int)val, RR_OP_SIZE) | (ke & FRAGCNT_DEPTH_DONE);
+            const uint32_t slots = chunk_slots((int)(ke & ~FRAGCNT_DEPTH_DONE), (int)val, RR_OP_SIZE);
+            P.fragcnt[base_f + r] = slots | (ke & FRAGCNT_DEPTH_DONE);
+            if (slots && !(ke & FRAGCNT_DEPTH_DONE)) P.worklist[atomicAdd(&P.counters[CTR_NWORK], 1u)] = base_f + r;     // kernel1 / kernel2 walk it (k_raster_warp)
         }
     }
     // kernel1's work for the small single-chunk triangles, after everything other blocks wait for has been published
     __syncthreads();            // every fragcnt word of this block is written: the rasterising lane may now update its flags
-    InlineRaster<true, BANDED> ir;
-    ir.q = &s_iq[warp]; ir.count = 0; ir.op = RR_OP_SIZE; ir.width = P.width; ir.height = P.height; ir.base = P.depth; ir.face_stride = 0;
-    ir.row_lo = P.row_lo; ir.row_hi = P.row_hi; ir.rowmask = P.rowmask; ir.sl = P.sl;
-    ir.push(inl0 && frag_ok, st0, 0u, base_f + ex_f);                 // single-chunk triangles: their one fragment's index
-    ir.push(inl1 && frag_ok, st1, 0u, base_f + ex_f + my_f0);
-    ir.flush();
+    InlineRaster<BANDED> ir;
+    ir.q = &s_iq[warp]; ir.count = 0; ir.op = RR_OP_SIZE; ir.width = P.width; ir.height = P.height; ir.target = P.depth;
+    ir.rf = RowFilter{P.row_lo, P.row_hi, P.rowmask}; ir.sl = P.sl;
+#pragma unroll 1
+    for (int i = 0; i < 2; i++) {                                      // (one copy of the rasteriser for both clip halves)
+        const bool has = (i ? inl1 : inl0) && frag_ok;
+        ir.push(has, i ? st1 : st0, base_f + ex_f + (i ? my_f0 : 0u));  // single-chunk triangles: their one fragment's index
+        ir.drain(i == 1);
+    }
 }
 
 // =====================================================================================================================
 // Rasterisation: kernel1 (cl2.cl:4986-5127), kernel2 (5391-5546), kernel1_realtime_shadowing (5130-5246).
 //
 // The reference gives one work-item one <=501-pixel chunk and walks it sequentially, so a pass lasts as long as its
-// longest walk (measured: 82 us for a pass whose total work is ~10 us). Two paths here, split by the number of pixel
-// slots a fragment visits (known at setup time):
-//   small (<= RASTER_SMALL_MAX slots): k_raster_small — one thread replays the walk verbatim; the tail is bounded.
-//   big: k_scan_big compacts them into a list with a prefix sum of their slot counts; k_raster_big gives every CTA an
-//        equal range of SLOTS wherever they come from, stages the owning fragments' geometry in shared memory and
-//        resolves each slot with the closed form of the walk (rr_math.cuh walk_pixel).
+// longest walk (measured: 82 us for a pass whose total work is ~10 us). Here:
+//   * a triangle whose whole walk is one chunk of at most RASTER_SMALL_MAX slots is rasterised by the setup kernel itself,
+//     through a per-warp queue (InlineRaster / k_shadow_setup's stage C): no record round trip, no second kernel;
+//   * every other fragment goes to a work list and gets a whole warp (k_raster_warp / k_raster_shadow_warp), which
+//     resolves its pixel slots 32 at a time with the closed form of the walk (rr_math.cuh walk_pixel).
 // Depth goes out as red.global.min.u32 on the L2-resident buffer; ids as red.global.max.u32 (canonical last writer).
 // =====================================================================================================================
 enum { RM_DEPTH = 0, RM_IDS = 1, RM_SHADOW = 2 };
-#define RASTER_THREADS 256
-#define RASTER_SLOTS 2048           // pixel slots per CTA work item (big path)
-#define RASTER_FRAGS 256            // fragments staged at a time (big path)
 
 struct RasterParams {
     const uint32_t* frags; const float4* cutdown; const uint32_t* fragcnt; const uint32_t* counters; uint32_t cap_frags;
-    const uint32_t* biglist; const uint32_t* bigslot;
+    const uint32_t* worklist; const uint32_t* extra;      // main view: fragments to walk (CTR_NWORK), plus — kernel2 only — CTR_NEXTRA unlisted inline ones
     int n_index;                    // CTR_NFRAG or CTR_S_NFRAG
     uint32_t* depth; uint32_t* ids; // RM_SHADOW: depth = base of the cubemap buffer of this pass
     uint32_t slab_of_light[16];     // RM_SHADOW: record word 0 = light << 8 | face; slab index of each light of the pass
@@ -803,223 +868,55 @@ __device__ __forceinline__ bool chunk_rows_outside(const float4 mm, int op_size,
     return y_hi < row_lo || y_lo >= row_hi;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) k_raster_small(const RasterParams P) {
-    constexpr int OP = (MODE == RM_SHADOW) ? RR_OP_SIZE_LIGHT : RR_OP_SIZE;
-    const uint32_t n = min(P.counters[P.n_index], P.cap_frags);
-    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
-        const uint32_t raw = __ldg(P.fragcnt + f), cnt = raw & FRAGCNT_MASK;
-        if (cnt > RASTER_SMALL_MAX || cnt == 0) continue;
-        if (MODE == RM_DEPTH && (raw & FRAGCNT_DEPTH_DONE)) continue;        // written inline by k_setup_main
-        if (MODE == RM_IDS && (raw & FRAGCNT_IDS_LISTED)) continue;          // resolved from the sample list by k_ids_list
-        uint32_t face, distance;
-        FragGeom g;
-        load_fragment<MODE>(P, f, face, distance, g);
-        if (MODE != RM_SHADOW && chunk_rows_outside(g.mm, OP, distance, P.row_lo, P.row_hi)) continue;
-        scan_chunk(g.mm, OP, distance, [&](float x, float y) {
-            if (MODE != RM_SHADOW && P.rowmask && !(P.rowmask[(int)y] & P.rowbit)) return;
-            if (point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) emit_sample<MODE>(P, x, y, g.A, g.B, g.C, face, f);
-        });
-    }
-}
-
 // kernel2 for the triangles the setup kernel rasterised inline: stream their recorded samples instead of walking again.
 __global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const uint32_t* __restrict__ depth, uint32_t* __restrict__ ids, int W, int row_lo, int row_hi,
                                                   const uint8_t* __restrict__ rowmask) {
-    const uint32_t n = min(*sl.desc_count, sl.cap_desc);
+    const uint32_t n = min(*sl.count, sl.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint4 de = sl.desc[i];
-        for (uint32_t j = 0; j < de.y; j++) {
-            const uint2 sm = sl.samples[de.x + j];
-            const int row = (int)(sm.x / (uint32_t)W);
-            if (row < row_lo || row >= row_hi) continue;
-            if (rowmask && !(rowmask[row] & ROW_OWNED)) continue;
-            const uint32_t val = depth[sm.x];
-            if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) atomicMax(ids + sm.x, de.z + 1u);
-        }
+        const uint2 sm = sl.samples[i];
+        const int row = (int)(sm.x / (uint32_t)W);
+        if (row < row_lo || row >= row_hi) continue;
+        if (rowmask && !(rowmask[row] & ROW_OWNED)) continue;
+        const uint32_t val = depth[sm.x];
+        if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) atomicMax(ids + sm.x, sl.frag[i] + 1u);
     }
 }
 
-// ---- k_scan_big: compact the big fragments and prefix-sum their slot counts (single pass, decoupled look-back) --------
-#define SCAN_THREADS 256
-#define SCAN_ITEMS 8
-#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
-#define SCAN_SLOT_BITS 37
-#define SCAN_PAYLOAD_MASK ((1ull << 62) - 1)
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_big(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ n_ptr, uint32_t cap,
-                                                            uint32_t* __restrict__ biglist, uint32_t* __restrict__ bigslot,
-                                                            uint32_t* __restrict__ counters, unsigned long long* __restrict__ lookback) {
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
-    __shared__ unsigned long long s_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n = min(*n_ptr, cap);
-    const uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(&counters[CTR_SCAN_TICKET], 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= n_tiles) break;                       // counters[CTR_SLOTS], [CTR_NBIG] were zeroed by the host
-        const uint32_t first = tile * SCAN_TILE + tid * SCAN_ITEMS;
-        uint32_t v[SCAN_ITEMS];
-        unsigned long long mine = 0;                      // (number of big fragments << 37) | their slots
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            uint32_t c = (first + i < n) ? (__ldg(cnt + first + i) & FRAGCNT_MASK) : 0u;
-            v[i] = c > RASTER_SMALL_MAX ? c : 0u;
-            if (v[i]) mine += (1ull << SCAN_SLOT_BITS) | v[i];
-        }
-        unsigned long long inc = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        unsigned long long woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < SCAN_THREADS / 32; w++) { unsigned long long x = s_warp[w]; if (w < warp) woff += x; tot += x; }
-        if (warp == 0) {
-            volatile unsigned long long* desc = lookback;
-            unsigned long long base = 0;
-            if (tile == 0) { if (lane == 0) desc[0] = (2ull << 62) | tot; }
-            else {
-                if (lane == 0) desc[tile] = (1ull << 62) | tot;
-                int look = (int)tile - 1;
-                uint32_t watchdog = 0;
-                while (true) {
-                    int idx = look - lane;
-                    unsigned long long d = 2ull << 62;
-                    if (idx >= 0) {
-                        do {
-                            d = desc[idx];
-                            if (++watchdog > (1u << 26)) { atomicOr(&counters[CTR_OVERFLOW], 4u); d = 2ull << 62; break; }
-                        } while ((d >> 62) == 0);
-                    }
-                    const unsigned incl = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-                    const int first_incl = incl ? (__ffs(incl) - 1) : 32;
-                    unsigned long long val = (lane <= first_incl) ? (d & SCAN_PAYLOAD_MASK) : 0ull;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-                    base += val;
-                    if (incl) break;
-                    look -= 32;
-                }
-                if (lane == 0) desc[tile] = (2ull << 62) | (base + tot);
-            }
-            if (lane == 0) {
-                s_base = base;
-                if (tile == n_tiles - 1) {
-                    const unsigned long long all = base + tot, slots = all & ((1ull << SCAN_SLOT_BITS) - 1);
-                    if (slots > 0xFFFFFFFFull) atomicOr(&counters[CTR_OVERFLOW], 8u);
-                    counters[CTR_SLOTS] = (uint32_t)min(slots, 0xFFFFFFFFull);
-                    counters[CTR_NBIG] = (uint32_t)(all >> SCAN_SLOT_BITS);
-                }
-            }
-        }
-        __syncthreads();
-        unsigned long long run = s_base + woff + inc - mine;
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            if (v[i]) {
-                const uint32_t at = (uint32_t)(run >> SCAN_SLOT_BITS);
-                biglist[at] = first + i;
-                bigslot[at] = (uint32_t)(run & ((1ull << SCAN_SLOT_BITS) - 1));
-                run += (1ull << SCAN_SLOT_BITS) | v[i];
-            }
-        }
-    }
-}
-
-// largest i in [0, n) with slot[i] <= s (slot[] is non-decreasing, slot[0] == 0); executed by one full warp
-__device__ __forceinline__ uint32_t warp_search_le(const uint32_t* __restrict__ slot, uint32_t n, uint32_t s) {
-    const int lane = threadIdx.x & 31;
-    uint32_t lo = 0, hi = n;                                 // answer in [lo, hi)
-    while (hi - lo > 1) {
-        const uint32_t step = (hi - lo + 31) / 32;
-        const uint32_t idx = lo + lane * step;
-        const bool ok = idx < hi && __ldg(slot + idx) <= s;
-        const unsigned m = __ballot_sync(0xffffffffu, ok);   // lane 0 is always ok (slot[lo] <= s)
-        const int last = 31 - __clz((int)m);
-        const uint32_t nlo = lo + (uint32_t)last * step;
-        hi = min(hi, nlo + step);
-        lo = nlo;
-    }
-    return lo;
-}
-
+// kernel1 (cl2.cl:4986-5127) / kernel2 (cl2.cl:5391-5546) for the fragments k_setup_main did not rasterise inline: one warp per
+// fragment of the work list, the lanes take the chunk's pixel slots 32 at a time through the closed form of the walk
+// (rr_math.cuh walk_pixel). A chunk has at most 501 slots, so a warp's work is bounded and consecutive chunks of a large
+// triangle land on different warps. Depth goes out as red.global.min.u32 on the L2-resident buffer, ids as
+// red.global.max.u32 (canonical last writer).
 template <int MODE>
-__global__ void __launch_bounds__(RASTER_THREADS) k_raster_big(const RasterParams P) {
-    constexpr int OP = (MODE == RM_SHADOW) ? RR_OP_SIZE_LIGHT : RR_OP_SIZE;
-    __shared__ float4 s_mm[RASTER_FRAGS];        // box
-    __shared__ float4 s_xa[RASTER_FRAGS];        // xr.xyz, A
-    __shared__ float4 s_yb[RASTER_FRAGS];        // yr.xyz, B
-    __shared__ float4 s_cw[RASTER_FRAGS];        // C, 1/width, k0 (int bits), width (int bits)
-    __shared__ uint32_t s_slot[RASTER_FRAGS];    // first slot of the fragment
-    __shared__ uint32_t s_face[RASTER_FRAGS];
-    __shared__ uint32_t s_frag[RASTER_FRAGS];    // fragment index (what kernel2 writes)
-    __shared__ uint32_t s_i0, s_i1;
-
-    const int tid = threadIdx.x;
-    const uint32_t n = P.counters[CTR_NBIG];
-    const uint32_t total = P.counters[CTR_SLOTS];
-    if (n == 0) return;
-    for (uint32_t item = blockIdx.x; (unsigned long long)item * RASTER_SLOTS < total; item += gridDim.x) {
-        const uint32_t s0 = item * RASTER_SLOTS;
-        const uint32_t s1 = (uint32_t)min((unsigned long long)total, (unsigned long long)s0 + RASTER_SLOTS);
-        __syncthreads();
-        if (tid < 32) { uint32_t i = warp_search_le(P.bigslot, n, s0); if (tid == 0) s_i0 = i; }
-        else if (tid < 64) { uint32_t i = warp_search_le(P.bigslot, n, s1 - 1); if (tid == 32) s_i1 = i; }
-        __syncthreads();
-        const uint32_t i0 = s_i0, i1 = s_i1;
-        for (uint32_t ib = i0; ib <= i1; ib += RASTER_FRAGS) {
-            const uint32_t nf = min((uint32_t)RASTER_FRAGS, i1 + 1 - ib);
-            __syncthreads();
-            if (tid < (int)nf) {
-                const uint32_t f = __ldg(P.biglist + ib + tid);
-                uint32_t face, distance;
-                FragGeom g;
-                load_fragment<MODE>(P, f, face, distance, g);
-                const int width = (int)(g.mm.y - g.mm.x);
-                s_mm[tid] = g.mm;
-                s_xa[tid] = make_float4(g.xr.x, g.xr.y, g.xr.z, g.A);
-                s_yb[tid] = make_float4(g.yr.x, g.yr.y, g.yr.z, g.B);
-                s_cw[tid] = make_float4(g.C, 1.f / (float)width, __int_as_float(OP * (int)distance), __int_as_float(width));
-                s_slot[tid] = __ldg(P.bigslot + ib + tid);
-                s_face[tid] = face;
-                s_frag[tid] = f;
-            }
-            __syncthreads();
-            // slots of this batch of fragments that fall in [s0, s1)
-            const uint32_t b0 = max(s0, s_slot[0]);
-            const uint32_t b1 = (ib + nf < n) ? min(s1, __ldg(P.bigslot + ib + nf)) : s1;
-            for (uint32_t s = b0 + tid; s < b1; s += RASTER_THREADS) {
-                int lo = 0, hi = (int)nf - 1;                 // last staged fragment whose first slot is <= s
-                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_slot[mid] <= s) lo = mid; else hi = mid - 1; }
-                const float4 mm = s_mm[lo], cw = s_cw[lo];
-                const int k0 = __float_as_int(cw.z), width = __float_as_int(cw.w);
-                const int k = k0 + (int)(s - s_slot[lo]);
-                float x, y;
-                if (!walk_pixel(k, k0, width, cw.y, mm, x, y)) continue;
-                const int iy = (int)y;
-                if (MODE != RM_SHADOW && (iy < P.row_lo || iy >= P.row_hi)) continue;
-                if (MODE != RM_SHADOW && P.rowmask && !(P.rowmask[iy] & P.rowbit)) continue;
-                const float4 xa = s_xa[lo], yb = s_yb[lo];
-                if (!point_in_tri(x, y, xa.x, yb.x, xa.y, yb.y, xa.z, yb.z)) continue;
-                emit_sample<MODE>(P, x, y, xa.w, yb.w, cw.x, s_face[lo], s_frag[lo]);
-            }
+__global__ void __launch_bounds__(256) k_raster_warp(const RasterParams P) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_work = min(P.counters[CTR_NWORK], P.cap_frags);
+    const uint32_t n_all = n_work + (MODE == RM_IDS ? min(P.counters[CTR_NEXTRA], P.cap_frags) : 0u);
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_all; i += warps) {
+        const uint32_t f = i < n_work ? __ldg(P.worklist + i) : __ldg(P.extra + (i - n_work));
+        const uint32_t cnt = __ldg(P.fragcnt + f) & FRAGCNT_MASK;
+        if (cnt == 0) continue;
+        uint32_t face, distance;
+        FragGeom g;
+        load_fragment<MODE>(P, f, face, distance, g);          // the same record for every lane: broadcast loads
+        if (chunk_rows_outside(g.mm, RR_OP_SIZE, distance, P.row_lo, P.row_hi)) continue;
+        const int width = (int)(g.mm.y - g.mm.x), k0 = RR_OP_SIZE * (int)distance;
+        const float iw = 1.f / (float)width;
+        for (uint32_t s = lane; s < cnt; s += 32u) {
+            float x, y;
+            if (!walk_pixel(k0 + (int)s, k0, width, iw, g.mm, x, y)) continue;
+            const int iy = (int)y;
+            if (iy < P.row_lo || iy >= P.row_hi) continue;
+            if (P.rowmask && !(P.rowmask[iy] & P.rowbit)) continue;
+            if (!point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) continue;
+            emit_sample<MODE>(P, x, y, g.A, g.B, g.C, face, f);
         }
     }
 }
 
 // =====================================================================================================================
-// shadow passes: k_shadow_setup == prearrange_realtime_shadowing (cl2.cl:4420-4636) for ALL lights of a pass in one launch.
-// The reference launches the kernel once per light and re-reads / re-transforms every triangle each time. Here a thread
-// loads its triangle once, brings it to world space once (bit-identical: that part of full_rotate_quat does not depend
-// on the light), and loops over the lights and their cube faces. Slot numbers of a shadow pass are never observable
-// (only the atomic_min result is), so allocation is ONE warp-aggregated 64-bit atomicAdd per (light, face) step that
-// reserves projected-triangle slots and fragment records together. Faces not owned by this context are skipped.
-// Records: {light << 8 | face, chunk, c_id, bits(rconst)} (cl2.cl:4626-4631 with the light folded into word 0).
+// shadow passes
 // =====================================================================================================================
 #define SHADOW_MAX_LIGHTS 16
 struct ShadowLight { float x, y, z; uint32_t slab; uint32_t face_mask; };
