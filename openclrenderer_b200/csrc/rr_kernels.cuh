@@ -645,11 +645,6 @@ __global__ void __launch_bounds__(SETUP_THREADS, RR_LB_SETUP_MAIN) k_setup_main(
     __shared__ uint32_t s_bid;
     __shared__ uint32_t s_warp_c[SETUP_THREADS / 32], s_warp_f[SETUP_THREADS / 32];
     __shared__ uint32_t s_base_c, s_base_f, s_tot_f;
-    __shared__ uint32_t s_fexcl[2 * SETUP_THREADS];      // exclusive fragment offset of slot (2*thread + i) inside the block
-    __shared__ uint32_t s_cid[2 * SETUP_THREADS];
-    __shared__ float s_rconst[2 * SETUP_THREADS];
-    __shared__ int s_kend[2 * SETUP_THREADS];
-    __shared__ uint32_t s_oid[SETUP_THREADS];
     __shared__ InlineQueue s_iq[SETUP_THREADS / 32];
 
     static_assert(SETUP_THREADS == 2 * CLUSTER_TRIS, "one k_setup_main block == two clusters");
@@ -724,72 +719,77 @@ __global__ void __launch_bounds__(SETUP_THREADS, RR_LB_SETUP_MAIN) k_setup_main(
         setup_lookback(P.lookback, P.counters, bid, is_last, cut_skipped_total, tot_c, tot_f, base_c, base_f);
         if (lane == 0) { s_base_c = base_c + cut_skipped; s_base_f = base_f; s_tot_f = tot_f; }
     }
-    // stage per-slot data for the cooperative record write
-    const uint32_t cid0 = ex_c;    // block-relative; global added below
-    s_fexcl[2 * tid] = ex_f;
-    s_fexcl[2 * tid + 1] = ex_f + my_f0;
-    s_rconst[2 * tid] = st0.rconst;
-    s_rconst[2 * tid + 1] = st1.rconst;
-    s_kend[2 * tid] = kend0 | (inl0 ? (int)FRAGCNT_DEPTH_DONE : 0);            // kend < 2^31 always
-    s_kend[2 * tid + 1] = kend1 | (inl1 ? (int)FRAGCNT_DEPTH_DONE : 0);
-    s_oid[tid] = oid;
     __syncthreads();
     const uint32_t base_c = s_base_c, base_f = s_base_f;
-    s_cid[2 * tid] = base_c + cid0;
-    s_cid[2 * tid + 1] = base_c + cid0 + 1;
+    const uint32_t cid0 = base_c + ex_c;
 
     // projected triangles: (x_px, y_px, z_cam, 0) unrounded, cl2.cl:4384-4386
     bool cut_ok = (base_c + tot_c) <= P.cap_cut;
     if (!cut_ok && tid == 0) atomicOr(&P.counters[CTR_OVERFLOW], 2u);
     if (cut_ok) {
         if (num > 0 && st0.keep) {
-            float4* dst = P.cutdown + (size_t)(base_c + cid0) * 3;
+            float4* dst = P.cutdown + (size_t)cid0 * 3;
             dst[0] = make_float4(st0.p0.x, st0.p0.y, st0.p0.z, 0.f);
             dst[1] = make_float4(st0.p1.x, st0.p1.y, st0.p1.z, 0.f);
             dst[2] = make_float4(st0.p2.x, st0.p2.y, st0.p2.z, 0.f);
         }
         if (num > 1 && st1.keep) {
-            float4* dst = P.cutdown + (size_t)(base_c + cid0 + 1) * 3;
+            float4* dst = P.cutdown + (size_t)(cid0 + 1) * 3;
             dst[0] = make_float4(st1.p0.x, st1.p0.y, st1.p0.z, 0.f);
             dst[1] = make_float4(st1.p1.x, st1.p1.y, st1.p1.z, 0.f);
             dst[2] = make_float4(st1.p2.x, st1.p2.y, st1.p2.z, 0.f);
         }
     }
-    __syncthreads();
 
-    // fragment records {tri id, chunk, c_id, bits(rconst), o_id}, cl2.cl:4394-4406 — block-cooperative, word-coalesced
+    // fragment records {tri id, chunk, c_id, bits(rconst), o_id}, cl2.cl:4394-4406, the per-fragment slot counts, and the work
+    // list of the fragments kernel1 / kernel2 still have to walk (everything that is not rasterised inline below).
     const uint32_t totf = s_tot_f;
     const bool frag_ok = (unsigned long long)base_f + totf <= (unsigned long long)P.cap_frags;
     if (!frag_ok && tid == 0) atomicOr(&P.counters[CTR_OVERFLOW], 1u);
-    uint32_t* out = P.frags + (size_t)base_f * RR_FRAG_WORDS;
-    const uint32_t nwords = frag_ok ? totf * RR_FRAG_WORDS : 0u;
-    for (uint32_t w = tid; w < nwords; w += SETUP_THREADS) {
-        const uint32_t r = w / RR_FRAG_WORDS, field = w - r * RR_FRAG_WORDS;
-        // last slot whose exclusive offset is <= r (slots with zero fragments share offsets; the last one owns r)
-        int lo = 0, hi = 2 * SETUP_THREADS - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (s_fexcl[mid] <= r) lo = mid; else hi = mid - 1;
+#pragma unroll 1
+    for (int i = 0; i < 2; i++) {
+        const uint32_t n = frag_ok ? (i ? my_f1 : my_f0) : 0u;
+        const uint32_t fi = base_f + ex_f + (i ? my_f0 : 0u), cid = cid0 + (uint32_t)i;
+        const float rc = i ? st1.rconst : st0.rconst;
+        const int kend = i ? kend1 : kend0;
+        const bool inl = i ? inl1 : inl0;
+        // one fragment (nearly every triangle): the owning lane writes its record; offsets grow with the lane, so a warp's stores
+        // fall into one short address range
+        const bool walk1 = n == 1 && !inl && chunk_slots(kend, 0, RR_OP_SIZE) > 0;
+        const unsigned mw = __ballot_sync(0xffffffffu, walk1);
+        uint32_t wbase = 0;
+        if (mw) {
+            if (lane == 0) wbase = atomicAdd(&P.counters[CTR_NWORK], (uint32_t)__popc(mw));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
         }
-        const int slot = lo;
-        uint32_t val;
-        switch (field) {
-            case 0: val = tblock * SETUP_THREADS + (uint32_t)(slot >> 1); break;
-            case 1: val = r - s_fexcl[slot]; break;
-            case 2: val = s_cid[slot]; break;
-            case 3: val = __float_as_uint(s_rconst[slot]); break;
-            default: val = s_oid[slot >> 1]; break;
+        if (n == 1) {
+            uint32_t* o = P.frags + (size_t)fi * RR_FRAG_WORDS;
+            o[0] = tri; o[1] = 0u; o[2] = cid; o[3] = __float_as_uint(rc); o[4] = oid;
+            P.fragcnt[fi] = chunk_slots(kend, 0, RR_OP_SIZE) | (inl ? FRAGCNT_DEPTH_DONE : 0u);
+            if (walk1) P.worklist[wbase + __popc(mw & ((1u << lane) - 1u))] = fi;
         }
-        out[w] = val;
-        if (field == 1) {
-            const uint32_t ke = (uint32_t)s_kend[slot];
-            const uint32_t slots = chunk_slots((int)(ke & ~FRAGCNT_DEPTH_DONE), (int)val, RR_OP_SIZE);
-            P.fragcnt[base_f + r] = slots | (ke & FRAGCNT_DEPTH_DONE);
-            if (slots && !(ke & FRAGCNT_DEPTH_DONE)) P.worklist[atomicAdd(&P.counters[CTR_NWORK], 1u)] = base_f + r;     // kernel1 / kernel2 walk it (k_raster_warp)
+        // several chunks: the warp writes them together, one 32-bit word per lane per step
+        for (unsigned m = __ballot_sync(0xffffffffu, n >= 2); m; m &= m - 1u) {
+            const int src = __ffs(m) - 1;
+            const uint32_t bn = __shfl_sync(0xffffffffu, n, src), bfi = __shfl_sync(0xffffffffu, fi, src), btri = __shfl_sync(0xffffffffu, tri, src);
+            const uint32_t bcid = __shfl_sync(0xffffffffu, cid, src), brc = __shfl_sync(0xffffffffu, __float_as_uint(rc), src), boid = __shfl_sync(0xffffffffu, oid, src);
+            const int bkend = __shfl_sync(0xffffffffu, kend, src);
+            const uint32_t n_walk = min(bn, (uint32_t)((bkend + RR_OP_SIZE - 1) / RR_OP_SIZE));     // chunks that visit at least one slot
+            uint32_t lbase = 0;
+            if (lane == 0 && n_walk) lbase = atomicAdd(&P.counters[CTR_NWORK], n_walk);
+            lbase = __shfl_sync(0xffffffffu, lbase, 0);
+            uint32_t* o = P.frags + (size_t)bfi * RR_FRAG_WORDS;
+            for (uint32_t w = lane; w < bn * RR_FRAG_WORDS; w += 32u) {
+                const uint32_t r = w / RR_FRAG_WORDS, field = w - r * RR_FRAG_WORDS;
+                o[w] = field == 0 ? btri : (field == 1 ? r : (field == 2 ? bcid : (field == 3 ? brc : boid)));
+            }
+            for (uint32_t r = lane; r < bn; r += 32u) {
+                P.fragcnt[bfi + r] = chunk_slots(bkend, (int)r, RR_OP_SIZE);
+                if (r < n_walk) P.worklist[lbase + r] = bfi + r;
+            }
         }
     }
     // kernel1's work for the small single-chunk triangles, after everything other blocks wait for has been published
-    __syncthreads();            // every fragcnt word of this block is written: the rasterising lane may now update its flags
     InlineRaster<BANDED> ir;
     ir.q = &s_iq[warp]; ir.count = 0; ir.op = RR_OP_SIZE; ir.width = P.width; ir.height = P.height; ir.target = P.depth;
     ir.rf = RowFilter{P.row_lo, P.row_hi, P.rowmask}; ir.sl = P.sl;
@@ -973,7 +973,8 @@ __device__ __forceinline__ void warp_alloc2(uint32_t* counters, uint32_t nc, uin
 //   A  per (triangle, light): which cube faces does the triangle mark, is it clearly back-facing   -> items (lane, face, light)
 //   B  per item: rotate into the face's camera, clip, project, cull, classify                      -> small triangles / records
 //   C  per small triangle: rasterise its box straight into the cubemap (kernel1_realtime_shadowing's work for it)
-#define SQ_ITEMS 128            // stage A -> B: up to 3 faces x 32 lanes arrive at once on top of < 32 waiting items
+#define SQ_GROUP 4              // lights per stage-A round (one byte of face bits per light in a 32-bit word)
+#define SQ_ITEMS 448            // stage A -> B: up to 3 faces x 4 lights x 32 lanes arrive at once on top of < 32 waiting items (+ 32 requeued clip halves)
 #define SR_SLOTS 64             // stage B -> C: 32 arrive on top of < 32 waiting
 #define SR_FIELDS 11            // rounded x of the 3 vertices, rounded y, camera z, rconst, face slab index
 struct ShadowWarpQueue {
@@ -1091,11 +1092,38 @@ __device__ __forceinline__ void shadow_raster_small(const ShadowWarpQueue& Q, in
 // Records: {light << 8 | face, chunk, c_id, bits(rconst)} (cl2.cl:4626-4631 with the light folded into word 0); they are
 // rasterised by k_raster_shadow_warp.
 // =====================================================================================================================
+// The rare tail of stage B: a triangle that is larger than one small chunk gets a projected-triangle slot and one record per chunk
+// (rasterised by k_raster_shadow_warp). Called by all 32 lanes (the allocation is one warp-aggregated atomic); out of line so that
+// its registers and code stay out of the hot loop.
+__device__ __noinline__ void shadow_store_big(uint32_t* __restrict__ counters, float4* __restrict__ cutdown, uint32_t cap_cut, uint32_t* __restrict__ frags, uint32_t cap_frags,
+                                              uint32_t* __restrict__ fragcnt, bool big, float3 p0, float3 p1, float3 p2, float3 xr, float3 yr, float rconst, float area,
+                                              float L, uint32_t word0) {
+    const int n_frag = big ? (int)ceilf(area / (float)RR_OP_SIZE_LIGHT) : 0;
+    uint32_t cid, fbase;
+    warp_alloc2(counters, big ? 1u : 0u, (uint32_t)n_frag, cid, fbase);
+    if (!big) return;
+    if (cid + 1u > cap_cut) { atomicOr(&counters[CTR_OVERFLOW], 2u); return; }
+    if ((unsigned long long)fbase + (uint32_t)n_frag > (unsigned long long)cap_frags) { atomicOr(&counters[CTR_OVERFLOW], 1u); return; }
+    float4* dst = cutdown + (size_t)cid * 3;
+    dst[0] = make_float4(p0.x, p0.y, p0.z, 0.f);
+    dst[1] = make_float4(p1.x, p1.y, p1.z, 0.f);
+    dst[2] = make_float4(p2.x, p2.y, p2.z, 0.f);
+    const float4 mm = calc_min_max(xr, yr, L, L);
+    const int width = (int)(mm.y - mm.x), nrows = (int)(mm.w - mm.z);
+    const int kend = walk_end(width, nrows, 1.f / (float)width, mm.z, mm.w);
+    uint4* rec = reinterpret_cast<uint4*>(frags) + fbase;
+    for (int a = 0; a < n_frag; a++) {
+        rec[a] = make_uint4(word0, (uint32_t)a, cid, __float_as_uint(rconst));
+        fragcnt[fbase + a] = chunk_slots(kend, a, RR_OP_SIZE_LIGHT);
+    }
+}
+
 __global__ void RR_LB_SHADOW_SETUP_ATTR k_shadow_setup(const ShadowSetupParams P) {
     __shared__ ShadowWarpQueue s_q[128 / 32];
     __shared__ RotSC s_face[6];
     __shared__ float4 s_light[SHADOW_MAX_LIGHTS];    // position, w = bits of (slab << 8 | face_mask)
     static_assert(CLUSTER_TRIS == 128, "one k_shadow_setup block == one cluster");
+    static_assert(SHADOW_MAX_LIGHTS <= 16, "face bits of a pass: one byte per light in two 64-bit words");
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t tri = blockIdx.x * blockDim.x + tid;
     uint4 reach4 = make_uint4(0x3F3F3F3Fu, 0x3F3F3F3Fu, 0x3F3F3F3Fu, 0x3F3F3F3Fu);
@@ -1113,72 +1141,71 @@ __global__ void RR_LB_SHADOW_SETUP_ATTR k_shadow_setup(const ShadowSetupParams P
 
     ShadowWarpQueue& Q = s_q[tid >> 5];
     const float L = P.L, half = P.L / 2.f;
-    bool active = tri < P.n_tris;
-    float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0, gpos = w0, nrm = w0;
-    float nn = 0.f, emax2 = 0.f;
+    // ---- the triangle in world space, and (stage A's arithmetic) the cube faces of every light it goes to: byte li of (flo, fhi)
+    float3 w0 = make_float3(0, 0, 0), w1 = w0, w2 = w0;
+    unsigned long long flo = 0ull, fhi = 0ull;
     bool two_sided = false;
-    if (active) {
+    if (tri < P.n_tris) {
         const float4 a = __ldg(P.pa + tri), b = __ldg(P.pb + tri);
         const float2 c = __ldg(P.pc + tri);
         const ObjLite G = P.objs[__float_as_uint(c.y)];
         const bool is_static = (G.feature_flag & RR_FEATURE_IS_STATIC) > 0;
-        if ((!P.only_static && is_static) || (P.only_static && !is_static)) active = false;     // cl2.cl:4460-4464
-        else {
-            gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
+        if (!((!P.only_static && is_static) || (P.only_static && !is_static))) {               // cl2.cl:4460-4464
+            const float3 gpos = make_float3(G.pos_scale.x, G.pos_scale.y, G.pos_scale.z);
             const float sc = G.pos_scale.w;
             w0 = rot_quat_n(make_float3(a.x, a.y, a.z) * sc, G.nquat) + gpos;                  // cl2.cl:4524-4525 == 505-507
             w1 = rot_quat_n(make_float3(a.w, b.x, b.y) * sc, G.nquat) + gpos;
             w2 = rot_quat_n(make_float3(b.z, b.w, c.x) * sc, G.nquat) + gpos;
             two_sided = (G.feature_flag & RR_FEATURE_TWO_SIDED) > 0;
             const float3 e1 = w1 - w0, e2 = w2 - w0, e3 = w2 - w1;
-            nrm = cross3(e1, e2);
-            nn = dot3(nrm, nrm);
-            emax2 = fmaxf(fmaxf(dot3(e1, e1), dot3(e2, e2)), dot3(e3, e3));
-        }
-    }
-    const bool pretest = P.pretest && active && !two_sided && isfinite(nn) && isfinite(emax2);
-    const float r2lo = 10.f * (P.icut + 1.f) * (P.icut + 1.f), r2hi = 0.8f * RR_DEPTH_FAR * RR_DEPTH_FAR, fov2 = half * half;
-    const unsigned lt = (1u << lane) - 1u;
-
-    int qa = 0, qr = 0;                      // items waiting for stage B / small triangles waiting for stage C (warp-uniform)
-    for (int li = 0; li <= P.n_lights; li++) {
-        const bool last = li == P.n_lights;
-        if (!last) {
-            if (!((light_reach >> li) & 1u)) continue;
-            // ---- stage A
-            const float4 l4 = s_light[li];
-            const float3 lpos = make_float3(l4.x, l4.y, l4.z);
-            const uint32_t face_mask = __float_as_uint(l4.w) & 0x3Fu, reach = reach_of(li);
-            uint32_t faces = 0;
-            const float3 gl = gpos - lpos;
-            if (active && !(dot3(gl, gl) > P.far2_max)) {                                        // length(...) > depth_far, cl2.cl:4472 (far2_max: see ShadowSetupParams)
+            const float3 nrm = cross3(e1, e2);
+            const float nn = dot3(nrm, nrm), emax2 = fmaxf(fmaxf(dot3(e1, e1), dot3(e2, e2)), dot3(e3, e3));
+            const bool pretest = P.pretest && !two_sided && isfinite(nn) && isfinite(emax2);
+            const float r2lo = 10.f * (P.icut + 1.f) * (P.icut + 1.f), r2hi = 0.8f * RR_DEPTH_FAR * RR_DEPTH_FAR, fov2 = half * half;
+#pragma unroll 1
+            for (int li = 0; li < P.n_lights; li++) {
+                if (!((light_reach >> li) & 1u)) continue;
+                const float4 l4 = s_light[li];
+                const float3 lpos = make_float3(l4.x, l4.y, l4.z);
+                const float3 gl = gpos - lpos;
+                if (dot3(gl, gl) > P.far2_max) continue;                                        // length(...) > depth_far, cl2.cl:4472 (far2_max: see ShadowSetupParams)
+                const uint32_t reach = reach_of(li);
+                uint32_t faces;
                 // a cluster whose box reaches a single face: every vertex is assigned that face (the reach is a superset)
                 if ((reach & (reach - 1u)) == 0u) faces = reach;
                 else faces = (1u << ret_cubeface(w0, lpos)) | (1u << ret_cubeface(w1, lpos)) | (1u << ret_cubeface(w2, lpos));   // cl2.cl:4520-4539
-                faces &= face_mask;
+                faces &= __float_as_uint(l4.w) & 0x3Fu;
                 if (faces && pretest && shadow_clearly_back(w0 - lpos, nrm, nn, emax2, fov2, r2lo, r2hi)) faces = 0;
+                if (li < 8) flo |= (unsigned long long)faces << (li * 8); else fhi |= (unsigned long long)faces << ((li - 8) * 8);
             }
-            const int cnt = __popc(faces);
-            const unsigned m1 = __ballot_sync(0xffffffffu, cnt > 0);
-            if (m1) {
-                const unsigned m2 = __ballot_sync(0xffffffffu, cnt > 1);
-                const unsigned short base_item = (unsigned short)(lane | (li << 8) | (two_sided ? 1 << 12 : 0));
-                if (!m2) {                   // the usual case: at most one face per triangle
-                    if (cnt) Q.item[qa + __popc(m1 & lt)] = (unsigned short)(base_item | ((__ffs(faces) - 1) << 5));
-                    qa += __popc(m1);
-                } else {
-                    int inc = cnt;
+        }
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    const int n_groups = (P.n_lights + SQ_GROUP - 1) / SQ_GROUP;
+
+    int qa = 0, qr = 0, g = 0;               // items waiting for stage B / small triangles waiting for stage C / next group of lights (warp-uniform)
+    while (true) {
+        // ---- stage A: the items of the next four lights, once fewer than 32 are waiting
+        if (g < n_groups && qa < 32) {
+            const uint32_t word = (uint32_t)((g < 2 ? flo : fhi) >> ((g & 1) * 32));
+            const int cnt = __popc(word);
+            int inc = cnt;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-                    int at = qa + inc - cnt;
-                    for (uint32_t fm = faces; fm; fm &= fm - 1u) Q.item[at++] = (unsigned short)(base_item | ((__ffs(fm) - 1) << 5));
-                    qa += __shfl_sync(0xffffffffu, inc, 31);
-                }
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            int at = qa + inc - cnt;
+            const uint32_t base_item = (uint32_t)lane | ((uint32_t)(g * SQ_GROUP) << 8) | (two_sided ? 1u << 12 : 0u);
+            for (uint32_t m = word; m; m &= m - 1u) {
+                const uint32_t bpos = (uint32_t)__ffs(m) - 1u;                                  // bit = 8 * light-in-group + face
+                Q.item[at++] = (unsigned short)(base_item + ((bpos >> 3) << 8) + ((bpos & 7u) << 5));
             }
+            qa += __shfl_sync(0xffffffffu, inc, 31);
+            g++;
             __syncwarp();
         }
+        const bool a_done = g >= n_groups;
         // ---- stage B: 32 items at a time (whatever is left after the last light)
-        while (qa >= 32 || (last && qa > 0)) {
+        const bool do_b = qa >= 32 || (a_done && qa > 0);
+        if (do_b) {
             const int take = min(qa, 32);
             qa -= take;
             const bool have = lane < take;
@@ -1226,13 +1253,9 @@ __global__ void RR_LB_SHADOW_SETUP_ATTR k_shadow_setup(const ShadowSetupParams P
                         area = (mm.y - mm.x) * (mm.w - mm.z);
                         small = area >= 1.f && area <= (float)RASTER_SMALL_MAX;                  // one chunk (ceil(area / 300) == 1) of at most 48 slots
                         big = area > (float)RASTER_SMALL_MAX;                                    // (an empty or NaN box produces nothing)
-                        if (small) {
-                            const float cmax = fmaxf(fmaxf(fmaxf(fabsf(xr.x), fabsf(xr.y)), fmaxf(fabsf(xr.z), fabsf(yr.x))), fmaxf(fabsf(yr.y), fabsf(yr.z)));
-                            const float ext = fmaxf(fmaxf(fmaxf(xr.x, xr.y), xr.z) - fminf(fminf(xr.x, xr.y), xr.z), fmaxf(fmaxf(yr.x, yr.y), yr.z) - fminf(fminf(yr.x, yr.y), yr.z));
-                            if (cmax <= 2047.f && ext <= 64.f) {                                  // exact arithmetic from here on (finite: passed the test above)
-                                faceword |= SR_EXACT;
-                                if (det == 0.f) small = false;                                   // collinear after rounding: point_in_tri's s + t < 0 can never hold
-                            }
+                        if (small && tri_exact_arith(xr, yr)) {
+                            faceword |= SR_EXACT;
+                            if (det == 0.f) small = false;                                       // collinear after rounding: point_in_tri's s + t < 0 can never hold
                         }
                     }
                 }
@@ -1253,41 +1276,20 @@ __global__ void RR_LB_SHADOW_SETUP_ATTR k_shadow_setup(const ShadowSetupParams P
             }
             qr += __popc(ms);
             // the rest gets records
-            if (__any_sync(0xffffffffu, big)) {
-                const int n_frag = big ? (int)ceilf(area / (float)RR_OP_SIZE_LIGHT) : 0;
-                uint32_t cid, fbase;
-                warp_alloc2(P.counters, big ? 1u : 0u, (uint32_t)n_frag, cid, fbase);
-                if (big) {
-                    if (cid + 1u > P.cap_cut) atomicOr(&P.counters[CTR_OVERFLOW], 2u);
-                    else if ((unsigned long long)fbase + (uint32_t)n_frag > (unsigned long long)P.cap_frags) atomicOr(&P.counters[CTR_OVERFLOW], 1u);
-                    else {
-                        float4* dst = P.cutdown + (size_t)cid * 3;
-                        dst[0] = make_float4(p0.x, p0.y, p0.z, 0.f);
-                        dst[1] = make_float4(p1.x, p1.y, p1.z, 0.f);
-                        dst[2] = make_float4(p2.x, p2.y, p2.z, 0.f);
-                        const float4 mm = calc_min_max(xr, yr, L, L);
-                        const int width = (int)(mm.y - mm.x), nrows = (int)(mm.w - mm.z);
-                        const int kend = walk_end(width, nrows, 1.f / (float)width, mm.z, mm.w);
-                        const uint32_t word0 = ((uint32_t)l << 8) | (uint32_t)kk;
-                        uint4* rec = reinterpret_cast<uint4*>(P.frags) + fbase;
-                        for (int a = 0; a < n_frag; a++) {
-                            rec[a] = make_uint4(word0, (uint32_t)a, cid, __float_as_uint(rconst));
-                            P.fragcnt[fbase + a] = chunk_slots(kend, a, RR_OP_SIZE_LIGHT);
-                        }
-                    }
-                }
-            }
+            if (__any_sync(0xffffffffu, big))
+                shadow_store_big(P.counters, P.cutdown, P.cap_cut, P.frags, P.cap_frags, P.fragcnt, big, p0, p1, p2, xr, yr, rconst, area, L, ((uint32_t)l << 8) | (uint32_t)kk);
             __syncwarp();
-            // ---- stage C
-            if (qr >= 32) {
-                qr -= 32;
-                shadow_raster_small(Q, qr + lane, true, L, P.buffer);
-                __syncwarp();
-            }
         }
-        if (last) break;
+        // ---- stage C: 32 small triangles at a time (whatever is left once stages A and B are done)
+        const bool do_c = qr >= 32 || (a_done && qa == 0 && qr > 0);
+        if (do_c) {
+            const int take = min(qr, 32);
+            qr -= take;
+            shadow_raster_small(Q, qr + lane, lane < take, L, P.buffer);
+            __syncwarp();
+        }
+        if (a_done && !do_b && !do_c) break;
     }
-    if (qr > 0) shadow_raster_small(Q, lane, lane < qr, L, P.buffer);
 }
 
 // kernel1_realtime_shadowing (cl2.cl:5130-5246) for the fragments k_shadow_setup stored: one warp per fragment, the lanes
@@ -1628,7 +1630,7 @@ struct ShadeParams {
 __device__ __forceinline__ float4 read_tex_pre(float cx, float cy, int which, int slice, float width, const uchar4* __restrict__ atlas) {
     const float ihnum = width * (1.f / 2048);
     float tnumy = floorf((float)which * ihnum);
-    float tnumx = (float)which - ((tnumy == 0.f && ihnum > 0.f) ? tnumy : tnumy / ihnum);   // first tile row: 0 / x == 0 without the division's slow path
+    float tnumx = (float)which - div_pow2(tnumy, ihnum);                // (ihnum = tile size / 2048)
     cx = clampf(cx, 0.001f, width - 0.001f);
     cy = clampf(cy, 0.001f, width - 0.001f);
     int ix = (int)fmaf(tnumx, width, cx), iy = (int)fmaf(tnumy, width, cy);

@@ -61,6 +61,17 @@ __device__ __forceinline__ float3 xyz(float4 v) { return make_float3(v.x, v.y, v
 // saturating float -> uint32 (NaN -> 0, negative -> 0, >= 2^32 -> UINT_MAX): cvt.rzi.u32.f32 does exactly this
 __device__ __forceinline__ uint32_t sat_u32(float f) { return __float2uint_rz(f); }
 
+// a / b for a divisor that is nearly always a power of two (tile size / 2048): multiplying by the exact reciprocal 2^-e gives the
+// correctly rounded quotient, bit for bit, without the IEEE division sequence (whose slow path a zero numerator would take);
+// any other divisor goes through the real division, kept out of line so that it is not evaluated speculatively
+__device__ __noinline__ float div_general(float a, float b) { return a / b; }
+__device__ __forceinline__ float div_pow2(float a, float b) {
+    const uint32_t bb = __float_as_uint(b);
+    // normal power of two whose reciprocal is normal as well
+    if ((bb & 0x807FFFFFu) == 0u && bb >= 0x01000000u && bb <= 0x7E000000u) return a * __uint_as_float(0x7F000000u - bb);
+    return div_general(a, b);
+}
+
 // cl2.cl:220-271
 __device__ __forceinline__ float3 rot(float3 point, float3 c_pos, const RotSC& r) {
     float3 rel = point - c_pos;
