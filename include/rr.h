@@ -139,6 +139,7 @@ int rr_scene_alloc(rr_ctx*, uint32_t n_tris, uint32_t n_objs);                  
 int rr_scene_write_tris(rr_ctx*, uint32_t first, uint32_t count, const rr_triangle* tris);       /* enqueue_write_buffer_async(g_tri_mem) object_context.cpp:409-441 (+ fill_ids cl2.cl:4231 is the caller's job: object_id must be set) */
 int rr_scene_write_objs(rr_ctx*, uint32_t first, uint32_t count, const rr_obj_desc* objs);       /* alloc_object_descriptors object_context.cpp:460-484 */
 int rr_scene_patch_obj(rr_ctx*, uint32_t obj_id, uint32_t byte_off, uint32_t nbytes, const void* src); /* object::g_flush partial writes object.cpp:652-857 */
+int rr_scene_read_objs(rr_ctx*, uint32_t first, uint32_t count, rr_obj_desc* dst);                 /* synchronous read-back of the device descriptors (clEnqueueReadBuffer on g_obj_desc): do_motion_blur updates their motion history on the device */
 
 /* ---- asynchronous rebuild (object_context::build(async) + flip_buffers, object_context.cpp:520-797) ------------------
  * The reference rebuilds a changed scene into `new_gpu_dat` on a second queue while the old one keeps rendering, and flips
@@ -165,6 +166,8 @@ int rr_lights_write(rr_ctx*, const rr_light* lights, uint32_t n_active);        
 /* ---- per frame ------------------------------------------------------------------------------------------------- */
 int rr_frame_shadows(rr_ctx*, int static_lights_dirty);                                          /* engine::generate_realtime_shadowing engine.cpp:1601-1790 */
 int rr_frame_draw(rr_ctx*, const float c_pos[4], const float c_rot[4], const float clear_rgba[4]); /* engine::draw_bulk_objs_n engine.cpp:2356 -> render_tris 1794-2025 */
+int rr_post_motion_blur(rr_ctx*, float strength, float camera_contribution);                     /* engine::do_motion_blur engine.cpp:1518-1538 -> do_motion_blur cl2.cl:6714-6860 (object history in the descriptors advances as there) */
+int rr_post_godrays(rr_ctx*);                                                                    /* engine::draw_godrays engine.cpp:1463-1482 -> screenspace_godrays cl2.cl:1792-1917; no-op unless a light has godray_intensity > 0 */
 int rr_post_pseudo_aa(rr_ctx*);                                                                  /* engine::do_pseudo_aa engine.cpp:1513 -> do_pseudo_aa cl2.cl:6437-6657; after rr_frame_draw, whole-frame contexts only */
 int rr_swap_buffers(rr_ctx*);                                                                    /* object_context_data::swap_buffers object_context.cpp:17-25 */
 int rr_sync(rr_ctx*);                                                                            /* cl::cqueue.finish(); reports RR_ERR_OVERFLOW */

@@ -108,6 +108,9 @@ _SIGS = {
     "frame_draw": (C.c_int, [_P, _F4, _F4, _F4]),
     "swap_buffers": (C.c_int, [_P]),
     "post_pseudo_aa": (C.c_int, [_P]),
+    "post_motion_blur": (C.c_int, [_P, C.c_float, C.c_float]),
+    "post_godrays": (C.c_int, [_P]),
+    "scene_read_objs": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
     "sync": (C.c_int, [_P]),
     "read_depth": (C.c_int, [_P, _P]),
     "read_ids": (C.c_int, [_P, _P]),
@@ -244,6 +247,21 @@ class CApi:
     def post_pseudo_aa(self):
         """engine::do_pseudo_aa: edge smoothing of the frame just drawn (before swap_buffers)"""
         self._call("post_pseudo_aa")
+
+    def post_motion_blur(self, strength=1.0, camera_contribution=1.0):
+        """engine::do_motion_blur: blur along each pixel's screen-space motion since the previous frame (before swap_buffers)"""
+        self._call("post_motion_blur", float(strength), float(camera_contribution))
+
+    def post_godrays(self):
+        """engine::draw_godrays: screen-space light shafts of the lights with godray_intensity > 0 (before swap_buffers)"""
+        self._call("post_godrays")
+
+    def scene_read_objs(self, first, count):
+        """the device copy of the descriptors (do_motion_blur advances their motion history)"""
+        out = np.zeros(count, dtype=OBJ_DESC)
+        if count:
+            self._call("scene_read_objs", first, count, _ptr(out))
+        return out
 
     def swap_buffers(self):
         self._call("swap_buffers")

@@ -137,7 +137,13 @@ struct rr_ctx {
     cudaEvent_t ev_draw_done = nullptr, ev_copy_done[RR_RING_MAX] = {};
     bool copy_pending[RR_RING_MAX] = {};
     ushort2* d_normals = nullptr;
-    uchar4* d_post = nullptr;                    // second colour target of the post passes (rr_post_pseudo_aa)
+    uchar4* d_post = nullptr;                    // second colour target of the post passes (rr_post_*)
+    // what the post passes are handed besides the G-buffer: the camera of the last rr_frame_draw, the one before it
+    // (object_context_data::c_pos_old, set at swap_buffers, object_context.cpp:23-24) and object_context_data::frame_id (engine.cpp:2024)
+    CamParams cam_last = {}, cam_old = {};
+    uint32_t frame_id = 0;
+    uint8_t* d_seen = nullptr;                   // per object: visible in the frame being blurred (do_motion_blur's history update)
+    uint32_t seen_cap = 0;
     uint32_t* d_shade_list = nullptr;            // compacted covered pixels
     uint2* d_samples = nullptr;                  // covered samples of inline-rasterised triangles (pixel, depth)
     uint32_t* d_sample_frag = nullptr;           // ... and the fragment index of each sample
@@ -413,7 +419,7 @@ static int preload_kernels() {
         (const void*)k_ids_list, (const void*)k_shadow_setup, (const void*)k_cluster_faces,
         (const void*)k_signal_flag, (const void*)k_signal_flags, (const void*)k_wait_flags, (const void*)k_push_faces, (const void*)k_fill_faces,
         (const void*)k_raster_shadow_warp, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip,
-        (const void*)k_shade_pre, (const void*)k_shade_pre4, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_copy_u32,
+        (const void*)k_shade_pre, (const void*)k_shade_pre4, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_motion_blur, (const void*)k_motion_history, (const void*)k_godrays, (const void*)k_copy_u32,
     };
     for (const void* f : fns) {
         cudaFuncAttributes a;
@@ -472,6 +478,8 @@ rr_ctx* rr_create(const rr_config* cfg) {
     c->fov = cfg->fov_const > 0 ? cfg->fov_const : rr_fov_const_from_hfov(cfg->hfov_deg, (float)cfg->width);
     c->sm_count = prop.multiProcessorCount;
     c->faces = make_face_table();
+    c->cam_last.pos = c->cam_old.pos = make_float3(0.f, 0.f, 0.f);       // c_pos_old / c_rot_old start at zero (object_context.hpp:89-90): angle 0, not a zero matrix
+    c->cam_last.rot = c->cam_old.rot = make_rotsc(0.f, 0.f, 0.f);
     c->cluster_cull = cfg->cluster_cull;
     if (const char* e = getenv("RR_SHADOW_PRETEST")) c->shadow_pretest = atoi(e) != 0;
     auto bail = [&](const char* what) { fail(RR_ERR_CUDA, "rr_create: %s: %s", what, cudaGetErrorString(cudaGetLastError())); rr_destroy(c); return (rr_ctx*)nullptr; };
@@ -552,7 +560,7 @@ void rr_destroy(rr_ctx* c) {
     for (int i = 0; i < 2; i++) { cudaFree(c->d_depth[i]); cudaFree(c->d_ids[i]); }
     if (!c->ext_rgba8) cudaFree(c->d_rgba8);
     cudaFree(c->d_fragcnt); cudaFree(c->d_worklist); cudaFree(c->d_extra);
-    cudaFree(c->d_post);
+    cudaFree(c->d_post); cudaFree(c->d_seen);
     cudaFree(c->d_normals); cudaFree(c->d_shade_list); cudaFree(c->d_samples); cudaFree(c->d_sample_frag); cudaFree(c->d_frags); cudaFree(c->d_cutdown); cudaFree(c->d_counters); cudaFree(c->d_lookback);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_objs_pinned) cudaFreeHost(c->h_objs_pinned);
@@ -639,6 +647,15 @@ int rr_scene_patch_obj(rr_ctx* c, uint32_t obj_id, uint32_t byte_off, uint32_t n
 }
 
 // ---- asynchronous rebuild: object_context::build(async) + flip_buffers (object_context.cpp:520-797) ------------------
+int rr_scene_read_objs(rr_ctx* c, uint32_t first, uint32_t count, rr_obj_desc* dst) {
+    if (!c || (!dst && count)) return fail(RR_ERR_INVALID, "null argument");
+    if ((uint64_t)first + count > c->n_objs) return fail(RR_ERR_INVALID, "rr_scene_read_objs: range outside the %u objects", c->n_objs);
+    if (!count) return RR_OK;
+    CU(cudaMemcpyAsync(dst, c->d_objs + first, (size_t)count * sizeof(rr_obj_desc), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+
 static int join_shadows_fwd(rr_ctx* c);
 namespace {
 int back_alloc_bytes(void** p, size_t bytes) {   // plain cudaMalloc: only called when the back scene has to grow
@@ -1110,22 +1127,22 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     if (mg_composite && c->mg.rank == 0 && (r = mg_wait(c, c->stream, false, c->mg.draw_epoch))) return r;             // composite complete
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SHADE], c->stream));
     c->have_frame_ev = c->stage_events;
+    c->cam_last = cam;
+    c->frame_id++;                                                                         // engine.cpp:2024
     CU(cudaGetLastError());
     return RR_OK;
 }
 
-// engine::do_pseudo_aa, engine.cpp:1513-1516 — after rr_frame_draw, before rr_swap_buffers
-int rr_post_pseudo_aa(rr_ctx* c) {
+// ---- post passes on the G-buffer (after rr_frame_draw, before rr_swap_buffers) ------------------------------------------------
+// Every pass reads the colour target and writes the second one (d_post), which then takes its place.
+static int post_begin(rr_ctx* c, const char* who) {
     if (!c) return fail(RR_ERR_INVALID, "null ctx");
-    if (c->mg.connected || c->banded) return fail(RR_ERR_INVALID, "rr_post_pseudo_aa: needs the whole frame's depth and normals on one context");
-    if (c->n_tris == 0) return RR_OK;
+    if (c->mg.connected || c->banded) return fail(RR_ERR_INVALID, "%s: needs the whole frame's G-buffer on one context", who);
+    if (!c->d_post) CU(cudaMalloc((void**)&c->d_post, (size_t)c->W * c->H * 4));
+    return RR_OK;
+}
+static int post_publish(rr_ctx* c) {
     const size_t P = (size_t)c->W * c->H;
-    if (!c->d_post) CU(cudaMalloc((void**)&c->d_post, P * 4));
-    const float aa_arg = 20.f * 2 * RR_PI_F / 360.f;
-    const float cosrad = (float)cos((double)aa_arg);                  // cos() pinned: double on the host, rounded to float
-    dim3 grid((c->W + 31) / 32, (c->H + 7) / 8);
-    k_pseudo_aa<<<grid, 256, 0, c->stream>>>(c->d_rgba8, c->d_post, c->d_depth[c->cur], c->d_normals, c->W, c->H, cosrad);
-    c->launches++;
     CU(cudaGetLastError());
     if (c->ext_rgba8) {                                               // caller-owned target: put the result back where the caller expects it
         k_copy_u32<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_post), reinterpret_cast<uint4*>(c->d_rgba8), P / 4,
@@ -1139,9 +1156,63 @@ int rr_post_pseudo_aa(rr_ctx* c) {
     return RR_OK;
 }
 
+// engine::do_pseudo_aa, engine.cpp:1513-1516
+int rr_post_pseudo_aa(rr_ctx* c) {
+    int r;
+    if ((r = post_begin(c, "rr_post_pseudo_aa"))) return r;
+    if (c->n_tris == 0) return RR_OK;
+    const float aa_arg = 20.f * 2 * RR_PI_F / 360.f;
+    const float cosrad = (float)cos((double)aa_arg);                  // cos() pinned: double on the host, rounded to float
+    dim3 grid((c->W + 31) / 32, (c->H + 7) / 8);
+    k_pseudo_aa<<<grid, 256, 0, c->stream>>>(c->d_rgba8, c->d_post, c->d_depth[c->cur], c->d_normals, c->W, c->H, cosrad);
+    c->launches++;
+    return post_publish(c);
+}
+
+// engine::do_motion_blur, engine.cpp:1518-1538
+int rr_post_motion_blur(rr_ctx* c, float strength, float camera_contribution) {
+    int r;
+    if ((r = post_begin(c, "rr_post_motion_blur"))) return r;
+    if (c->n_tris == 0 || c->n_objs == 0) return RR_OK;
+    if (c->seen_cap < c->n_objs) {
+        if (c->d_seen) cudaFree(c->d_seen);
+        CU(cudaMalloc((void**)&c->d_seen, c->n_objs));
+        CU(cudaMemsetAsync(c->d_seen, 0, c->n_objs, c->stream));
+        c->seen_cap = c->n_objs;
+    }
+    MotionBlurParams mp;
+    mp.in = c->d_rgba8; mp.out = c->d_post; mp.depth = c->d_depth[c->cur]; mp.ids = c->d_ids[c->cur]; mp.frags = c->d_frags; mp.n_frags = c->d_counters + CTR_NFRAG;
+    mp.objs = c->d_objs; mp.n_objs = c->n_objs; mp.seen = c->d_seen;
+    mp.cam = c->cam_last; mp.cam_old = c->cam_old;
+    mp.W = c->W; mp.H = c->H; mp.fov = c->fov; mp.icut = (float)c->cfg.depth_icutoff; mp.strength = strength; mp.camera_contribution = camera_contribution;
+    mp.frame_id = c->frame_id;
+    dim3 grid((c->W + 31) / 32, (c->H + 7) / 8);
+    k_motion_blur<<<grid, 256, 0, c->stream>>>(mp);
+    k_motion_history<<<(c->n_objs + 127) / 128, 128, 0, c->stream>>>(c->d_objs, c->n_objs, c->d_seen, c->frame_id);
+    c->launches += 2;
+    return post_publish(c);
+}
+
+// engine::draw_godrays, engine.cpp:1463-1482 (nothing to do unless a light has godray_intensity > 0: light_data->any_godray)
+int rr_post_godrays(rr_ctx* c) {
+    int r;
+    if ((r = post_begin(c, "rr_post_godrays"))) return r;
+    bool any = false;
+    for (const rr_light& l : c->lights) any = any || l.godray_intensity > 0;
+    if (!any) return RR_OK;
+    GodrayParams gp;
+    gp.in = c->d_rgba8; gp.out = c->d_post; gp.depth = c->d_depth[c->cur]; gp.lights = c->d_lights; gp.n_lights = (int)c->lights.size();
+    gp.cam = c->cam_last; gp.W = c->W; gp.H = c->H; gp.fov = c->fov;
+    dim3 grid((c->W + 31) / 32, (c->H + 7) / 8);
+    k_godrays<<<grid, 256, 0, c->stream>>>(gp);
+    c->launches++;
+    return post_publish(c);
+}
+
 int rr_swap_buffers(rr_ctx* c) {
     if (!c) return fail(RR_ERR_INVALID, "null ctx");
     c->cur ^= 1;                                           // depth_buffer.flip(), object_context.cpp:21
+    c->cam_old = c->cam_last;                              // c_pos_old / c_rot_old, object_context.cpp:23-24
     return RR_OK;
 }
 

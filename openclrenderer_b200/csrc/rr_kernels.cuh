@@ -2113,6 +2113,157 @@ __global__ void __launch_bounds__(256) k_pseudo_aa(const uchar4* __restrict__ in
     out[px] = res;
 }
 
+// =====================================================================================================================
+// do_motion_blur (cl2.cl:6714-6860) and screenspace_godrays (cl2.cl:1792-1917): the other post passes on the G-buffer.
+// Both read the frame kernel3 produced (`in`) through the CLK_FILTER_LINEAR formula of the OpenCL specification (§8.2,
+// unnormalised coordinates: i0 = floor(u - 0.5), a = frac(u - 0.5), four taps, clamped to the image) and write every pixel
+// to a second target (`out`), which then becomes the colour target — the reference runs godrays in place on one image
+// (engine.cpp:1471-1476), motion blur from gl_screen[1] into gl_screen[0] (engine.cpp:1520-1521). Streaming gather kernels,
+// HBM / L2 bound: 4 B/pixel in and out plus the taps.
+// =====================================================================================================================
+__device__ __forceinline__ float4 sample_linear_rgba8(const uchar4* __restrict__ img, int W, int H, float u, float v) {
+    const float fu = u - 0.5f, fv = v - 0.5f;
+    const float i0f = floorf(fu), j0f = floorf(fv);
+    const float a = fu - i0f, b = fv - j0f;
+    const int i0 = (int)clampf(i0f, 0.f, (float)(W - 1)), i1 = (int)clampf(i0f + 1.f, 0.f, (float)(W - 1));
+    const int j0 = (int)clampf(j0f, 0.f, (float)(H - 1)), j1 = (int)clampf(j0f + 1.f, 0.f, (float)(H - 1));
+    auto T = [&](int i, int j) { const uchar4 t = __ldg(img + (size_t)j * W + i); return make_float4((float)t.x / 255.f, (float)t.y / 255.f, (float)t.z / 255.f, (float)t.w / 255.f); };
+    const float4 t00 = T(i0, j0), t10 = T(i1, j0), t01 = T(i0, j1), t11 = T(i1, j1);
+    return (t00 * (1.f - a) + t10 * a) * (1.f - b) + (t01 * (1.f - a) + t11 * a) * b;
+}
+__device__ __forceinline__ uchar4 quant_rgba8(float4 c) { return make_uchar4(quant8(c.x), quant8(c.y), quant8(c.z), quant8(c.w)); }
+
+struct MotionBlurParams {
+    const uchar4* in; uchar4* out;
+    const uint32_t* depth; const uint32_t* ids; const uint32_t* frags; const uint32_t* n_frags;
+    const rr_obj_desc* objs; uint32_t n_objs; uint8_t* seen;
+    CamParams cam, cam_old;
+    int W, H; float fov, icut, strength, camera_contribution;
+    uint32_t frame_id;
+};
+
+__global__ void __launch_bounds__(256) k_motion_blur(const MotionBlurParams P) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.W || y >= P.H) return;
+    const int W = P.W, H = P.H;
+    const float Wf = (float)W, Hf = (float)H, fov = P.fov;
+    const size_t px = (size_t)y * W + x;
+    const uchar4 mine = P.in[px];
+    const uint32_t dbuf_val = P.depth[px];
+    const uint32_t idv = dbuf_val != 0xFFFFFFFFu ? P.ids[px] : 0u;
+    uint32_t o_id = 0xFFFFFFFFu;
+    if (idv != 0u && idv <= P.n_frags[0]) o_id = __ldg(P.frags + (size_t)(idv - 1u) * RR_FRAG_WORDS + 4);
+    if (o_id >= P.n_objs) { P.out[px] = mine; return; }                  // nothing drawn here (or an unresolved id, q7): the frame's colour stays
+    const rr_obj_desc* G = P.objs + o_id;
+    const float actual_depth = ((float)dbuf_val * RR_INV_U32MAXF) * RR_DEPTH_FAR;
+    const float3 local_position = make_float3((((float)x - Wf / 2.0f) * actual_depth / fov), (((float)y - Hf / 2.0f) * actual_depth / fov), actual_depth);
+    float3 global_position = back_rot(local_position, make_float3(0, 0, 0), P.cam.rot);
+    global_position = global_position + P.cam.pos;
+    float3 object_local = global_position - make_float3(G->world_pos[0], G->world_pos[1], G->world_pos[2]);
+    object_local = rot_quat_n(object_local, back_quat(make_float4(G->world_rot_quat[0], G->world_rot_quat[1], G->world_rot_quat[2], G->world_rot_quat[3])));
+    const bool even = (P.frame_id & 1u) == 0u;
+    const float* owp = even ? G->old_world_pos_1 : G->old_world_pos_2;
+    const float* owq = even ? G->old_world_rot_quat_1 : G->old_world_rot_quat_2;
+    P.seen[o_id] = 1;                                                    // its history advances after the pass (k_motion_history)
+    float3 last_frame_pos = rot_quat(object_local, make_float4(owq[0], owq[1], owq[2], owq[3]));
+    last_frame_pos = last_frame_pos + make_float3(owp[0], owp[1], owp[2]);
+    float3 last_frame_no_camera = rot(last_frame_pos, P.cam.pos, P.cam.rot);
+    last_frame_pos = rot(last_frame_pos, P.cam_old.pos, P.cam_old.rot);
+    last_frame_no_camera = project(last_frame_no_camera, Wf / 2.f, Hf / 2.f, fov);
+    last_frame_pos = project(last_frame_pos, Wf / 2.f, Hf / 2.f, fov);
+    if (last_frame_pos.z < P.icut) { P.out[px] = quant_rgba8(sample_linear_rgba8(P.in, W, H, (float)x + 0.5f, (float)y + 0.5f)); return; }
+    const float2 current_screen_pos = make_float2((float)x, (float)y);
+    float2 to_me_vector = current_screen_pos - make_float2(last_frame_pos.x, last_frame_pos.y);
+    const float2 to_me_nocamera = current_screen_pos - make_float2(last_frame_no_camera.x, last_frame_no_camera.y);
+    to_me_vector = to_me_vector * P.camera_contribution + to_me_nocamera * (1.f - P.camera_contribution);
+    to_me_vector = to_me_vector * P.strength;
+    int n = (int)(fmaxf(fabsf(to_me_vector.x), fabsf(to_me_vector.y)) + 1);
+    const int bound = 50;
+    if (n > bound) {
+        to_me_vector = make_float2(to_me_vector.x / (float)n, to_me_vector.y / (float)n);
+        to_me_vector = to_me_vector * (float)bound;
+        n = bound;
+    }
+    float2 diff = make_float2(0, 0);
+    if (n != 0) diff = make_float2(to_me_vector.x / (float)n, to_me_vector.y / (float)n);
+    float2 current = current_screen_pos - make_float2(to_me_vector.x / 2.f, to_me_vector.y / 2.f);
+    float4 accum = make_float4(0, 0, 0, 0);
+    float fcount = 0;
+    for (int i = 0; i < n; i++, current = current + diff) {
+        if (current.x < 0 || current.x >= Wf || current.y < 0 || current.y >= Hf) continue;
+        accum = accum + sample_linear_rgba8(P.in, W, H, current.x + 0.5f, current.y + 0.5f) * 1.f;
+        fcount += 1.f;
+    }
+    if (fcount != 0) accum = accum / fcount;
+    P.out[px] = quant_rgba8(accum);
+}
+
+// the history half of do_motion_blur (cl2.cl:6768-6784): objects seen in at least one pixel store their current placement in
+// the slot the NEXT frame reads
+__global__ void __launch_bounds__(128) k_motion_history(rr_obj_desc* __restrict__ objs, uint32_t n_objs, uint8_t* __restrict__ seen, uint32_t frame_id) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_objs || !seen[i]) return;
+    seen[i] = 0;
+    rr_obj_desc& G = objs[i];
+    float* dp = (frame_id & 1u) == 0u ? G.old_world_pos_2 : G.old_world_pos_1;
+    float* dq = (frame_id & 1u) == 0u ? G.old_world_rot_quat_2 : G.old_world_rot_quat_1;
+    dp[0] = G.world_pos[0]; dp[1] = G.world_pos[1]; dp[2] = G.world_pos[2];
+    dq[0] = G.world_rot_quat[0]; dq[1] = G.world_rot_quat[1]; dq[2] = G.world_rot_quat[2]; dq[3] = G.world_rot_quat[3];
+}
+
+struct GodrayParams {
+    const uchar4* in; uchar4* out; const uint32_t* depth;
+    const rr_light* lights; int n_lights;
+    CamParams cam; int W, H; float fov;
+};
+
+__global__ void __launch_bounds__(256) k_godrays(const GodrayParams P) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.W || y >= P.H) return;
+    const int W = P.W, H = P.H;
+    const float Wf = (float)W, Hf = (float)H;
+    const size_t px = (size_t)y * W + x;
+    const float samples = 80.f;
+    const uint32_t my_depth = P.depth[px];
+    float4 my_col = sample_linear_rgba8(P.in, W, H, (float)x - 0.25f, (float)y - 0.25f);
+    const float decay_factor = 0.97f, weight = 0.01f, max_length = 400.f;
+    for (int i = 0; i < P.n_lights; i++) {
+        const rr_light* l = P.lights + i;
+        const float ray_intensity = __ldg(&l->godray_intensity);
+        if (ray_intensity <= 0) continue;
+        float idecay = 1.f;
+        float3 iter_col = make_float3(0, 0, 0);
+        float3 slpos = rot(make_float3(__ldg(&l->pos[0]), __ldg(&l->pos[1]), __ldg(&l->pos[2])), P.cam.pos, P.cam.rot);
+        slpos = project(slpos, Wf / 2.f, Hf / 2.f, P.fov);
+        float3 current_pos = make_float3((float)x, (float)y, ((float)my_depth * RR_INV_U32MAXF) * RR_DEPTH_FAR);
+        float3 destination_pos = slpos;
+        const float3 original = current_pos;
+        if (slpos.z < 0) destination_pos = (current_pos - destination_pos) + current_pos;
+        const float vx = fabsf(current_pos.x - destination_pos.x), vy = fabsf(current_pos.y - destination_pos.y);
+        const float mnum = vx > vy ? vx : vy;
+        float3 dir = (destination_pos - current_pos) / mnum;
+        dir = dir * (max_length / samples);
+        const float3 col = make_float3(__ldg(&l->col[0]), __ldg(&l->col[1]), __ldg(&l->col[2]));
+        for (int j = 0; (float)j < mnum && (float)j < samples; j++) {
+            if (current_pos.x < 0 || current_pos.y < 0 || current_pos.x >= Wf - 1 || current_pos.y >= Hf - 1) continue;
+            const uint32_t cdepth = __ldg(P.depth + (size_t)((int)current_pos.y) * W + (int)current_pos.x);
+            const float fdepth = ((float)cdepth * RR_INV_U32MAXF) * RR_DEPTH_FAR;
+            float3 val = make_float3(0, 0, 0);
+            if (fdepth < original.z - 5 && cdepth != 0xFFFFFFFFu) {
+                idecay *= 0.9f;
+                val = col * ray_intensity;
+            }
+            val = val * idecay * weight;
+            iter_col = iter_col + val;
+            idecay *= decay_factor;
+            current_pos = current_pos + dir;
+        }
+        my_col.x += iter_col.x; my_col.y += iter_col.y; my_col.z += iter_col.z;
+    }
+    my_col.w = 1;
+    P.out[px] = quant_rgba8(my_col * 0.99f);
+}
+
 __global__ void k_lightlite(const rr_light* __restrict__ lights, uint32_t n, LightLite* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -337,6 +337,10 @@ struct orc_ctx {
     uint64_t depth_samples = 0;       // covered depth samples of the last main pass (A_depth)
     uint64_t shadow_samples = 0;      // A_shadow
     uint64_t sat_events = 0;          // float->uint conversions that saturated (hard part 4)
+    // camera of the last orc_frame_draw and of the frame before it (object_context_data::c_pos_old, object_context.cpp:23-24),
+    // and object_context_data::frame_id (engine.cpp:2024) — what the post passes are handed
+    float cam_pos[4] = {0, 0, 0, 0}, cam_rot[4] = {0, 0, 0, 0}, cam_pos_old[4] = {0, 0, 0, 0}, cam_rot_old[4] = {0, 0, 0, 0};
+    uint32_t frame_id = 0;
 };
 
 namespace {
@@ -1113,6 +1117,165 @@ void pseudo_aa(orc_ctx* c) {
     }
 }
 
+// ---- CLK_FILTER_LINEAR read of the colour target (OpenCL 1.2 §8.2, unnormalised coordinates) -------------------------
+// (u, v) -> i0 = floor(u - 0.5), a = frac(u - 0.5), likewise j0 / b; T = texel / 255;
+// result = (1-a)(1-b) T[i0,j0] + a(1-b) T[i0+1,j0] + (1-a)b T[i0,j0+1] + ab T[i0+1,j0+1].
+// Taps are clamped to the image: that is CLK_ADDRESS_CLAMP_TO_EDGE (godrays); do_motion_blur's CLK_ADDRESS_NONE reads are
+// in range except for the +1 tap on the last column / row, which the specification leaves undefined — clamped here.
+// The reference's image is float (GL RGBA16 / half); the headless target is RGBA8, so the taps are the quantised colours.
+inline f4 sample_linear_rgba8(const std::vector<uint8_t>& img, int W, int H, float u, float v) {
+    const float fu = u - 0.5f, fv = v - 0.5f;
+    const float i0f = floorf(fu), j0f = floorf(fv);
+    const float a = fu - i0f, b = fv - j0f;
+    const int i0 = (int)cl_clamp(i0f, 0.f, (float)(W - 1)), i1 = (int)cl_clamp(i0f + 1.f, 0.f, (float)(W - 1));
+    const int j0 = (int)cl_clamp(j0f, 0.f, (float)(H - 1)), j1 = (int)cl_clamp(j0f + 1.f, 0.f, (float)(H - 1));
+    auto T = [&](int i, int j) { const uint8_t* t = &img[((size_t)j * W + i) * 4]; return f4{t[0] / 255.f, t[1] / 255.f, t[2] / 255.f, t[3] / 255.f}; };
+    const f4 t00 = T(i0, j0), t10 = T(i1, j0), t01 = T(i0, j1), t11 = T(i1, j1);
+    return (t00 * (1.f - a) + t10 * a) * (1.f - b) + (t01 * (1.f - a) + t11 * a) * b;
+}
+inline void store_rgba8(std::vector<uint8_t>& img, size_t px, f4 col) {
+    const float o[4] = {col.x, col.y, col.z, col.w};
+    for (int k = 0; k < 4; k++) img[px * 4 + k] = (uint8_t)(cl_clamp(o[k], 0.f, 1.f) * 255.f + 0.5f);
+}
+
+// ---- do_motion_blur, cl2.cl:6714-6860 ------------------------------------------------------------------------------------
+// in_screen = gl_screen[1], back_screen = gl_screen[0] (engine.cpp:1520-1521): kernel3 wrote the frame to both, so a pixel this
+// pass does not write keeps the frame's colour. Covered pixels whose id did not resolve are treated like uncovered ones
+// (the reference would follow a stale id, q7). The kernel also advances the motion history of every object it sees
+// (old_world_pos_1/2 ping-pong on frame_id parity, racing identical stores): applied after the pass here.
+void motion_blur(orc_ctx* c, float strength, float camera_contribution) {
+    const int W = c->W, H = c->H;
+    const float Wf = (float)W, Hf = (float)H, fov = c->fov;
+    const uint32_t* depth_buffer = c->depth[c->cur].data();
+    const std::vector<uint8_t> in = c->rgba8;
+    const rotsc crot = make_rotsc(c->cam_rot[0], c->cam_rot[1], c->cam_rot[2]), crot_old = make_rotsc(c->cam_rot_old[0], c->cam_rot_old[1], c->cam_rot_old[2]);
+    const f3 cpos = v3(c->cam_pos), cpos_old = v3(c->cam_pos_old);
+    const uint32_t frame_id = c->frame_id;
+    std::vector<uint8_t> seen(c->objs.size(), 0);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(c->threads)
+    for (int y = 0; y < H; y++) {
+        for (int x = 0; x < W; x++) {
+            const size_t px = (size_t)y * W + x;
+            const uint32_t dbuf_val = depth_buffer[px];
+            if (dbuf_val == 0xFFFFFFFFu) continue;
+            const uint32_t idv = c->ids[px];
+            if (idv == 0u || idv > c->n_frags) continue;
+            const uint32_t o_id = c->frags[(size_t)(idv - 1u) * FRAG_MUL + 4];
+            if (o_id >= c->objs.size()) continue;
+            const rr_obj_desc& G = c->objs[o_id];
+            const float actual_depth = ((float)dbuf_val / U32MAXF) * DEPTH_FAR;
+            const f3 local_position = {((x - Wf / 2.0f) * actual_depth / fov), ((y - Hf / 2.0f) * actual_depth / fov), actual_depth};
+            f3 global_position = back_rot(local_position, {0, 0, 0}, crot);
+            global_position = global_position + cpos;
+            f3 object_local = global_position - v3(G.world_pos);
+            object_local = back_rot_quat(object_local, f4{G.world_rot_quat[0], G.world_rot_quat[1], G.world_rot_quat[2], G.world_rot_quat[3]});
+            const float* owp = (frame_id & 1) == 0 ? G.old_world_pos_1 : G.old_world_pos_2;
+            const float* owq = (frame_id & 1) == 0 ? G.old_world_rot_quat_1 : G.old_world_rot_quat_2;
+            seen[o_id] = 1;
+            f3 last_frame_pos = rot_quat(object_local, f4{owq[0], owq[1], owq[2], owq[3]});
+            last_frame_pos = last_frame_pos + v3(owp);
+            f3 last_frame_no_camera = rot(last_frame_pos, cpos, crot);
+            last_frame_pos = rot(last_frame_pos, cpos_old, crot_old);
+            last_frame_no_camera = depth_project_singular(last_frame_no_camera, Wf, Hf, fov);
+            last_frame_pos = depth_project_singular(last_frame_pos, Wf, Hf, fov);
+            if (last_frame_pos.z < (float)c->cfg.depth_icutoff) {
+                store_rgba8(c->rgba8, px, sample_linear_rgba8(in, W, H, (float)x + 0.5f, (float)y + 0.5f));
+                continue;
+            }
+            const f2 current_screen_pos = {(float)x, (float)y};
+            f2 to_me_vector = current_screen_pos - f2{last_frame_pos.x, last_frame_pos.y};
+            const f2 to_me_nocamera = current_screen_pos - f2{last_frame_no_camera.x, last_frame_no_camera.y};
+            to_me_vector = to_me_vector * camera_contribution + to_me_nocamera * (1.f - camera_contribution);
+            to_me_vector = to_me_vector * strength;
+            int n = (int)(cl_max(fabsf(to_me_vector.x), fabsf(to_me_vector.y)) + 1);
+            const int bound = 50;
+            if (n > bound) {
+                to_me_vector = {to_me_vector.x / (float)n, to_me_vector.y / (float)n};
+                to_me_vector = to_me_vector * (float)bound;
+                n = bound;
+            }
+            f2 diff = {0, 0};
+            if (n != 0) diff = {to_me_vector.x / (float)n, to_me_vector.y / (float)n};
+            f2 current = current_screen_pos - f2{to_me_vector.x / 2.f, to_me_vector.y / 2.f};
+            f4 accum = {0, 0, 0, 0};
+            float fcount = 0;
+            for (int i = 0; i < n; i++, current = current + diff) {
+                if (current.x < 0 || current.x >= Wf || current.y < 0 || current.y >= Hf) continue;
+                const float w = 1;
+                const f4 col = sample_linear_rgba8(in, W, H, current.x + 0.5f, current.y + 0.5f);
+                accum = accum + col * w;
+                fcount += w;
+            }
+            if (fcount != 0) accum = accum / fcount;
+            store_rgba8(c->rgba8, px, accum);
+        }
+    }
+    for (size_t o = 0; o < c->objs.size(); o++) {
+        if (!seen[o]) continue;
+        rr_obj_desc& G = c->objs[o];
+        if ((frame_id & 1) == 0) { memcpy(G.old_world_pos_2, G.world_pos, 12); memcpy(G.old_world_rot_quat_2, G.world_rot_quat, 16); }
+        else { memcpy(G.old_world_pos_1, G.world_pos, 12); memcpy(G.old_world_rot_quat_1, G.world_rot_quat, 16); }
+    }
+}
+
+// ---- screenspace_godrays, cl2.cl:1792-1917 -------------------------------------------------------------------------------
+// The reference runs it in place (screen_in == screen_out == gl_screen[0], engine.cpp:1471-1476); canonical here as for
+// do_pseudo_aa: every read sees the frame as it was before the pass.
+void godrays(orc_ctx* c) {
+    const int W = c->W, H = c->H;
+    const float Wf = (float)W, Hf = (float)H, fov = c->fov;
+    const uint32_t* depth_buffer = c->depth[c->cur].data();
+    const std::vector<uint8_t> in = c->rgba8;
+    const rotsc crot = make_rotsc(c->cam_rot[0], c->cam_rot[1], c->cam_rot[2]);
+    const f3 cpos = v3(c->cam_pos);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(c->threads)
+    for (int y = 0; y < H; y++) {
+        for (int x = 0; x < W; x++) {
+            const size_t px = (size_t)y * W + x;
+            const float samples = 80.f;
+            const uint32_t my_depth = depth_buffer[px];
+            f4 my_col = sample_linear_rgba8(in, W, H, (float)x - 0.25f, (float)y - 0.25f);
+            const float decay_factor = 0.97f, weight = 0.01f, max_length = 400.f;
+            for (size_t i = 0; i < c->lights.size(); i++) {
+                const rr_light& l = c->lights[i];
+                const float ray_intensity = l.godray_intensity;
+                if (ray_intensity <= 0) continue;
+                float idecay = 1.f;
+                f3 iter_col = {0, 0, 0};
+                f3 slpos = rot(v3(l.pos), cpos, crot);
+                slpos = depth_project_singular(slpos, Wf, Hf, fov);
+                f3 current_pos = {(float)x, (float)y, ((float)my_depth / U32MAXF) * DEPTH_FAR};
+                f3 destination_pos = slpos;
+                const f3 original = current_pos;
+                if (slpos.z < 0) destination_pos = (current_pos - destination_pos) + current_pos;
+                const float vx = fabsf(current_pos.x - destination_pos.x), vy = fabsf(current_pos.y - destination_pos.y);
+                const float mnum = vx > vy ? vx : vy;
+                f3 dir = (destination_pos - current_pos) / mnum;
+                dir = dir * (max_length / samples);
+                const f3 col = v3(l.col);
+                for (int j = 0; (float)j < mnum && (float)j < samples; j++) {
+                    if (current_pos.x < 0 || current_pos.y < 0 || current_pos.x >= Wf - 1 || current_pos.y >= Hf - 1) continue;
+                    const uint32_t cdepth = depth_buffer[(size_t)((int)current_pos.y) * W + (int)current_pos.x];
+                    const float fdepth = ((float)cdepth / U32MAXF) * DEPTH_FAR;
+                    f3 val = {0, 0, 0};
+                    if (fdepth < original.z - 5 && cdepth != 0xFFFFFFFFu) {
+                        idecay *= 0.9f;
+                        val = col * ray_intensity;
+                    }
+                    val = val * idecay * weight;
+                    iter_col = iter_col + val;
+                    idecay *= decay_factor;
+                    current_pos = current_pos + dir;
+                }
+                my_col.x += iter_col.x; my_col.y += iter_col.y; my_col.z += iter_col.z;
+            }
+            my_col.w = 1;
+            const float exposure = 0.99f;
+            store_rgba8(c->rgba8, px, my_col * exposure);
+        }
+    }
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -1261,6 +1424,8 @@ int orc_frame_draw(orc_ctx* c, const float c_pos[4], const float c_rot[4], const
     c->tm.setup_ms = (float)(t1 - t0); c->tm.depth_ms = (float)(t2 - t1); c->tm.id_ms = (float)(t3 - t2);
     c->tm.shade_ms = (float)(t4 - t3); c->tm.frame_ms = (float)(t4 - t0);
     c->tm.n_cutdown = c->n_cut; c->tm.n_fragments = c->n_frags;
+    memcpy(c->cam_pos, c_pos, 16); memcpy(c->cam_rot, c_rot, 16);
+    c->frame_id++;                                                      // engine.cpp:2024
     return RR_OK;
 }
 
@@ -1276,7 +1441,20 @@ int orc_stage_ids(orc_ctx* c) { kernel2(c); return RR_OK; }
 // engine::do_pseudo_aa, engine.cpp:1513-1516: after orc_frame_draw, before orc_swap_buffers
 int orc_post_pseudo_aa(orc_ctx* c) { pseudo_aa(c); return RR_OK; }
 
-int orc_swap_buffers(orc_ctx* c) { c->cur ^= 1; return RR_OK; }        // depth_buffer.flip(), object_context.cpp:21
+// engine::do_motion_blur, engine.cpp:1518-1538 / engine::draw_godrays, engine.cpp:1463-1482: after orc_frame_draw, before orc_swap_buffers
+int orc_post_motion_blur(orc_ctx* c, float strength, float camera_contribution) { motion_blur(c, strength, camera_contribution); return RR_OK; }
+int orc_post_godrays(orc_ctx* c) { godrays(c); return RR_OK; }
+int orc_scene_read_objs(orc_ctx* c, uint32_t first, uint32_t count, rr_obj_desc* dst) {
+    if ((uint64_t)first + count > c->objs.size()) return RR_ERR_INVALID;
+    if (count) memcpy(dst, &c->objs[first], (size_t)count * sizeof(rr_obj_desc));
+    return RR_OK;
+}
+
+int orc_swap_buffers(orc_ctx* c) {                                      // object_context_data::swap_buffers, object_context.cpp:17-25
+    c->cur ^= 1;                                                         // depth_buffer.flip()
+    memcpy(c->cam_pos_old, c->cam_pos, 16); memcpy(c->cam_rot_old, c->cam_rot, 16);
+    return RR_OK;
+}
 int orc_sync(orc_ctx*) { return RR_OK; }
 
 // After orc_frame_draw and BEFORE orc_swap_buffers these return the frame just drawn.

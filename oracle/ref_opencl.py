@@ -188,6 +188,8 @@ class RefCL:
         self.cut_num = self._buf(np.zeros(1, np.uint32))
         self.dummy_buf = self._buf(np.zeros(4, np.uint32))
         self.dummy_img = self._image(CL_RGBA, CL_FLOAT, 4, 4)
+        self.scratch_img = None                                             # third full-size colour image (post passes: see post_pseudo_aa)
+        self.c_pos = self.c_rot = self.c_pos_old = self.c_rot_old = self._f4((0, 0, 0, 0))
         self.n_tris = 0
         self.lights = np.zeros(0, LIGHT)
         self.n_shadow = self.n_static = 0
@@ -387,6 +389,48 @@ class RefCL:
                 u(1 if self.cfg.use_linear_rendering else 0)]
         self._run("kernel3", args, (self.W, self.H), (16, 16))
         self.frame_id += 1
+        self.c_pos, self.c_rot = pos, rot
+
+    # ---- post passes (engine.cpp:1463-1538). The reference's own kernels, but never in place: kernel3 has written the frame to both
+    # screen images (screen / backup_screen), so a pass reads screen[1] and writes screen[0] — what read_rgba8 returns.
+    def _post_kernel(self, name):
+        if name not in self.k:
+            err = C.c_int(0)
+            self.k[name] = P(self.cl.clCreateKernel(self.prog, name.encode(), C.byref(err)))
+            _chk(err.value, "clCreateKernel " + name)
+
+    def post_pseudo_aa(self):
+        """do_pseudo_aa, cl2.cl:6437-6657. The engine binds `screen` and `in_screen` to the same image (engine.cpp:1854-1856); here
+        `screen` is a scratch image, `front_screen` (which gets the same values, cl2.cl:6628-6629) is screen[0]."""
+        self._post_kernel("do_pseudo_aa")
+        if self.scratch_img is None:
+            self.scratch_img = self._image(CL_RGBA, CL_FLOAT, self.W, self.H)
+        self._run("do_pseudo_aa", [self.id_img, self.g_tid_buf, self.screen[1], self.scratch_img, self.screen[0], self.g_cut_tri_mem, self.depth[self.cur],
+                                   self.normals], (self.W, self.H), (8, 8))
+
+    def post_motion_blur(self, strength=1.0, camera_contribution=1.0):
+        """engine::do_motion_blur, engine.cpp:1518-1538 (in = gl_screen[1], out = gl_screen[0] there too)."""
+        self._post_kernel("do_motion_blur")
+        f = lambda v: np.array([v], np.float32)
+        self._run("do_motion_blur", [self.id_img, self.g_tid_buf, self.screen[1], self.screen[0], self.g_cut_tri_mem, self.depth[self.cur], self.g_obj_desc,
+                                     np.array([self.frame_id], np.uint32), self.c_pos, self.c_rot, self.c_pos_old, self.c_rot_old, f(strength),
+                                     f(camera_contribution)], (self.W, self.H), (16, 16))
+
+    def post_godrays(self):
+        """engine::draw_godrays, engine.cpp:1463-1482 (in place there; screen[1] -> screen[0] here)."""
+        if not (self.lights["godray_intensity"] > 0).any():
+            return
+        self._post_kernel("screenspace_godrays")
+        self._run("screenspace_godrays", [self.depth[self.cur], self.screen[1], self.screen[0], self.g_light_num, self.g_light_mem, self.c_pos, self.c_rot],
+                  (self.W, self.H), (16, 16))
+
+    def scene_patch_obj(self, obj_id, byte_off, data):
+        b = np.frombuffer(bytes(data), dtype=np.uint8)
+        self._write(self.g_obj_desc, b, obj_id * 144 + byte_off)
+
+    def scene_read_objs(self, first, count):
+        from openclrenderer_b200._abi import OBJ_DESC
+        return self._read(self.g_obj_desc, np.zeros(count, OBJ_DESC), first * 144)
 
     def enter_steady_state(self):
         """after a converged frame: launch sizes come from that frame's counts with no blocking reads, as the engine's
@@ -397,6 +441,7 @@ class RefCL:
 
     def swap_buffers(self):
         self.cur ^= 1
+        self.c_pos_old, self.c_rot_old = self.c_pos, self.c_rot                 # object_context.cpp:23-24
 
     def sync(self):
         self.cl.clFinish(self.q)

@@ -83,3 +83,33 @@ def test_live_reference_as_shipped_is_close(name):
     assert abs(len(r.read_fragments()) - len(g.read_fragments())) <= 8
     diff = np.abs(r.read_rgba8().astype(np.int16) - g.read_rgba8().astype(np.int16)).max(axis=-1)
     assert (diff <= 2).mean() >= 0.999
+
+
+@pytest.mark.parametrize("which", ["pseudo_aa", "motion_blur", "godrays"])
+def test_live_reference_post_passes(which):
+    """The post passes pinned against the reference's own kernels (do_pseudo_aa cl2.cl:6437, do_motion_blur 6714,
+    screenspace_godrays 1792) run with separate input and output images. The reference filters a float image with the GPU's
+    fixed-point CLK_FILTER_LINEAR weights, the product the quantised RGBA8 target with the specification's formula: +-2 LSB."""
+    from openclrenderer_b200 import scene
+    from tests.test_post_passes import _moving_frames
+    cl = _refcl()
+    s = scene.scene_c2(640, 360, light_dim=256)
+    out = {}
+    for key, x in (("ref", cl.RefCL(s.cfg, mode="pinned")), ("cuda", Renderer(s.cfg))):
+        if which == "pseudo_aa":
+            s.upload(x)
+            x.frame_shadows(1)
+            x.frame_draw(s.c_pos, s.c_rot, s.clear)
+            x.post_pseudo_aa()
+            x.sync()
+            out[key] = ([x.read_rgba8()], None)
+        else:
+            out[key] = _moving_frames(x, s, 3, blur=(which == "motion_blur"), godray=(which == "godrays"))
+    (rf, robjs), (gf, gobjs) = out["ref"], out["cuda"]
+    for i, (a, b) in enumerate(zip(rf, gf)):
+        d = np.abs(a.astype(np.int16) - b.astype(np.int16))[..., :3].max(axis=-1)
+        assert (d <= 2).mean() >= 0.995, f"{which} frame {i}: only {(d <= 2).mean() * 100:.3f}% within +-2 LSB (max {d.max()})"
+        assert (d <= 1).mean() >= 0.97, f"{which} frame {i}: only {(d <= 1).mean() * 100:.3f}% within +-1 LSB"
+    if which == "motion_blur":
+        for f in ("old_world_pos_1", "old_world_pos_2", "old_world_rot_quat_1", "old_world_rot_quat_2"):
+            assert np.array_equal(robjs[f][:, :3], gobjs[f][:, :3]), f
