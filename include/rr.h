@@ -157,6 +157,10 @@ int rr_scene_build_commit(rr_ctx*);               /* flip_buffers */
 int rr_atlas_alloc(rr_ctx*, uint32_t n_slices, const uint32_t* nums, uint32_t n_nums,
                    const uint32_t* sizes, uint32_t n_sizes, uint32_t mipmap_start);              /* g_texture_array / g_texture_nums / g_texture_sizes */
 int rr_atlas_upload(rr_ctx*, uint32_t gpu_id, const uint8_t* rgba, uint32_t w, uint32_t h, int flip); /* texture::update_me_to_gpu texture.cpp:323-358 = update_gpu_tex + generate_mips + 3x generate_mip_mips */
+int rr_atlas_upload_batch(rr_ctx*, uint32_t n, const uint32_t* gpu_ids, const uint8_t* const* rgba, const uint32_t* w, const uint32_t* h, int flip);
+                                                                                                 /* the upload loop of texture_context::alloc_gpu texture_context.cpp:478-517 for n textures at once: one staged copy, one launch per phase (base + 4 mip levels); same atlas bytes as n rr_atlas_upload calls */
+int rr_atlas_fill_colour(rr_ctx*, uint32_t gpu_id, const float col_0_255[4], uint32_t w, uint32_t h); /* texture::update_gpu_texture_col texture.cpp:445-463 -> update_gpu_tex_colour cl2.cl:955-984 (texture and its 4 mips) */
+int rr_atlas_upload_mono(rr_ctx*, uint32_t gpu_id, const uint8_t* raw, uint32_t len, uint32_t w, uint32_t h, int flip); /* texture::update_gpu_texture_mono texture.cpp:554-584 -> generate_from_raw cl2.cl:1006-1031 (stride = len / h; mips untouched) */
 int rr_atlas_write_raw(rr_ctx*, const uint8_t* atlas, size_t nbytes);                            /* test hook: inject a prebuilt atlas (decouples shading parity from atlas parity) */
 int rr_atlas_read_raw(rr_ctx*, uint8_t* dst, size_t nbytes);
 

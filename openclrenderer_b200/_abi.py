@@ -101,6 +101,9 @@ _SIGS = {
     "scene_build_ready": (C.c_int, [_P]),
     "scene_build_commit": (C.c_int, [_P]),
     "atlas_upload": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_int]),
+    "atlas_upload_batch": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, C.c_int]),
+    "atlas_fill_colour": (C.c_int, [_P, C.c_uint32, _F4, C.c_uint32, C.c_uint32]),
+    "atlas_upload_mono": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "atlas_write_raw": (C.c_int, [_P, _P, C.c_size_t]),
     "atlas_read_raw": (C.c_int, [_P, _P, C.c_size_t]),
     "lights_write": (C.c_int, [_P, _P, C.c_uint32]),
@@ -217,6 +220,25 @@ class CApi:
         rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
         h, w = rgba.shape[:2]
         self._call("atlas_upload", gpu_id, _ptr(rgba), w, h, flip)
+
+    def atlas_upload_batch(self, gpu_ids, images, flip=1):
+        """all textures of an atlas build in one call (texture_context::alloc_gpu's upload loop)"""
+        images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        n = len(images)
+        ids = np.ascontiguousarray(gpu_ids, dtype=np.uint32)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in images])
+        w = np.array([im.shape[1] for im in images], dtype=np.uint32)
+        h = np.array([im.shape[0] for im in images], dtype=np.uint32)
+        self._call("atlas_upload_batch", n, _ptr(ids), C.cast(ptrs, _P), _ptr(w), _ptr(h), flip)
+
+    def atlas_fill_colour(self, gpu_id, col_0_255, w, h):
+        """texture::update_gpu_texture_col: a flat colour (0..255 units) into texture gpu_id and its mips"""
+        self._call("atlas_fill_colour", gpu_id, _F4(*[float(x) for x in col_0_255]), w, h)
+
+    def atlas_upload_mono(self, gpu_id, raw, w, h, flip=1):
+        """texture::update_gpu_texture_mono: one byte per texel"""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        self._call("atlas_upload_mono", gpu_id, _ptr(raw), raw.nbytes, w, h, flip)
 
     def atlas_read_raw(self):
         out = np.empty((self.atlas_slices, 2048, 2048, 4), dtype=np.uint8)

@@ -106,6 +106,8 @@ struct rr_ctx {
     bool objlite_dirty = true;
     // atlas
     uchar4* d_atlas = nullptr;
+    cudaTextureObject_t atlas_tex = 0;           // optional fetch path of kernel3 (RR_TEX_OBJECTS=1): point-sampled pitch-2D view of d_atlas
+    bool use_tex_objects = true;                 // measured equal or slightly faster than ld.global.nc (profiles/r2_texobj_ab.txt); RR_TEX_OBJECTS=0 selects the plain loads
     size_t atlas_texels = 0;
     uint32_t *d_nums = nullptr, *d_sizes = nullptr;
     uint32_t n_nums = 0, n_sizes = 0, mipmap_start = 0;
@@ -418,7 +420,8 @@ static int preload_kernels() {
         (const void*)k_raster_warp<RM_DEPTH>, (const void*)k_raster_warp<RM_IDS>,
         (const void*)k_ids_list, (const void*)k_shadow_setup, (const void*)k_cluster_faces,
         (const void*)k_signal_flag, (const void*)k_signal_flags, (const void*)k_wait_flags, (const void*)k_push_faces, (const void*)k_fill_faces,
-        (const void*)k_raster_shadow_warp, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip,
+        (const void*)k_raster_shadow_warp, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip, (const void*)k_atlas_upload_batch, (const void*)k_atlas_mip_batch,
+        (const void*)k_atlas_fill_colour, (const void*)k_atlas_from_raw,
         (const void*)k_shade_pre, (const void*)k_shade_pre4, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_motion_blur, (const void*)k_motion_history, (const void*)k_godrays, (const void*)k_copy_u32,
     };
     for (const void* f : fns) {
@@ -482,6 +485,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     c->cam_last.rot = c->cam_old.rot = make_rotsc(0.f, 0.f, 0.f);
     c->cluster_cull = cfg->cluster_cull;
     if (const char* e = getenv("RR_SHADOW_PRETEST")) c->shadow_pretest = atoi(e) != 0;
+    if (const char* e = getenv("RR_TEX_OBJECTS")) c->use_tex_objects = atoi(e) != 0;
     auto bail = [&](const char* what) { fail(RR_ERR_CUDA, "rr_create: %s: %s", what, cudaGetErrorString(cudaGetLastError())); rr_destroy(c); return (rr_ctx*)nullptr; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
     for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail("event");
@@ -552,6 +556,7 @@ void rr_destroy(rr_ctx* c) {
     cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite); cudaFree(c->d_obj_r2); cudaFree(c->d_obj_rows);
     cudaFree(c->d_clusters); cudaFree(c->d_cluster_vis); cudaFree(c->d_cluster_faces); cudaFree(c->d_active); cudaFree(c->d_skipped);
     cudaFree(c->d_rowmask); cudaFree(c->d_rowpfx);
+    if (c->atlas_tex) cudaDestroyTextureObject(c->atlas_tex);
     cudaFree(c->d_atlas); cudaFree(c->d_nums); cudaFree(c->d_sizes); cudaFree(c->d_upload);
     cudaFree(c->d_lights); cudaFree(c->d_lightlite);
     if (!c->ext_shadow_dyn) cudaFree(c->d_shadow_dyn);
@@ -805,6 +810,20 @@ int rr_atlas_alloc(rr_ctx* c, uint32_t n_slices, const uint32_t* nums, uint32_t 
     if (n_sizes) CU(cudaMemcpyAsync(c->d_sizes, sizes, (size_t)n_sizes * 4, cudaMemcpyHostToDevice, c->stream));
     c->n_nums = n_nums; c->n_sizes = n_sizes; c->mipmap_start = mipmap_start;
     CU(cudaStreamSynchronize(c->stream));
+    if (c->atlas_tex) { cudaDestroyTextureObject(c->atlas_tex); c->atlas_tex = 0; }
+    if (c->use_tex_objects && (size_t)slices * RR_ATLAS_DIM <= 65000) {              // pitch-2D textures are limited to 65000 rows
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypePitch2D;
+        rd.res.pitch2D.devPtr = c->d_atlas;
+        rd.res.pitch2D.desc = cudaCreateChannelDesc<uchar4>();
+        rd.res.pitch2D.width = RR_ATLAS_DIM; rd.res.pitch2D.height = (size_t)slices * RR_ATLAS_DIM; rd.res.pitch2D.pitchInBytes = (size_t)RR_ATLAS_DIM * 4;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&c->atlas_tex, &rd, &td, nullptr));
+    }
     return RR_OK;
 }
 
@@ -828,6 +847,78 @@ int rr_atlas_upload(rr_ctx* c, uint32_t gpu_id, const uint8_t* rgba, uint32_t w,
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+
+// texture_context::alloc_gpu's upload loop (texture_context.cpp:478-517) for a whole set of textures: one staged copy, five launches
+int rr_atlas_upload_batch(rr_ctx* c, uint32_t n, const uint32_t* gpu_ids, const uint8_t* const* rgba, const uint32_t* w, const uint32_t* h, int flip) {
+    if (!c || (n && (!gpu_ids || !rgba || !w || !h))) return fail(RR_ERR_INVALID, "null argument");
+    if (!c->d_atlas) return fail(RR_ERR_INVALID, "atlas not allocated");
+    if (n == 0) return RR_OK;
+    std::vector<AtlasJob> jobs(n);
+    size_t texels = 0;
+    uint32_t tiles = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (gpu_ids[i] >= c->n_nums || !rgba[i]) return fail(RR_ERR_INVALID, "rr_atlas_upload_batch: bad texture %u", i);
+        jobs[i] = AtlasJob{(unsigned long long)texels, w[i], h[i], gpu_ids[i], tiles};
+        texels += (size_t)w[i] * h[i];
+        const uint64_t t = (uint64_t)((w[i] + 15) / 16) * ((h[i] + 15) / 16);
+        if (tiles + t > 0x7FFFFFFFull) return fail(RR_ERR_INVALID, "rr_atlas_upload_batch: batch too large");
+        tiles += (uint32_t)t;
+    }
+    if (texels == 0 || tiles == 0) return RR_OK;
+    int r;
+    if (texels > c->upload_cap) { if ((r = dev_alloc(c->d_upload, texels))) return r; c->upload_cap = texels; }
+    AtlasJob* d_jobs = nullptr;
+    CU(cudaMalloc((void**)&d_jobs, (size_t)n * sizeof(AtlasJob)));
+    uchar4* h_stage = nullptr;                                        // one pinned staging block: a single DMA instead of one write per texture
+    if (cudaMallocHost((void**)&h_stage, texels * 4) != cudaSuccess) { cudaFree(d_jobs); return fail(RR_ERR_OOM, "rr_atlas_upload_batch: staging"); }
+    for (uint32_t i = 0; i < n; i++) memcpy(h_stage + jobs[i].src_off, rgba[i], (size_t)w[i] * h[i] * 4);
+    cudaError_t e = cudaMemcpyAsync(c->d_upload, h_stage, texels * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)n * sizeof(AtlasJob), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        k_atlas_upload_batch<<<tiles, 256, 0, c->stream>>>(d_jobs, n, c->d_upload, flip, c->d_atlas, c->d_nums, c->d_sizes);
+        for (int level = 0; level < RR_MIP_LEVELS; level++)
+            k_atlas_mip_batch<<<tiles, 256, 0, c->stream>>>(d_jobs, n, level, c->mipmap_start, c->d_atlas, c->d_nums, c->d_sizes);
+        c->launches += 1 + RR_MIP_LEVELS;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFreeHost(h_stage);
+    cudaFree(d_jobs);
+    if (e != cudaSuccess) return fail(RR_ERR_CUDA, "rr_atlas_upload_batch: %s", cudaGetErrorString(e));
+    return RR_OK;
+}
+
+// texture::update_gpu_texture_col, texture.cpp:445-463 (col in 0..255 units, launch size = the texture's image size)
+int rr_atlas_fill_colour(rr_ctx* c, uint32_t gpu_id, const float col[4], uint32_t w, uint32_t h) {
+    if (!c || !col) return fail(RR_ERR_INVALID, "null argument");
+    if (!c->d_atlas || gpu_id >= c->n_nums) return fail(RR_ERR_INVALID, "atlas not allocated or bad texture id");
+    if (w == 0 || h == 0) return RR_OK;
+    dim3 grid((w + 15) / 16, (h + 15) / 16);
+    k_atlas_fill_colour<<<grid, 256, 0, c->stream>>>(make_float4(col[0], col[1], col[2], col[3]), gpu_id, c->mipmap_start, (int)w, (int)h, c->d_atlas, c->d_nums, c->d_sizes);
+    c->launches++;
+    CU(cudaGetLastError());
+    return RR_OK;
+}
+
+// texture::update_gpu_texture_mono, texture.cpp:554-584: len bytes, stride = len / height; asynchronous like there (the bytes are
+// staged before the call returns)
+int rr_atlas_upload_mono(rr_ctx* c, uint32_t gpu_id, const uint8_t* raw, uint32_t len, uint32_t w, uint32_t h, int flip) {
+    (void)flip;                                                       // generate_from_raw ignores it (cl2.cl:1020-1026)
+    if (!c || !raw) return fail(RR_ERR_INVALID, "null argument");
+    if (!c->d_atlas || gpu_id >= c->n_nums) return fail(RR_ERR_INVALID, "atlas not allocated or bad texture id");
+    if (w == 0 || h == 0 || len == 0) return RR_OK;
+    const uint32_t stride = len / h;
+    if ((uint64_t)(h - 1) * stride + w > len) return fail(RR_ERR_INVALID, "rr_atlas_upload_mono: %u bytes do not hold a %ux%u image", len, w, h);
+    int r;
+    const size_t need = ((size_t)len + 3) / 4;
+    if (need > c->upload_cap) { if ((r = dev_alloc(c->d_upload, need))) return r; c->upload_cap = need; }
+    if ((r = upload_staged(c, c->d_upload, raw, len))) return r;
+    dim3 grid((w + 15) / 16, (h + 15) / 16);
+    k_atlas_from_raw<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const unsigned char*>(c->d_upload), (int)stride, (int)w, (int)h, gpu_id, c->d_atlas, c->d_nums, c->d_sizes);
+    c->launches++;
+    CU(cudaGetLastError());
     return RR_OK;
 }
 
@@ -1085,7 +1176,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
     if (c->mg.connected) c->d_rgba8 = (c->mg.rank == 0 || c->mg.local_readback) ? c->mg.fb[c->mg_target] : c->mg.fb0[c->mg_target];
     hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
-    hp.atlas.texels = c->d_atlas; hp.atlas.nums = c->d_nums; hp.atlas.sizes = c->d_sizes; hp.atlas.mip_start = c->mipmap_start;
+    hp.atlas.texels = c->d_atlas; hp.atlas.nums = c->d_nums; hp.atlas.sizes = c->d_sizes; hp.atlas.mip_start = c->mipmap_start; hp.atlas.tex = c->atlas_tex;
     hp.lights = c->d_lights; hp.n_lights = (int)c->lights.size();
     hp.shadow_dyn = c->d_shadow_dyn; hp.shadow_static = c->d_shadow_static;
     hp.faces = c->faces; hp.cam = cam;

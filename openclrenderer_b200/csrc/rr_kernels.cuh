@@ -1516,7 +1516,8 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t* __restrict__ p, size
 // =====================================================================================================================
 // texture atlas: update_gpu_tex (cl2.cl:923-953), generate_mips (1071-1129), generate_mip_mips (1132-1189)
 // =====================================================================================================================
-struct AtlasView { const uchar4* texels; const uint32_t* nums; const uint32_t* sizes; uint32_t mip_start; };
+struct AtlasView { const uchar4* texels; const uint32_t* nums; const uint32_t* sizes; uint32_t mip_start;
+                   cudaTextureObject_t tex; };      // tex != 0: fetch texels through a point-sampled texture object over the same memory (rr_config-free A/B: RR_TEX_OBJECTS)
 
 // read_tex_array, cl2.cl:785-821
 __device__ __forceinline__ float4 read_tex_array(float cx, float cy, uint32_t tid, const uchar4* __restrict__ atlas, const uint32_t* __restrict__ nums,
@@ -1551,9 +1552,9 @@ __device__ __forceinline__ void write_tex_array(uchar4 v, float cx, float cy, ui
     atlas[(size_t)slice * RR_ATLAS_DIM * RR_ATLAS_DIM + (size_t)iy * RR_ATLAS_DIM + ix] = v;
 }
 
-__global__ void __launch_bounds__(256) k_atlas_upload(const uchar4* __restrict__ src, int w, int h, uint32_t tex_id, int flip, uchar4* __restrict__ atlas,
-                                                      const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
-    int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+// update_gpu_tex, cl2.cl:923-953, for texel (x, y) of a w x h source image
+__device__ __forceinline__ void atlas_upload_texel(const uchar4* __restrict__ src, int w, int h, int x, int y, uint32_t tex_id, int flip, uchar4* __restrict__ atlas,
+                                                   const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
     if (x >= w || y >= h) return;
     uchar4 s = src[(size_t)y * w + x];
     // read_imagef on CL_UNORM_INT8 then *255 then truncating convert (cl2.cl:940-944), pinned as ((float)c/255.f)*255.f
@@ -1569,9 +1570,9 @@ __global__ void __launch_bounds__(256) k_atlas_upload(const uchar4* __restrict__
     write_tex_array(o, (float)x, (float)yy, tex_id, atlas, nums, sizes);
 }
 
-__global__ void __launch_bounds__(256) k_atlas_mip(uint32_t src_id, uint32_t dst_id, int gw, int gh, uchar4* __restrict__ atlas,
-                                                   const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
-    int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+// generate_mips (cl2.cl:1071-1129) / generate_mip_mips (1132-1189) for work-item (x, y) of a gw x gh launch
+__device__ __forceinline__ void atlas_mip_texel(uint32_t src_id, uint32_t dst_id, int gw, int gh, int x, int y, uchar4* __restrict__ atlas,
+                                                const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
     if (x >= gw || y >= gh) return;
     int slice = (int)(nums[src_id] >> 16);
     float width = (float)sizes[slice];
@@ -1598,6 +1599,79 @@ __global__ void __launch_bounds__(256) k_atlas_mip(uint32_t src_id, uint32_t dst
     if (yx_x >= nwidth || yx_y >= nwidth) return;
     uchar4 o = make_uchar4((unsigned char)sat_u32(accum.x), (unsigned char)sat_u32(accum.y), (unsigned char)sat_u32(accum.z), (unsigned char)sat_u32(accum.w));
     write_tex_array(o, yx_x, yx_y, dst_id, atlas, nums, sizes);
+}
+
+__global__ void __launch_bounds__(256) k_atlas_upload(const uchar4* __restrict__ src, int w, int h, uint32_t tex_id, int flip, uchar4* __restrict__ atlas,
+                                                      const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
+    atlas_upload_texel(src, w, h, blockIdx.x * 16 + (threadIdx.x & 15), blockIdx.y * 16 + (threadIdx.x >> 4), tex_id, flip, atlas, nums, sizes);
+}
+
+__global__ void __launch_bounds__(256) k_atlas_mip(uint32_t src_id, uint32_t dst_id, int gw, int gh, uchar4* __restrict__ atlas,
+                                                   const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
+    atlas_mip_texel(src_id, dst_id, gw, gh, blockIdx.x * 16 + (threadIdx.x & 15), blockIdx.y * 16 + (threadIdx.x >> 4), atlas, nums, sizes);
+}
+
+// ---- batched atlas build (texture_context::alloc_gpu, texture_context.cpp:478-517, uploads every texture with its own write,
+// kernel and four mip kernels, serially on one queue). Here all textures of a batch go through ONE launch per phase: the base
+// upload, then each of the four mip levels (a level reads the one before it, so the levels stay separate launches).
+// A job = one texture; the grid is the concatenation of the jobs' 16x16 tiles, `tile0` its exclusive prefix.
+struct AtlasJob { unsigned long long src_off; uint32_t w, h, tex_id, tile0; };      // src_off: texel offset of the image in the staged batch
+
+__device__ __forceinline__ bool atlas_job_of_block(const AtlasJob* __restrict__ jobs, uint32_t n_jobs, uint32_t block, AtlasJob& job, int& x, int& y) {
+    uint32_t lo = 0, hi = n_jobs;                    // last job with tile0 <= block
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&jobs[mid].tile0) <= block) lo = mid; else hi = mid; }
+    job = jobs[lo];
+    const uint32_t t = block - job.tile0, tw = (job.w + 15) / 16;
+    if (t >= tw * ((job.h + 15) / 16)) return false;
+    x = (int)((t % tw) * 16 + (threadIdx.x & 15));
+    y = (int)((t / tw) * 16 + (threadIdx.x >> 4));
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_atlas_upload_batch(const AtlasJob* __restrict__ jobs, uint32_t n_jobs, const uchar4* __restrict__ staged, int flip,
+                                                            uchar4* __restrict__ atlas, const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
+    AtlasJob job; int x, y;
+    if (!atlas_job_of_block(jobs, n_jobs, blockIdx.x, job, x, y)) return;
+    atlas_upload_texel(staged + job.src_off, (int)job.w, (int)job.h, x, y, job.tex_id, flip, atlas, nums, sizes);
+}
+
+// level 0: generate_mips (base -> first mip); level 1..3: generate_mip_mips (mip level-1 -> mip level), texture.cpp:465-493
+__global__ void __launch_bounds__(256) k_atlas_mip_batch(const AtlasJob* __restrict__ jobs, uint32_t n_jobs, int level, uint32_t mipmap_start,
+                                                         uchar4* __restrict__ atlas, const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
+    AtlasJob job; int x, y;
+    if (!atlas_job_of_block(jobs, n_jobs, blockIdx.x, job, x, y)) return;
+    const uint32_t m0 = job.tex_id * RR_MIP_LEVELS + mipmap_start;
+    atlas_mip_texel(level == 0 ? job.tex_id : m0 + (uint32_t)level - 1u, m0 + (uint32_t)level, (int)job.w, (int)job.h, x, y, atlas, nums, sizes);
+}
+
+// update_gpu_tex_colour, cl2.cl:955-984 (texture::update_gpu_texture_col, texture.cpp:445-463): a flat colour into the texture and
+// its four mips. col is in 0..255 units; convert_uint4 pinned as the saturating truncation used everywhere else.
+__global__ void __launch_bounds__(256) k_atlas_fill_colour(float4 col, uint32_t tex_id, uint32_t mipmap_start, int gw, int gh, uchar4* __restrict__ atlas,
+                                                           const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
+    const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (x >= gw || y >= gh) return;
+    const int slice = (int)(nums[tex_id] >> 16);
+    const float width = (float)sizes[slice];
+    if ((float)x >= width || (float)y >= width) return;
+    const uchar4 ucol = make_uchar4((unsigned char)sat_u32(col.x), (unsigned char)sat_u32(col.y), (unsigned char)sat_u32(col.z), (unsigned char)sat_u32(col.w));
+    write_tex_array(ucol, (float)x, (float)y, tex_id, atlas, nums, sizes);
+    for (int i = 0; i < RR_MIP_LEVELS; i++) {
+        const uint32_t mtexid = tex_id * RR_MIP_LEVELS + mipmap_start + (uint32_t)i;
+        const float nwidth = (float)sizes[nums[mtexid] >> 16];
+        write_tex_array(ucol, ((float)x / width) * nwidth, ((float)y / width) * nwidth, mtexid, atlas, nums, sizes);
+    }
+}
+
+// generate_from_raw, cl2.cl:1006-1031 (texture::update_gpu_texture_mono, texture.cpp:554-584): one byte per texel, replicated to the
+// four channels; the mips are not touched (the call is commented out there) and `flip` is ignored by the kernel
+__global__ void __launch_bounds__(256) k_atlas_from_raw(const unsigned char* __restrict__ raw, int stride, int dimx, int dimy, uint32_t tex_id,
+                                                        uchar4* __restrict__ atlas, const uint32_t* __restrict__ nums, const uint32_t* __restrict__ sizes) {
+    const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (x >= dimx || y >= dimy) return;
+    const int width = (int)sizes[nums[tex_id] >> 16];
+    if (x >= width || y >= width) return;
+    const unsigned char v = raw[(size_t)y * stride + x];
+    write_tex_array(make_uchar4(v, v, v, v), (float)x, (float)y, tex_id, atlas, nums, sizes);
 }
 
 // =====================================================================================================================
@@ -1627,24 +1701,29 @@ struct ShadeParams {
 };
 
 // read_tex_array_all_precalculated, cl2.cl:823-851
-__device__ __forceinline__ float4 read_tex_pre(float cx, float cy, int which, int slice, float width, const uchar4* __restrict__ atlas) {
+__device__ __forceinline__ float4 read_tex_pre(float cx, float cy, int which, int slice, float width, const uchar4* __restrict__ atlas, cudaTextureObject_t tex = 0) {
     const float ihnum = width * (1.f / 2048);
     float tnumy = floorf((float)which * ihnum);
     float tnumx = (float)which - div_pow2(tnumy, ihnum);                // (ihnum = tile size / 2048)
     cx = clampf(cx, 0.001f, width - 0.001f);
     cy = clampf(cy, 0.001f, width - 0.001f);
     int ix = (int)fmaf(tnumx, width, cx), iy = (int)fmaf(tnumy, width, cy);
-    uchar4 t = __ldg(atlas + (size_t)slice * RR_ATLAS_DIM * RR_ATLAS_DIM + (size_t)iy * RR_ATLAS_DIM + ix);
+    // integer texels, blended in the kernel exactly as the reference does (SURVEY.md §7 hard part 7). Two fetch paths over the same
+    // pitch-linear atlas: the read-only data path (ld.global.nc) or a point-sampled texture object (element read mode, unnormalised
+    // coordinates) — same bytes either way; measured side by side in profiles/r2_texobj_ab.txt
+    uchar4 t;
+    if (tex) t = tex2D<uchar4>(tex, (float)ix + 0.5f, (float)(iy + slice * RR_ATLAS_DIM) + 0.5f);
+    else t = __ldg(atlas + (size_t)slice * RR_ATLAS_DIM * RR_ATLAS_DIM + (size_t)iy * RR_ATLAS_DIM + ix);
     return make_float4((float)t.x, (float)t.y, (float)t.z, (float)t.w);
 }
 
 // return_bilinear_col_all_precalculated, cl2.cl:1426-1455
-__device__ __forceinline__ float4 bilinear_pre(float mx, float my, int which, int slice, float width, const uchar4* __restrict__ atlas) {
+__device__ __forceinline__ float4 bilinear_pre(float mx, float my, int which, int slice, float width, const uchar4* __restrict__ atlas, cudaTextureObject_t tex) {
     float px = floorf(mx), py = floorf(my);
-    float4 c0 = read_tex_pre(px, py, which, slice, width, atlas);
-    float4 c1 = read_tex_pre(px + 1, py, which, slice, width, atlas);
-    float4 c2 = read_tex_pre(px, py + 1, which, slice, width, atlas);
-    float4 c3 = read_tex_pre(px + 1, py + 1, which, slice, width, atlas);
+    float4 c0 = read_tex_pre(px, py, which, slice, width, atlas, tex);
+    float4 c1 = read_tex_pre(px + 1, py, which, slice, width, atlas, tex);
+    float4 c2 = read_tex_pre(px, py + 1, which, slice, width, atlas, tex);
+    float4 c3 = read_tex_pre(px + 1, py + 1, which, slice, width, atlas, tex);
     float ux = mx - px, uy = my - py;
     float bx = 1.f - ux, by = 1.f - uy;
     return mad4(c0, bx, c1 * ux) * by + mad4(c2, bx, c3 * ux) * uy;
@@ -1667,8 +1746,8 @@ __device__ __forceinline__ float4 texture_filter_diff(float2 vt, float2 vtdiff, 
     int slice_lower = lower_nv >> 16, slice_higher = higher_nv >> 16;
     int which_lower = lower_nv & 0xFFFF, which_higher = higher_nv & 0xFFFF;
     float size_lower = (float)__ldg(av.sizes + slice_lower), size_higher = (float)__ldg(av.sizes + slice_higher);
-    float4 col1 = bilinear_pre(vx * size_lower, vy * size_lower, which_lower, slice_lower, size_lower, av.texels);
-    float4 col2 = bilinear_pre(vx * size_higher, vy * size_higher, which_higher, slice_higher, size_higher, av.texels);
+    float4 col1 = bilinear_pre(vx * size_lower, vy * size_lower, which_lower, slice_lower, size_lower, av.texels, av.tex);
+    float4 col2 = bilinear_pre(vx * size_higher, vy * size_higher, which_higher, slice_higher, size_higher, av.texels, av.tex);
     float4 fc = col1 + (col2 - col1) * fmd;
     return fc * (1.f / 255.f);
 }

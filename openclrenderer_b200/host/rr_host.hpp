@@ -137,6 +137,16 @@ struct texture {
         is_loaded = true;
     }
     int get_largest_dimension() const { return std::max(w, h); }
+    // dynamic writes into the live atlas (texture.hpp:96-99)
+    void update_gpu_texture_col(const cl_float4& col, rr_ctx* dev) {                  // texture.cpp:445-463 (col in 0..255 units)
+        if (id == -1 || gpu_id < 0) return;
+        const float c4[4] = {col.x, col.y, col.z, col.w};
+        if (rr_atlas_fill_colour(dev, (uint32_t)gpu_id, c4, (uint32_t)w, (uint32_t)h)) rr_fatal("rr_atlas_fill_colour");
+    }
+    void update_gpu_texture_mono(rr_ctx* dev, const uint8_t* buffer_dat, uint32_t len, int width, int height, bool flip = true) {   // texture.cpp:554-584
+        if (gpu_id < 0) return;
+        if (rr_atlas_upload_mono(dev, (uint32_t)gpu_id, buffer_dat, len, (uint32_t)width, (uint32_t)height, flip ? 1 : 0)) rr_fatal("rr_atlas_upload_mono");
+    }
 };
 
 struct object_context;
@@ -407,12 +417,17 @@ inline texture_context_data texture_context::alloc_gpu(object_context& ctx, rr_c
     std::vector<cl_uint> nums, sizes;
     plan_texture_pages(dims, nums, sizes);
     if (rr_atlas_alloc(dev, (uint32_t)sizes.size(), nums.data(), (uint32_t)nums.size(), sizes.data(), (uint32_t)sizes.size(), mipmap_start)) rr_fatal("rr_atlas_alloc");
+    // texture_context.cpp:478-517 uploads the textures one by one (write + kernel + 4 mip kernels each); here the whole set goes
+    // down in one staged copy and one launch per phase
+    std::vector<uint32_t> gpu_ids, ws, hs;
+    std::vector<const uint8_t*> images;
     int c = 0;
     for (auto id : texture_id_orders) {
         texture* t = id_to_tex(id);
         t->gpu_id = c++;
-        if (rr_atlas_upload(dev, (uint32_t)t->gpu_id, t->c_image.data(), (uint32_t)t->w, (uint32_t)t->h, 1)) rr_fatal("rr_atlas_upload");
+        gpu_ids.push_back((uint32_t)t->gpu_id); images.push_back(t->c_image.data()); ws.push_back((uint32_t)t->w); hs.push_back((uint32_t)t->h);
     }
+    if (rr_atlas_upload_batch(dev, (uint32_t)gpu_ids.size(), gpu_ids.data(), images.data(), ws.data(), hs.data(), 1)) rr_fatal("rr_atlas_upload_batch");
     built_ids = in_use; built_dims = dims; built = true;
     texture_context_data d; d.mipmap_start = mipmap_start;
     return d;

@@ -1366,6 +1366,43 @@ int orc_atlas_upload(orc_ctx* c, uint32_t gpu_id, const uint8_t* rgba, uint32_t 
     }
     return RR_OK;
 }
+// the same uploads for a set of textures (texture_context.cpp:478-517 is a serial loop over them)
+int orc_atlas_upload_batch(orc_ctx* c, uint32_t n, const uint32_t* gpu_ids, const uint8_t* const* rgba, const uint32_t* w, const uint32_t* h, int flip) {
+    for (uint32_t i = 0; i < n; i++) { int r = orc_atlas_upload(c, gpu_ids[i], rgba[i], w[i], h[i], flip); if (r) return r; }
+    return RR_OK;
+}
+// update_gpu_tex_colour, cl2.cl:955-984 (texture::update_gpu_texture_col, texture.cpp:445-463); global size = the texture's image size
+int orc_atlas_fill_colour(orc_ctx* c, uint32_t tex_id, const float col[4], uint32_t gw, uint32_t gh) {
+    if (tex_id >= c->nums.size()) return RR_ERR_INVALID;
+    const int slice = (int)(c->nums[tex_id] >> 16);
+    const float width = (float)c->sizes[slice];
+    const uint32_t ucol[4] = {sat_u32(col[0]), sat_u32(col[1]), sat_u32(col[2]), sat_u32(col[3])};      // convert_uint4, pinned saturating
+    for (int y = 0; y < (int)gh; y++)
+        for (int x = 0; x < (int)gw; x++) {
+            if ((float)x >= width || (float)y >= width) continue;
+            write_tex_array(ucol, {(float)x, (float)y}, tex_id, c);
+            for (int i = 0; i < MIP_LEVELS; i++) {
+                const uint32_t mtexid = tex_id * MIP_LEVELS + c->mipmap_start + (uint32_t)i;
+                const float nwidth = (float)c->sizes[c->nums[mtexid] >> 16];
+                write_tex_array(ucol, {((float)x / width) * nwidth, ((float)y / width) * nwidth}, mtexid, c);
+            }
+        }
+    return RR_OK;
+}
+// generate_from_raw, cl2.cl:1006-1031 (texture::update_gpu_texture_mono, texture.cpp:554-584)
+int orc_atlas_upload_mono(orc_ctx* c, uint32_t tex_id, const uint8_t* raw, uint32_t len, uint32_t w, uint32_t h, int /*flip*/) {
+    if (tex_id >= c->nums.size() || h == 0) return RR_ERR_INVALID;
+    const int stride = (int)(len / h);
+    const int width = (int)c->sizes[c->nums[tex_id] >> 16];
+    for (int y = 0; y < (int)h; y++)
+        for (int x = 0; x < (int)w; x++) {
+            if (x >= width || y >= width) continue;
+            const uint32_t v = raw[(size_t)y * stride + x];
+            const uint32_t val[4] = {v, v, v, v};
+            write_tex_array(val, {(float)x, (float)y}, tex_id, c);
+        }
+    return RR_OK;
+}
 int orc_atlas_write_raw(orc_ctx* c, const uint8_t* a, size_t n) { if (n > c->atlas.size()) return RR_ERR_INVALID; memcpy(c->atlas.data(), a, n); return RR_OK; }
 int orc_atlas_read_raw(orc_ctx* c, uint8_t* d, size_t n) { if (n > c->atlas.size()) return RR_ERR_INVALID; memcpy(d, c->atlas.data(), n); return RR_OK; }
 

@@ -131,3 +131,20 @@ def test_interleaved_rows_without_exchange():
         own = rrd.owned_rows(s.cfg.height, tile, world, k)
         assert np.array_equal(b.read_depth()[own], fd[own])
         assert np.array_equal(b.read_rgba8()[own], fc[own])
+
+
+def test_peer_that_never_arrives_times_out_with_rr_err_peer(monkeypatch):
+    """the bounded wait of the exchange (k_wait_flags): a context whose peer never renders its share must not hang — the wait
+    gives up after RR_MGPU_TIMEOUT_MS, raises the error bit in the control block, and rr_sync reports RR_ERR_PEER."""
+    from openclrenderer_b200 import RRError
+    monkeypatch.setenv("RR_MGPU_TIMEOUT_MS", "100")
+    s = scene.scene_spheres(320, 192, n_spheres=6, grid=(3, 2), seed=3, n_lights=2, light_dim=64, tex_sizes=(64, 32))
+    rs = [Renderer(rrd.tile_config(s.cfg, 2, k, 16, 24)) for k in range(2)]
+    for r in rs:
+        s.upload(r)
+    rr.mgpu_connect_local(rs)
+    rs[1].frame_shadows(1)                    # rank 1 alone: rank 0's faces and its "target is free" flag never come
+    rs[1].frame_draw(s.c_pos, s.c_rot, s.clear)
+    with pytest.raises(RRError) as e:
+        rs[1].sync()
+    assert e.value.code == -5, e.value
