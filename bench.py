@@ -336,6 +336,11 @@ def run_ours(args):
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_total, launches = float(tmax[0]), int(tsum[1])
+    push_bytes = None
+    if p2p and world > 1:                  # cubemap bytes the ranks stored into each other's memory during the timed frames (NVLink)
+        pb = torch.tensor([float(r.mgpu_pushed_bytes())], dtype=torch.float64, device=dev)
+        dist.all_reduce(pb, op=dist.ReduceOp.SUM)
+        push_bytes = float(pb[0]) / (args.steps + args.warmup)
     if os.environ.get("RR_BENCH_RANK_TIMINGS"):
         r.set_profiling(True)
         frame(10_000)
@@ -426,8 +431,8 @@ def run_ours(args):
         r.frame_draw(c_pos, c_rot, s.clear)
         barrier()
         if rank == 0:
-            dev = r.read_rgba8()
-            e2e_check = int((dev != shared.frames[last % D]).any(axis=-1).sum())
+            dev_img = r.read_rgba8()
+            e2e_check = int((dev_img != shared.frames[last % D]).any(axis=-1).sum())
             e2e["host_frame_pixels_differing_from_device_composite"] = e2e_check
         r.swap_buffers()
         barrier()
@@ -441,6 +446,13 @@ def run_ours(args):
                                                                                 else f"bands{world}+faces{world} nccl") if world > 1 else "single",
                                                                 "band_halo": args.halo if world > 1 else None}),
                 "fps": round(1e3 / ms, 2), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+        if push_bytes is not None:
+            slab_bytes = 4 * 6 * L * L * n_shadow
+            line["nvlink"] = {"face_push_bytes_per_frame": int(push_bytes), "cubemap_bytes": int(slab_bytes),
+                              "what": "bytes k_push_faces stored into peer memory per frame, all ranks (only 512-byte chunks that hold a sample or held one "
+                                      "last time are sent; a full exchange would move cubemap_bytes x (N-1)); colour rows go straight from k_shade into "
+                                      "rank 0's target or, with distributed read-back, to the host over each GPU's own PCIe link",
+                              "GBps_if_serial": round(push_bytes / (ms * 1e-3) / 1e9, 1)}
 
     # ---- stage profile (every N: max over ranks), verification of the split frame (N > 1, always), roofline, CPU baseline (N = 1)
     stage_keys = ("shadow_depth_ms", "setup_ms", "depth_ms", "id_ms", "shade_ms", "frame_ms")
@@ -526,11 +538,11 @@ def run_ours(args):
         dom = max(ms_of, key=lambda k: ms_of[k])
         achieved = B[dom] / (ms_of[dom] * 1e-3) / 1e9
         peak = hbm * world                     # N contexts: the frame's bytes over the max-over-ranks stage time against N x the measured copy bandwidth
-        line["roofline"] = {"bound": "hbm", "limiter": "instruction issue (ncu: DRAM 3-6 % of peak, issue slots 50-60 % busy; profiles/r2*_ncu_*.txt)",
+        line["roofline"] = {"bound": "hbm", "limiter": "instruction issue (ncu: DRAM 3-7 % of peak, issue slots 50-68 % busy; profiles/r2_ncu_top_kernels.txt)",
                             "kernel": {"setup": "k_setup_main (+ inline depth of small triangles)",
                                        "shadow": "k_shadow_setup (all %d lights, inline raster) + k_raster_shadow_warp" % S,
-                                       "depth": "k_scan_big + k_raster_small<depth> + k_raster_big<depth>",
-                                       "id": "k_ids_list + k_raster_small<ids> + k_raster_big<ids>", "shade": "k_shade_pre + k_shade"}[dom],
+                                       "depth": "k_raster_warp<depth> (work list of the fragments not rasterised inline)",
+                                       "id": "k_ids_list + k_raster_warp<ids>", "shade": "k_shade_pre4 + k_shade"}[dom],
                             "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                             "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""), "algorithmic_bytes_per_launch": int(B[dom]), "avg_ms": round(ms_of[dom], 4)}
         if world == 1:

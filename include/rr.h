@@ -220,6 +220,7 @@ int rr_mgpu_disconnect(rr_ctx*);
  * exactly those rows into `host_rgba8` — pass every context the SAME host frame (memory shared between the processes and
  * page-locked in each with rr_host_register): each GPU then moves 1/world of the frame over its own PCIe link. */
 int rr_mgpu_set_readback(rr_ctx*, int distributed);
+int rr_mgpu_pushed_bytes(rr_ctx*, uint64_t* bytes);          /* statistics: bytes of cubemap faces this context stored into its peers (NVLink) since the last call */
 int rr_host_register(void* p, size_t nbytes);     /* cudaHostRegister(portable): make caller-owned (e.g. shared) memory a DMA target */
 int rr_host_unregister(void* p);
 

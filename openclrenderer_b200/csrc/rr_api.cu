@@ -392,7 +392,7 @@ int mg_push(rr_ctx* c, cudaStream_t st, int b, uint32_t epoch) {
     MgPushParams p;
     p.local = c->mg.shadow[b]; p.face_words = (uint32_t)c->L * (uint32_t)c->L; p.prev_dirty = c->mg.prev_dirty[b];
     p.n_pairs = mg_owned_pairs(c, p.pair);
-    p.n_peers = 0; p.sig.n = 0; p.sig.counter = &c->mg.ctrl->push_done; p.sig.value = epoch;
+    p.n_peers = 0; p.sig.n = 0; p.sig.counter = &c->mg.ctrl->push_done; p.sig.value = epoch; p.pushed = &c->mg.ctrl->pushed_chunks;
     for (int q = 0; q < c->mg.world; q++) {
         if (q == c->mg.rank) continue;
         p.peer[p.n_peers++] = c->mg.peer_shadow[q][b];
@@ -1610,6 +1610,19 @@ int rr_mgpu_disconnect(rr_ctx* c) {
         c->mg.exported = false;
     }
     cudaGetLastError();
+    return RR_OK;
+}
+
+// bytes this context's k_push_faces has stored into peer memory (over NVLink) since the last call: 512-byte chunks x peers
+int rr_mgpu_pushed_bytes(rr_ctx* c, uint64_t* bytes) {
+    if (!c || !bytes) return fail(RR_ERR_INVALID, "null argument");
+    *bytes = 0;
+    if (!c->mg.connected) return RR_OK;
+    CU(cudaStreamSynchronize(c->stream2));
+    uint32_t chunks = 0;
+    CU(cudaMemcpy(&chunks, &c->mg.ctrl->pushed_chunks, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(&c->mg.ctrl->pushed_chunks, 0, 4));
+    *bytes = (uint64_t)chunks * MG_PUSH_CHUNK_WORDS * 4 * (uint64_t)std::max(0, c->mg.world - 1);
     return RR_OK;
 }
 

@@ -1397,9 +1397,10 @@ struct MgCtrl {
     uint32_t draw_flag[MG_MAX_WORLD];       // [q] = last draw epoch rank q has finished storing into this context's colour target
     uint32_t push_done, shade_done;         // last-CTA counters of the local producing kernels
     uint32_t error;                         // bit 0: a wait timed out
+    uint32_t pushed_chunks;                 // statistics: 512-byte chunks k_push_faces has sent to each peer since the last rr_mgpu_pushed_bytes
     uint32_t fb_free;                       // written by rank 0: last draw epoch whose colour target on rank 0 may be stored into (the copy of
                                             // the frame that used the ring slot before has left it); peers wait for it before their first store
-    uint32_t _pad[12];
+    uint32_t _pad[11];
 };
 
 struct MgSignal {                           // raised by the last CTA of a kernel; n == 0: nothing to do
@@ -1466,6 +1467,7 @@ struct MgPushParams {
     int n_pairs;
     uint32_t face_words;                    // L * L
     uint8_t* prev_dirty;                    // [n_pairs * face_words / MG_PUSH_CHUNK_WORDS] of this buffer
+    uint32_t* pushed;                       // statistics counter (MgCtrl::pushed_chunks of this context)
     MgSignal sig;
 };
 
@@ -1482,6 +1484,7 @@ __global__ void __launch_bounds__(256) k_push_faces(const MgPushParams P) {
         const bool was = P.prev_dirty[ch] != 0;
         if (dirty || was) {
             for (int q = 0; q < P.n_peers; q++) *reinterpret_cast<uint4*>(P.peer[q] + off) = v;
+            if (lane == 0) atomicAdd(P.pushed, 1u);
         }
         __syncwarp();
         if (lane == 0 && dirty != was) P.prev_dirty[ch] = dirty ? 1 : 0;

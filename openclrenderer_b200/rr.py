@@ -57,6 +57,8 @@ def load_library():
         _LIB.rr_mgpu_connect_local.argtypes = [C.POINTER(_P), C.c_int]
         _LIB.rr_mgpu_disconnect.restype = C.c_int
         _LIB.rr_mgpu_disconnect.argtypes = [_P]
+        _LIB.rr_mgpu_pushed_bytes.restype = C.c_int
+        _LIB.rr_mgpu_pushed_bytes.argtypes = [_P, C.POINTER(C.c_uint64)]
         _LIB.rr_mgpu_set_readback.restype = C.c_int
         _LIB.rr_mgpu_set_readback.argtypes = [_P, C.c_int]
         _LIB.rr_host_register.restype = C.c_int
@@ -162,6 +164,14 @@ class Renderer(CApi):
         r = self._lib.rr_mgpu_set_readback(self._ctx, int(distributed))
         if r != RR_OK:
             raise RRError(r, self.last_error())
+
+    def mgpu_pushed_bytes(self):
+        """bytes of cubemap faces this context has stored into its peers' memory since the last call"""
+        n = C.c_uint64(0)
+        r = self._lib.rr_mgpu_pushed_bytes(self._ctx, C.byref(n))
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+        return int(n.value)
 
     def mgpu_disconnect(self):
         self._lib.rr_mgpu_disconnect(self._ctx)

@@ -19,12 +19,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from openclrenderer_b200 import scene  # noqa: E402
 
+def _sph_close():
+    """the sphere field seen from inside it: a quarter of the screen covered, triangles from sub-pixel to hundreds of pixels, some cut
+    by the near plane (multi-chunk fragments, the clip path) — the `sph` scene alone covers under 1 % of its frame."""
+    s = scene.scene_spheres(960, 540, n_spheres=24, grid=(6, 4), seed=7, n_lights=4, light_dim=256, tex_sizes=(256, 128, 64, 64))
+    s.c_pos = (511.0, 25.0, 257.0)          # ten units off the surface of sphere 3: 27 % of the frame covered, triangles of up to 83 chunks
+    s.c_rot = (0.0, 0.0, 0.0)
+    return s
+
+
 SCENES = {
     "c1A": lambda: scene.scene_c1("A"),
     "c1B": lambda: scene.scene_c1("B"),
     "c2": lambda: scene.scene_c2(),
     "c2_small": lambda: scene.scene_c2(640, 360, 256),
     "sph": lambda: scene.scene_spheres(960, 540, n_spheres=24, grid=(6, 4), seed=7, n_lights=4, light_dim=256, tex_sizes=(256, 128, 64, 64)),
+    "sph_close": _sph_close,
 }
 
 
@@ -53,7 +63,7 @@ def main():
         # allocation-order independent view of the fragment records: sorted (triangle, chunk, bits(rconst), object)
         key = np.lexsort((fr[:, 1], fr[:, 0]))
         out[name + "_frags"] = fr[key][:, [0, 1, 3, 4]]
-        if name in ("c2_small", "sph"):
+        if name in ("c2_small", "sph", "sph_close"):
             out[name + "_shadow0"] = r.read_shadow(0, 0)
         meta[name] = {"options": r.options, "fragments": int(len(fr)), "covered": int((out[name + "_depth"] != 0xFFFFFFFF).sum())}
         print(name, meta[name]["fragments"], meta[name]["covered"])

@@ -19,7 +19,7 @@ def gold():
     return {k: z[k] for k in z.files}
 
 
-@pytest.mark.parametrize("name,tri_floor", [("c1A", 0.999), ("c1B", 0.999), ("c2", 0.99), ("c2_small", 0.99), ("sph", 0.95)])
+@pytest.mark.parametrize("name,tri_floor", [("c1A", 0.999), ("c1B", 0.999), ("c2", 0.99), ("c2_small", 0.99), ("sph", 0.95), ("sph_close", 0.95)])
 def test_cuda_matches_reference_golden(gold, name, tri_floor):
     s = SCENES[name]()
     g = Renderer(s.cfg)
@@ -35,7 +35,7 @@ def _refcl():
     return ref_opencl
 
 
-@pytest.mark.parametrize("name", ["c1A", "c2_small", "sph"])
+@pytest.mark.parametrize("name", ["c1A", "c2_small", "sph", "c2", "sph_close"])
 def test_live_reference_pinned_equals_oracle_and_cuda(name):
     """pinned arithmetic: reference == oracle == CUDA, bit for bit, on depth, shadow cubemaps, atlas and fragment multiset."""
     cl = _refcl()
@@ -67,7 +67,7 @@ def test_live_reference_pinned_equals_oracle_and_cuda(name):
     assert diff[same | ~cov].max() <= 2
 
 
-@pytest.mark.parametrize("name", ["c1A", "c2_small"])
+@pytest.mark.parametrize("name", ["c1A", "c2_small", "c2", "sph", "sph_close"])
 def test_live_reference_as_shipped_is_close(name):
     """as shipped (-cl-fast-relaxed-math, FP_CONTRACT ON, native_* intrinsics): same coverage and fragments up to a handful
     of boundary pixels, depth within the reference's own +-20 tolerance almost everywhere, colours within +-2 LSB on >= 99.9 %."""

@@ -39,7 +39,7 @@ def check_against_golden(r, gold, name, tri_floor):
     return float((diff <= 1).mean())
 
 
-@pytest.mark.parametrize("name,tri_floor", [("c1A", 0.999), ("c1B", 0.999), ("c2_small", 0.99), ("sph", 0.95), ("c2", 0.99)])
+@pytest.mark.parametrize("name,tri_floor", [("c1A", 0.999), ("c1B", 0.999), ("c2_small", 0.99), ("sph", 0.95), ("c2", 0.99), ("sph_close", 0.95)])
 def test_oracle_matches_reference_golden(gold, name, tri_floor):
     s = SCENES[name]()
     o = Oracle(s.cfg, threads=0)
