@@ -286,7 +286,8 @@ int ensure_objlite(rr_ctx* c) {
 
 template <int MODE>
 int raster(rr_ctx* c, cudaStream_t st, const RasterParams& rp) {
-    k_raster_warp<MODE><<<grid_for(c, 4), 256, 0, st>>>(rp);
+    static const int per_sm = getenv("RR_RASTER_GRID") ? atoi(getenv("RR_RASTER_GRID")) : 8;
+    k_raster_warp<MODE><<<grid_for(c, per_sm), 256, 0, st>>>(rp);
     c->launches++;
     CU(cudaGetLastError());
     return RR_OK;
@@ -487,7 +488,11 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (const char* e = getenv("RR_SHADOW_PRETEST")) c->shadow_pretest = atoi(e) != 0;
     if (const char* e = getenv("RR_TEX_OBJECTS")) c->use_tex_objects = atoi(e) != 0;
     auto bail = [&](const char* what) { fail(RR_ERR_CUDA, "rr_create: %s: %s", what, cudaGetErrorString(cudaGetLastError())); rr_destroy(c); return (rr_ctx*)nullptr; };
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+    // RR_STREAM_PRIO (A/B knob): 1 = the main view's stream outranks the shadow stream, 2 = the other way round, 0 = equal
+    int prio_lo = 0, prio_hi = 0, prio_mode = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);            // lo = least urgent (numerically largest)
+    if (const char* e = getenv("RR_STREAM_PRIO")) prio_mode = atoi(e);
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_mode == 1 ? prio_hi : prio_lo) != cudaSuccess) return bail("stream");
     for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail("event");
     const size_t P = (size_t)c->W * c->H;
     for (int i = 0; i < 2; i++) {
@@ -506,7 +511,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaMalloc((void**)&c->d_worklist, (size_t)c->cap_frags * 4 + 16) != cudaSuccess) return bail("work list");
     if (cudaMalloc((void**)&c->d_extra, (size_t)c->cap_frags * 4 + 16) != cudaSuccess) return bail("extra list");
     if (cudaMalloc((void**)&c->d_counters, CTR_COUNT * 4) != cudaSuccess) return bail("counters");
-    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail("stream2");
+    if (cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_mode == 2 ? prio_hi : prio_lo) != cudaSuccess) return bail("stream2");
     if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail("stream3");
     if (cudaEventCreateWithFlags(&c->ev_draw_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     for (int i = 0; i < RR_RING_MAX; i++) if (cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");

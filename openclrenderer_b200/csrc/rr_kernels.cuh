@@ -959,7 +959,7 @@ __device__ __forceinline__ void warp_alloc2(uint32_t* counters, uint32_t nc, uin
 // Minimum resident CTAs per SM the register allocation is asked to allow (build-time knobs for A/B runs:
 // -DRR_LB_SHADOW_SETUP=n, -DRR_LB_SHADE=n, RR_LIB=<other build>; examples/lb_sweep.sh).
 #ifndef RR_LB_SHADOW_SETUP
-#define RR_LB_SHADOW_SETUP 6
+#define RR_LB_SHADOW_SETUP 7
 #endif
 #define RR_LB_SHADOW_SETUP_ATTR __launch_bounds__(128, RR_LB_SHADOW_SETUP)
 #ifdef RR_LB_SHADE
