@@ -228,6 +228,7 @@ def run_ours(args):
     if world > 1:
         # keep stdout to the one JSON line: some boxes print NCCL's version banner there unless the level is set explicitly
         os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # whatever NCCL logs (its version banner at WARN) goes to stderr
         dist.init_process_group("nccl", device_id=dev)
     s = make_scene(args.workload)
     W, H, L = s.cfg.width, s.cfg.height, s.cfg.light_dim
