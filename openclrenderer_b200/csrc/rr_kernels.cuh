@@ -345,7 +345,7 @@ __device__ __noinline__ void inline_literal_emit(float3 xr, float3 yr, float A, 
             const float fd = fmaf(A, x, fmaf(B, y, C));
             const uint32_t d = sat_u32(RR_U32MAXF / fd);
             const uint32_t px = (uint32_t)((int)(y * width) + (int)x);
-            atomicMin(target + px, d);
+            red_min_u32(target + px, d);
             if (samples) { samples[n] = make_uint2(px, d); sfrag[n] = fidx; n++; }
         }
         mask >>= 1;
@@ -430,7 +430,7 @@ struct InlineRaster {
                 const float fd = fmaf(A, x, fmaf(B, y, C));
                 const uint32_t dd = sat_u32(RR_U32MAXF / fd);
                 const uint32_t px = (uint32_t)((int)(y * width) + (int)x);
-                atomicMin(target + px, dd);
+                red_min_u32(target + px, dd);
                 if (rec) { sl.samples[at] = make_uint2(px, dd); sl.frag[at] = fidx; at++; }
             }
         } else {
@@ -566,42 +566,49 @@ __global__ void __launch_bounds__(PROLOGUE_THREADS) k_frame_prologue(const Prolo
     if (tid == 0) s_last = atomicAdd(&P.counters[CTR_PROLOGUE_TICKET], 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
-    // ---- last CTA: compaction over all setup blocks. Two passes over the flags (count, then place); a warp takes 32 blocks per
-    // step with one 16-bit load per lane, so the loads of a pass are independent and stay in flight together.
+    // ---- last CTA: ordered compaction over all setup blocks, 8 * PROLOGUE_THREADS blocks per round: a thread takes eight
+    // consecutive blocks (their sixteen cluster flags are one 16-byte load: a single round trip per round), the CTA scans the
+    // per-thread (surviving blocks, skipped slots) pairs, every thread places its survivors.
     const uint32_t n_clusters = P.cv.n_clusters, n_tris = P.n_tris, n_blocks = P.n_blocks;
     const unsigned short* vis16 = reinterpret_cast<const unsigned short*>(P.vis);      // written by other CTAs of this launch: ld.cg
-    constexpr uint32_t NW = PROLOGUE_THREADS / 32;
-    const uint32_t per_w = ((n_blocks + NW * 32 - 1) / (NW * 32)) * 32;
-    const uint32_t w0 = min(n_blocks, warp * per_w), w1 = min(n_blocks, w0 + per_w);
-    auto culled = [&](uint32_t b) {
-        const uint32_t v = __ldcg(vis16 + b);
-        return (v & 0xFFu) == 0u && (2 * b + 1 >= n_clusters || (v >> 8) == 0u);
-    };
+    constexpr uint32_t NW = PROLOGUE_THREADS / 32, PER_T = 8;
     const uint32_t last_count = n_tris - (n_blocks - 1) * 2u * CLUSTER_TRIS;           // only the last block can be short
-    uint32_t na = 0, ns = 0;
-    for (uint32_t base = w0; base < w1; base += 32) {
-        const uint32_t b = base + lane;
-        if (b < w1) { if (culled(b)) ns += (b == n_blocks - 1) ? last_count : 2u * CLUSTER_TRIS; else na++; }
-    }
+    uint32_t ta = 0, ts = 0;                                                           // running totals (CTA-uniform)
+    for (uint32_t chunk = 0; chunk < n_blocks; chunk += PROLOGUE_THREADS * PER_T) {
+        const uint32_t b0 = chunk + (uint32_t)tid * PER_T;
+        uint32_t v[PER_T];
+        if (b0 + PER_T <= n_blocks) {
+            const uint4 q = __ldcg(reinterpret_cast<const uint4*>(vis16 + b0));       // b0 is a multiple of 8: 16-byte aligned
+            v[0] = q.x & 0xFFFFu; v[1] = q.x >> 16; v[2] = q.y & 0xFFFFu; v[3] = q.y >> 16;
+            v[4] = q.z & 0xFFFFu; v[5] = q.z >> 16; v[6] = q.w & 0xFFFFu; v[7] = q.w >> 16;
+        } else {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, d); ns += __shfl_xor_sync(0xffffffffu, ns, d); }
-    if (lane == 0) { s_a[warp] = na; s_s[warp] = ns; }
-    __syncthreads();
-    uint32_t at = 0, sk = 0, ta = 0, ts = 0;
-    for (int w = 0; w < (int)NW; w++) { if (w < warp) { at += s_a[w]; sk += s_s[w]; } ta += s_a[w]; ts += s_s[w]; }
-    for (uint32_t base = w0; base < w1; base += 32) {
-        const uint32_t b = base + lane;
-        const bool in = b < w1;
-        const bool cu = in && culled(b);
-        const unsigned mc = __ballot_sync(0xffffffffu, cu), ma = __ballot_sync(0xffffffffu, in && !cu);
-        const unsigned lt = (1u << lane) - 1u;
-        if (in && !cu) {
-            const uint32_t pos = at + __popc(ma & lt);
-            P.active[pos] = b;
-            P.skipped_before[pos] = sk + 2u * CLUSTER_TRIS * __popc(mc & lt);         // a short last block has nothing behind it
+            for (uint32_t k = 0; k < PER_T; k++) v[k] = b0 + k < n_blocks ? (uint32_t)__ldcg(vis16 + b0 + k) : 0xFFFFu;
         }
-        at += __popc(ma);
-        sk += 2u * CLUSTER_TRIS * __popc(mc);
+        uint32_t cmask = 0, na = 0, ns = 0;                                            // bit k: block b0 + k is culled
+#pragma unroll
+        for (uint32_t k = 0; k < PER_T; k++) {
+            const uint32_t b = b0 + k;
+            if (b >= n_blocks) break;
+            const bool cu = (v[k] & 0xFFu) == 0u && (2 * b + 1 >= n_clusters || (v[k] >> 8) == 0u);
+            if (cu) { cmask |= 1u << k; ns += (b == n_blocks - 1) ? last_count : 2u * CLUSTER_TRIS; } else na++;
+        }
+        uint32_t ia = na, is = ns;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, ia, d), y = __shfl_up_sync(0xffffffffu, is, d); if (lane >= d) { ia += x; is += y; } }
+        __syncthreads();                                                               // (s_a / s_s of the previous round are consumed)
+        if (lane == 31) { s_a[warp] = ia; s_s[warp] = is; }
+        __syncthreads();
+        uint32_t at = ta + ia - na, sk = ts + is - ns, ca = 0, cs = 0;
+        for (int w = 0; w < (int)NW; w++) { if (w < warp) { at += s_a[w]; sk += s_s[w]; } ca += s_a[w]; cs += s_s[w]; }
+#pragma unroll
+        for (uint32_t k = 0; k < PER_T; k++) {
+            const uint32_t b = b0 + k;
+            if (b >= n_blocks) break;
+            if (cmask & (1u << k)) sk += (b == n_blocks - 1) ? last_count : 2u * CLUSTER_TRIS;
+            else { P.active[at] = b; P.skipped_before[at] = sk; at++; }
+        }
+        ta += ca; ts += cs;
     }
     if (tid == 0) {
         P.counters[CTR_PROLOGUE_TICKET] = 0u;
@@ -830,16 +837,16 @@ __device__ __forceinline__ void emit_sample(const RasterParams& P, float x, floa
     const float fd = fmaf(A, x, fmaf(B, y, C));
     const uint32_t d = sat_u32(RR_U32MAXF / fd);
     if (MODE == RM_DEPTH) {
-        atomicMin(P.depth + ((int)(y * P.width) + (int)x), d);
+        red_min_u32(P.depth + ((int)(y * P.width) + (int)x), d);
     } else if (MODE == RM_SHADOW) {
-        atomicMin(P.depth + ((size_t)P.slab_of_light[face >> 8] * 6 + (face & 0xFF)) * P.W * P.W + ((int)(y * P.width) + (int)x), d);
+        red_min_u32(P.depth + ((size_t)P.slab_of_light[face >> 8] * 6 + (face & 0xFF)) * P.W * P.W + ((int)(y * P.width) + (int)x), d);
     } else {
         const int px = (int)y * P.W + (int)x;
         const uint32_t val = P.depth[px];
         // racing plain stores in the reference; canonical winner = highest fragment index (last writer in id order).
         // The id image holds fragment index + 1: 0 = no fragment passed the test (e.g. depth < 20, where the reference's
         // unsigned window wraps, cl2.cl:5534) — such pixels are shaded like uncovered ones instead of with a stale id (q7)
-        if (d > val - RR_BUF_ERROR && d < val + RR_BUF_ERROR) atomicMax(P.ids + px, f + 1u);
+        if (d > val - RR_BUF_ERROR && d < val + RR_BUF_ERROR) red_max_u32(P.ids + px, f + 1u);
     }
 }
 
@@ -878,7 +885,7 @@ __global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const uin
         if (row < row_lo || row >= row_hi) continue;
         if (rowmask && !(rowmask[row] & ROW_OWNED)) continue;
         const uint32_t val = depth[sm.x];
-        if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) atomicMax(ids + sm.x, sl.frag[i] + 1u);
+        if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) red_max_u32(ids + sm.x, sl.frag[i] + 1u);
     }
 }
 
@@ -1010,7 +1017,7 @@ __device__ __noinline__ void shadow_raster_small_literal(float3 xr, float3 yr, f
     scan_chunk(mm, RR_OP_SIZE_LIGHT, 0u, [&](float x, float y) {
         if (point_in_tri(x, y, xr.x, yr.x, xr.y, yr.y, xr.z, yr.z)) {
             const float fd = fmaf(A, x, fmaf(B, y, C));
-            atomicMin(target + ((int)(y * L) + (int)x), sat_u32(RR_U32MAXF / fd));
+            red_min_u32(target + ((int)(y * L) + (int)x), sat_u32(RR_U32MAXF / fd));
         }
     });
 }
@@ -1077,7 +1084,7 @@ __device__ __forceinline__ void shadow_raster_small(const ShadowWarpQueue& Q, in
         const int r = (int)(((float)i + 0.5f) * iwt);       // i / wt: i < 32, wt <= 32, so (i + 0.5) / wt is at least 1/64 away from an integer
         const float x = x0 + (float)(i - r * wt), y = y0 + (float)r;
         const float fd = fmaf(A, x, fmaf(B, y, C));
-        atomicMin(target + ((int)(y * L) + (int)x), sat_u32(RR_U32MAXF / fd));
+        red_min_u32(target + ((int)(y * L) + (int)x), sat_u32(RR_U32MAXF / fd));
     }
 }
 
@@ -2359,7 +2366,7 @@ __global__ void __launch_bounds__(256) k_bench_atomic_min(uint32_t* buf, uint32_
     uint32_t s = wang_hash(blockIdx.x * blockDim.x + threadIdx.x + 1u);
     for (uint32_t i = 0; i < iters; i++) {
         s = rand_xorshift(s);
-        atomicMin(buf + (s & n_words_mask), s >> 3);
+        red_min_u32(buf + (s & n_words_mask), s >> 3);
     }
 }
 

@@ -58,6 +58,11 @@ __device__ __forceinline__ float4 mad4(float4 a, float b, float4 c) {
 }
 __device__ __forceinline__ float3 xyz(float4 v) { return make_float3(v.x, v.y, v.z); }
 
+// atomic_min / atomic_max whose result nobody reads, as a reduction: red.global.{min,max}.u32 is fire-and-forget at the L2 (no
+// return path). Written out because ptxas kept ATOMG with a discarded destination in the setup kernel (ncu: lts op_atom).
+__device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.min.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.max.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
 // saturating float -> uint32 (NaN -> 0, negative -> 0, >= 2^32 -> UINT_MAX): cvt.rzi.u32.f32 does exactly this
 __device__ __forceinline__ uint32_t sat_u32(float f) { return __float2uint_rz(f); }
 

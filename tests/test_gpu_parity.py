@@ -323,3 +323,46 @@ def test_object_transform_patches_match_oracle():
         for k in range(2):
             assert np.array_equal(g.read_shadow(0, k), o.read_shadow(0, k))
         assert_frame_parity(g, o, label=f"patched step {step}")
+
+
+def _micro_soup(seed, n, w, h, light_dim):
+    """thousands of tiny triangles (0.2 .. 8 px) placed in SCREEN space over the whole frame, its borders and corners, a band of
+    them in the top rows (where the walk's float row counter can lag, cl2.cl:5076) and some sub-pixel ones that round to
+    collinear vertices: the cases the exact integer rasteriser of the setup kernels special-cases, against the literal walk."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cfg = Config.default(w, h, light_dim=light_dim)
+    fov = scene.fov_for(cfg)
+    cx = rng.uniform(-12, w + 12, size=n)
+    cy = rng.uniform(-12, h + 12, size=n)
+    top = rng.uniform(size=n) < 0.25
+    cy[top] = rng.uniform(-4, 60, size=top.sum())
+    left = rng.uniform(size=n) < 0.1
+    cx[left] = rng.uniform(-4, 30, size=left.sum())
+    size = np.exp(rng.uniform(np.log(0.2), np.log(8.0), size=n))
+    z = np.exp(rng.uniform(np.log(60.0), np.log(4000.0), size=n))
+    px = cx[:, None] + rng.normal(size=(n, 3)) * size[:, None]
+    py = cy[:, None] + rng.normal(size=(n, 3)) * size[:, None]
+    pz = z[:, None] * (1.0 + rng.normal(size=(n, 3)) * 0.01)
+    tris = np.zeros(n, dtype=TRIANGLE)
+    pos = np.stack([(px - w / 2) * pz / fov, (py - h / 2) * pz / fov, pz], axis=-1)
+    tris["vertices"]["pos"][:, :, :3] = pos.astype(np.float32)
+    tris["vertices"]["normal"][:, :, 2] = -1.0
+    tris["vertices"]["vt"] = rng.uniform(0, 1, size=(n, 3, 2)).astype(np.float32)
+    tris["vertices"]["object_id"][:, 0] = rng.integers(0, 2, size=n)       # half two-sided, half culled by winding (early shadow back-face cull)
+    objs = np.array([scene.make_obj_desc(pos=(0, 0, 0), scale=1.0, tid=0, feature_flag=FEATURE_TWO_SIDED),
+                     scene.make_obj_desc(pos=(0, 0, 0), scale=1.0, tid=0)], dtype=OBJ_DESC)
+    lights = np.array([scene.make_light((40, -60, 30), shadow=1), scene.make_light((-900, 500, 2500), shadow=1)], dtype=LIGHT)
+    tex = [scene.procedural_texture(64, 9)]
+    return scene.Scene(cfg, tris, objs, lights, tex, c_pos=(0, 0, 0), c_rot=(0, 0, 0), clear=(0, 0, 0, 1.0), name=f"micro{seed}")
+
+
+@pytest.mark.parametrize("seed,w,h,L", [(11, 640, 360, 64), (12, 333, 217, 128), (13, 41 * 8, 200, 256)])
+def test_micro_triangles_on_borders_and_top_rows(seed, w, h, L):
+    s = _micro_soup(seed, 20000, w, h, L)
+    g, o = render_both(s, frames=2, threads=0)
+    for k in range(2):
+        assert np.array_equal(g.read_shadow(0, k), o.read_shadow(0, k)), f"cubemap {k} differs"
+    st = assert_frame_parity(g, o, label=s.name)
+    assert st["covered"] > 2000
+    d = o.read_depth()
+    assert (d[:8] != 0xFFFFFFFF).any() and (d[:, :4] != 0xFFFFFFFF).any(), "the scene must reach the top rows and the left columns"

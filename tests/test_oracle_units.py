@@ -199,3 +199,40 @@ def test_scan_covers_half_open_box_with_one_pixel_overlap():
     mm = (0, 41, 0, 200)
     cols0 = {tuple(q) for d in range(17) for q in ob.unit_scan(mm, 500, d) if q[0] == 0}
     assert 0 < len(cols0) < 200
+
+
+# ---- the invariants the exact integer rasteriser of the setup kernels relies on (rr_kernels.cuh: shadow_raster_small, InlineRaster) ----
+@settings(max_examples=300, deadline=None)
+@given(st.integers(0, 4000), st.integers(1, 48), st.integers(0, 4200), st.integers(1, 48))
+def test_small_box_walk_has_no_lagging_row_when_rows_fit_under_min_y(mm0, w, mm2, h):
+    """a single small chunk (<= 48 slots) whose box starts at row min_y >= rows - 1 is walked exactly row-major: the float row
+    counter floor(fma(k, 1/width, min_y)) cannot lag at a row start r * width when r <= min_y (the fast path's condition)"""
+    if w * h > 48 or h - 1 > mm2:
+        return
+    px = ob.unit_scan((mm0, mm0 + w, mm2, mm2 + h), 300, 0)
+    want = [(x, y) for y in range(mm2, mm2 + h) for x in range(mm0, mm0 + w)]
+    assert [tuple(p) for p in px] == want
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.integers(-2047, 2047), min_size=6, max_size=6), st.integers(0, 2 ** 31))
+def test_point_in_tri_on_integer_vertices_is_closed_triangle_membership(v, seed):
+    """rounded vertices with small extents: every partial sum of point_in_tri (cl2.cl:4798-4807) is an integer below 2^24, so the
+    fp32 result equals exact integer arithmetic — inside <=> s >= 0, t >= 0, s + t <= 2|A| — and a covered pixel lies inside the
+    vertices' own bounding box (the fast path visits nothing else)"""
+    x0, y0 = v[0], v[1]
+    x1, y1 = x0 + v[2] % 65 - 32, y0 + v[3] % 65 - 32
+    x2, y2 = x0 + v[4] % 65 - 32, y0 + v[5] % 65 - 32
+    rng = np.random.default_rng(seed)
+    A2 = -y1 * x2 + y0 * (-x1 + x2) + x0 * (y1 - y2) + x1 * y2          # 2A, exact
+    sg = -1 if A2 < 0 else 1
+    lo_x, hi_x, lo_y, hi_y = min(x0, x1, x2), max(x0, x1, x2), min(y0, y1, y2), max(y0, y1, y2)
+    for _ in range(40):
+        px, py = int(rng.integers(lo_x - 2, hi_x + 3)), int(rng.integers(lo_y - 2, hi_y + 3))
+        s = (y0 * x2 - x0 * y2 + (y2 - y0) * px + (x0 - x2) * py) * sg
+        t = (x0 * y1 - y0 * x1 + (y0 - y1) * px + (x1 - x0) * py) * sg
+        want = s >= 0 and t >= 0 and s + t <= abs(A2) and A2 != 0
+        got = bool(ob.load_oracle().orc_unit_point_in_tri(float(px), float(py), (np.array([x0, y0, x1, y1, x2, y2], np.float32)).ctypes.data_as(ob._P)))
+        assert got == want, (v, px, py, s, t, A2)
+        if got:
+            assert lo_x <= px <= hi_x and lo_y <= py <= hi_y
