@@ -542,8 +542,8 @@ def run_ours(args):
         line["roofline"] = {"bound": "hbm", "limiter": "instruction issue (ncu: DRAM 3-7 % of peak, issue slots 50-68 % busy; profiles/r2_ncu_top_kernels.txt)",
                             "kernel": {"setup": "k_setup_main (+ inline depth of small triangles)",
                                        "shadow": "k_shadow_setup (all %d lights, inline raster) + k_raster_shadow_warp" % S,
-                                       "depth": "k_raster_warp<depth> (work list of the fragments not rasterised inline)",
-                                       "id": "k_ids_list + k_raster_warp<ids>", "shade": "k_shade_pre4 + k_shade"}[dom],
+                                       "depth": "k_raster_warp_depth (work list of the fragments not rasterised inline)",
+                                       "id": "k_ids_list (stream over the recorded samples)", "shade": "k_shade_pre4 (list) + k_shade; k_clear_next on a side stream"}[dom],
                             "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                             "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""), "algorithmic_bytes_per_launch": int(B[dom]), "avg_ms": round(ms_of[dom], 4)}
         if world == 1:

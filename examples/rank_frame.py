@@ -33,3 +33,17 @@ for i in range(a.frames):
     r.swap_buffers()
 r.sync()
 print(r.timings())
+if os.environ.get("RANK_FRAME_LOOP"):                      # steady-state time of this rank's frames alone (no exchange, no profiling events)
+    import time
+    r.set_profiling(False)
+    n = int(os.environ["RANK_FRAME_LOOP"])
+    for rep in range(2):
+        t0 = time.perf_counter()
+        for i in range(n):
+            c_pos, c_rot = camera(s, i)
+            r.frame_shadows(0)
+            r.frame_draw(c_pos, c_rot, s.clear)
+            r.swap_buffers()
+        r.sync()
+        ms = 1e3 * (time.perf_counter() - t0) / n
+    print(f"rank {a.rank} of {a.world}: {ms:.4f} ms/frame alone")

@@ -159,12 +159,16 @@ struct rr_ctx {
     unsigned long long* d_lookback = nullptr;
     uint32_t lookback_blocks = 0;
     uint32_t* d_fragcnt = nullptr;               // per-fragment pixel-slot counts
-    uint32_t *d_worklist = nullptr, *d_extra = nullptr;    // fragments kernel1 / kernel2 still have to walk (k_setup_main -> k_raster_warp)
+    uint32_t *d_worklist = nullptr, *d_extra = nullptr;    // fragments kernel1 / kernel2 still have to walk (k_setup_main -> k_raster_warp_depth / k_ids_list)
     uint32_t* h_counters = nullptr;      // pinned (main counters, then shadow counters)
     // second raster workspace + stream: the shadow passes of a frame run concurrently with the main view's setup / depth /
     // id kernels (they only meet at shading). The reference shares g_tid_buf / g_cut_tri_mem between them and serialises.
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_shadow_done = nullptr;
+    // side stream of kernel3's streaming stores (k_clear_next): forked at the top of rr_frame_draw, joined in front of the shading list
+    cudaStream_t stream5 = nullptr;
+    cudaEvent_t ev_fork_clear = nullptr, ev_clear_done = nullptr;
+    bool split_clear = true;                     // RR_SPLIT_CLEAR=0: the stores stay in k_shade_pre4 on the main stream (A/B)
     bool shadow_pending = false;
     uint32_t *d_sfrags = nullptr, *d_sfragcnt = nullptr, *d_scounters = nullptr;
     float4* d_scutdown = nullptr;
@@ -284,10 +288,10 @@ int ensure_objlite(rr_ctx* c) {
     return RR_OK;
 }
 
-template <int MODE>
-int raster(rr_ctx* c, cudaStream_t st, const RasterParams& rp) {
-    static const int per_sm = getenv("RR_RASTER_GRID") ? atoi(getenv("RR_RASTER_GRID")) : 8;
-    k_raster_warp<MODE><<<grid_for(c, per_sm), 256, 0, st>>>(rp);
+// kernel1 for the work list (k_raster_warp_depth): depth + the covered samples kernel2 streams afterwards
+int raster_depth(rr_ctx* c, cudaStream_t st, const RasterParams& rp, const SampleList& sl) {
+    static const int per_sm = getenv("RR_RASTER_GRID") ? atoi(getenv("RR_RASTER_GRID")) : 6;      // 24 KB of sample stash per CTA of eight warps
+    k_raster_warp_depth<<<grid_for(c, per_sm), RW_WARPS * 32, 0, st>>>(rp, sl);
     c->launches++;
     CU(cudaGetLastError());
     return RR_OK;
@@ -418,12 +422,12 @@ static int preload_kernels() {
     const void* fns[] = {
         (const void*)k_repack, (const void*)k_objlite, (const void*)k_lightlite, (const void*)k_obj_rows, (const void*)k_cluster_bounds,
         (const void*)k_frame_prologue, (const void*)k_setup_main<false>, (const void*)k_setup_main<true>,
-        (const void*)k_raster_warp<RM_DEPTH>, (const void*)k_raster_warp<RM_IDS>,
-        (const void*)k_ids_list, (const void*)k_shadow_setup, (const void*)k_cluster_faces,
+        (const void*)k_raster_warp_depth,
+        (const void*)k_ids_list<true>, (const void*)k_ids_list<false>, (const void*)k_shadow_setup, (const void*)k_cluster_faces,
         (const void*)k_signal_flag, (const void*)k_signal_flags, (const void*)k_wait_flags, (const void*)k_push_faces, (const void*)k_fill_faces,
         (const void*)k_raster_shadow_warp, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip, (const void*)k_atlas_upload_batch, (const void*)k_atlas_mip_batch,
         (const void*)k_atlas_fill_colour, (const void*)k_atlas_from_raw,
-        (const void*)k_shade_pre, (const void*)k_shade_pre4, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_motion_blur, (const void*)k_motion_history, (const void*)k_godrays, (const void*)k_copy_u32,
+        (const void*)k_shade_pre, (const void*)k_shade_pre4<true, true>, (const void*)k_shade_pre4<false, true>, (const void*)k_shade_list, (const void*)k_clear_next, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_motion_blur, (const void*)k_motion_history, (const void*)k_godrays, (const void*)k_copy_u32,
     };
     for (const void* f : fns) {
         cudaFuncAttributes a;
@@ -503,6 +507,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaMalloc((void**)&c->d_normals, P * 4) != cudaSuccess) return bail("normals");
     if (cudaMalloc((void**)&c->d_shade_list, P * 4) != cudaSuccess) return bail("shade list");
     c->cap_samples = (uint32_t)std::min<size_t>(4 * P + (1u << 20), 0x7FFFFFFFu);
+    if (const char* e = getenv("RR_SAMPLE_CAP")) c->cap_samples = std::max<uint32_t>(1u, std::min<uint32_t>(c->cap_samples, (uint32_t)strtoul(e, nullptr, 10)));   // tests: force the `extra` path of kernel2
     if (cudaMalloc((void**)&c->d_samples, (size_t)c->cap_samples * 8) != cudaSuccess) return bail("sample list");
     c->cap_frags = cfg->max_fragments ? cfg->max_fragments : (16u << 20);
     if (cudaMalloc((void**)&c->d_frags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("fragment buffer");
@@ -517,6 +522,10 @@ rr_ctx* rr_create(const rr_config* cfg) {
     for (int i = 0; i < RR_RING_MAX; i++) if (cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (cudaEventCreateWithFlags(&c->ev_shadow_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    if (cudaStreamCreateWithFlags(&c->stream5, cudaStreamNonBlocking) != cudaSuccess) return bail("stream5");
+    if (cudaEventCreateWithFlags(&c->ev_fork_clear, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    if (cudaEventCreateWithFlags(&c->ev_clear_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    if (const char* e = getenv("RR_SPLIT_CLEAR")) c->split_clear = atoi(e) != 0;
     {
         const size_t srec = (size_t)c->cap_frags * RR_FRAG_WORDS / RR_SFRAG_WORDS;     // shadow records are 4 words
         if (cudaMalloc((void**)&c->d_sfrags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("shadow fragment buffer");
@@ -558,6 +567,9 @@ void rr_destroy(rr_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_shadow_done) cudaEventDestroy(c->ev_shadow_done);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->stream5) { cudaStreamSynchronize(c->stream5); cudaStreamDestroy(c->stream5); }
+    if (c->ev_fork_clear) cudaEventDestroy(c->ev_fork_clear);
+    if (c->ev_clear_done) cudaEventDestroy(c->ev_clear_done);
     cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite); cudaFree(c->d_obj_r2); cudaFree(c->d_obj_rows);
     cudaFree(c->d_clusters); cudaFree(c->d_cluster_vis); cudaFree(c->d_cluster_faces); cudaFree(c->d_active); cudaFree(c->d_skipped);
     cudaFree(c->d_rowmask); cudaFree(c->d_rowpfx);
@@ -1031,7 +1043,7 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         k_shadow_setup<<<(c->n_tris + 127) / 128, 128, 0, st>>>(sp);
         c->launches++;
         dp.frags = c->d_sfrags; dp.cutdown = c->d_scutdown; dp.fragcnt = c->d_sfragcnt; dp.counters = c->d_scounters; dp.cap_frags = sp.cap_frags;
-        dp.worklist = nullptr; dp.extra = nullptr;
+        dp.worklist = nullptr; dp.extra = nullptr; dp.shade_list = nullptr; dp.shade_count = nullptr;
         dp.n_index = CTR_S_NFRAG;
         dp.depth = buffer; dp.ids = nullptr; dp.width = (float)c->L; dp.height = (float)c->L; dp.W = c->L;
         dp.row_lo = 0; dp.row_hi = c->L; dp.rowmask = nullptr; dp.rowbit = 0;
@@ -1121,6 +1133,45 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
         c->launches++;
     }
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_F0], c->stream));
+    // kernel3's parameters (needed first: its streaming stores are launched now, on the side stream)
+    ShadeParams hp;
+    hp.tris = c->d_tris; hp.objs = c->d_objs; hp.objlite = c->d_objlite; hp.lightlite = c->d_lightlite; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
+    hp.depth = c->d_depth[c->cur]; hp.ids = c->d_ids[c->cur];
+    hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
+    if (c->mg.connected) c->d_rgba8 = (c->mg.rank == 0 || c->mg.local_readback) ? c->mg.fb[c->mg_target] : c->mg.fb0[c->mg_target];
+    hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
+    hp.atlas.texels = c->d_atlas; hp.atlas.nums = c->d_nums; hp.atlas.sizes = c->d_sizes; hp.atlas.mip_start = c->mipmap_start; hp.atlas.tex = c->atlas_tex;
+    hp.lights = c->d_lights; hp.n_lights = (int)c->lights.size();
+    hp.shadow_dyn = c->d_shadow_dyn; hp.shadow_static = c->d_shadow_static;
+    hp.faces = c->faces; hp.cam = cam;
+    hp.clear = clear_rgba ? make_float4(clear_rgba[0], clear_rgba[1], clear_rgba[2], clear_rgba[3]) : make_float4(0, 0, 0, 0);
+    hp.W = c->W; hp.H = c->H; hp.L = c->L; hp.fov = c->fov;
+    hp.ambient = c->cfg.ambient; hp.ssao_rad = c->cfg.ssao_rad; hp.ssao_div = c->cfg.ssao_div;
+    hp.inv_mip_bias = 1.f / c->cfg.mip_bias;
+    hp.shadow_bias = c->cfg.shadow_bias; hp.shadow_bias_max = powf(c->cfg.shadow_bias, c->cfg.shadow_exp);
+    hp.linear = (c->cfg.test_linear && c->cfg.use_linear_rendering) ? 1 : 0;
+    hp.no_ssao = c->cfg.no_ssao;
+    hp.row0 = row0; hp.row1 = row1; hp.band_y0 = band0; hp.band_y1 = band1; hp.rowmask = c->d_rowmask;
+    if (hp.n_lights > 0 && (!c->d_lights)) return fail(RR_ERR_INVALID, "lights not written");
+    hp.shade_list = c->d_shade_list; hp.shade_count = c->d_counters + CTR_NSHADE;
+    // The streaming stores of kernel3 — next frame's depth / id clear and the clear colour — depend on nothing this frame computes:
+    // they run on a side stream (k_clear_next) and are joined in front of the shading list. Everything that last read those buffers
+    // (the previous frame's shading and post passes, the copy of the ring slot) is ordered before this call on the main stream. The
+    // fork sits behind k_setup_main: the 100 MB of stores then overlap the latency-bound kernels that follow it (kernel1 / kernel2 of
+    // the work list) and the rest of the shadow pass instead of taking SM slots from the issue-bound setup kernels (RR_CLEAR_AT=0: at
+    // the start of the frame). A peer of the composite target stores its clear colour later, behind the fb_free wait.
+    const bool split_clear = c->split_clear && c->W % 4 == 0;
+    static const int clear_at = getenv("RR_CLEAR_AT") ? atoi(getenv("RR_CLEAR_AT")) : 0;
+    auto fork_clear = [&]() -> int {
+        CU(cudaEventRecord(c->ev_fork_clear, c->stream));
+        CU(cudaStreamWaitEvent(c->stream5, c->ev_fork_clear, 0));
+        static const int clear_per_sm = getenv("RR_CLEAR_GRID") ? atoi(getenv("RR_CLEAR_GRID")) : 2;      // a small footprint: it runs beside other kernels
+        k_clear_next<<<grid_for(c, clear_per_sm), 256, 0, c->stream5>>>(hp, (mg_composite && c->mg.rank != 0) ? 0 : 1);
+        c->launches++;
+        CU(cudaEventRecord(c->ev_clear_done, c->stream5));
+        return RR_OK;
+    };
+    if (split_clear && clear_at == 0 && (r = fork_clear())) return r;
     // prearrange
     SetupMainParams sp;
     sp.pa = c->d_pa; sp.pb = c->d_pb; sp.pc = c->d_pc; sp.objs = c->d_objlite; sp.n_tris = c->n_tris;
@@ -1158,6 +1209,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     if (c->banded) k_setup_main<true><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     else k_setup_main<false><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     c->launches++;
+    if (split_clear && clear_at != 0 && (r = fork_clear())) return r;
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_SETUP], c->stream));
     // kernel1 / kernel2
     RasterParams rp;
@@ -1167,34 +1219,19 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     rp.depth = c->d_depth[c->cur]; rp.ids = c->d_ids[c->cur];
     rp.width = (float)c->W; rp.height = (float)c->H; rp.W = c->W;
     rp.row_lo = row0; rp.row_hi = row1; rp.rowmask = c->d_rowmask; rp.rowbit = ROW_NEEDED;
-    if ((r = raster<RM_DEPTH>(c, c->stream, rp))) return r;
+    if ((r = raster_depth(c, c->stream, rp, sp.sl))) return r;
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_DEPTH], c->stream));
     rp.row_lo = band0; rp.row_hi = band1; rp.rowbit = ROW_OWNED;
-    k_ids_list<<<grid_for(c, 8), 256, 0, c->stream>>>(sp.sl, c->d_depth[c->cur], c->d_ids[c->cur], c->W, band0, band1, c->d_rowmask);
+    // kernel2: a stream over the samples both depth kernels recorded; with the streaming stores on the side stream it also builds
+    // kernel3's covered-pixel list (the first sample to resolve a pixel appends it), so no pass over the screen is left in the frame
+    static const bool list_env = !(getenv("RR_LIST_FROM_IDS") && atoi(getenv("RR_LIST_FROM_IDS")) == 0);
+    const bool list_from_ids = list_env && split_clear && !(mg_composite && c->mg.rank != 0);
+    rp.shade_list = c->d_shade_list; rp.shade_count = c->d_counters + CTR_NSHADE;
+    if (list_from_ids) k_ids_list<true><<<grid_for(c, 6), 256, 0, c->stream>>>(sp.sl, rp);
+    else k_ids_list<false><<<grid_for(c, 8), 256, 0, c->stream>>>(sp.sl, rp);
     c->launches++;
-    if ((r = raster<RM_IDS>(c, c->stream, rp))) return r;
     if (c->stage_events) CU(cudaEventRecord(c->ev[EV_IDS], c->stream));
     // kernel3
-    ShadeParams hp;
-    hp.tris = c->d_tris; hp.objs = c->d_objs; hp.objlite = c->d_objlite; hp.lightlite = c->d_lightlite; hp.frags = c->d_frags; hp.cutdown = c->d_cutdown; hp.n_frags = c->d_counters + CTR_NFRAG;
-    hp.depth = c->d_depth[c->cur]; hp.ids = c->d_ids[c->cur];
-    hp.depth_next = c->d_depth[c->cur ^ 1]; hp.ids_next = c->d_ids[c->cur ^ 1];
-    if (c->mg.connected) c->d_rgba8 = (c->mg.rank == 0 || c->mg.local_readback) ? c->mg.fb[c->mg_target] : c->mg.fb0[c->mg_target];
-    hp.rgba8 = c->d_rgba8; hp.normals = c->d_normals;
-    hp.atlas.texels = c->d_atlas; hp.atlas.nums = c->d_nums; hp.atlas.sizes = c->d_sizes; hp.atlas.mip_start = c->mipmap_start; hp.atlas.tex = c->atlas_tex;
-    hp.lights = c->d_lights; hp.n_lights = (int)c->lights.size();
-    hp.shadow_dyn = c->d_shadow_dyn; hp.shadow_static = c->d_shadow_static;
-    hp.faces = c->faces; hp.cam = cam;
-    hp.clear = clear_rgba ? make_float4(clear_rgba[0], clear_rgba[1], clear_rgba[2], clear_rgba[3]) : make_float4(0, 0, 0, 0);
-    hp.W = c->W; hp.H = c->H; hp.L = c->L; hp.fov = c->fov;
-    hp.ambient = c->cfg.ambient; hp.ssao_rad = c->cfg.ssao_rad; hp.ssao_div = c->cfg.ssao_div;
-    hp.inv_mip_bias = 1.f / c->cfg.mip_bias;
-    hp.shadow_bias = c->cfg.shadow_bias; hp.shadow_bias_max = powf(c->cfg.shadow_bias, c->cfg.shadow_exp);
-    hp.linear = (c->cfg.test_linear && c->cfg.use_linear_rendering) ? 1 : 0;
-    hp.no_ssao = c->cfg.no_ssao;
-    hp.row0 = row0; hp.row1 = row1; hp.band_y0 = band0; hp.band_y1 = band1; hp.rowmask = c->d_rowmask;
-    if (hp.n_lights > 0 && (!c->d_lights)) return fail(RR_ERR_INVALID, "lights not written");
-    hp.shade_list = c->d_shade_list; hp.shade_count = c->d_counters + CTR_NSHADE;
     if (mg_composite && c->mg.rank != 0) {
         // first store of this frame into rank 0's colour target (the clear colour of k_shade_pre): not before rank 0 says the
         // target is free — the shadow-epoch wait further down comes too late for it and does not exist without shadow lights
@@ -1205,8 +1242,12 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     }
     if (c->W % 4 == 0) {
         dim3 grid4((c->W + 127) / 128, (row1 - row0 + 7) / 8);
-        k_shade_pre4<<<grid4, 256, 0, c->stream>>>(hp);
-        c->launches++;
+        if (!split_clear) { k_shade_pre4<true, true><<<grid4, 256, 0, c->stream>>>(hp); c->launches++; }
+        else {
+            CU(cudaStreamWaitEvent(c->stream, c->ev_clear_done, 0));
+            if (mg_composite && c->mg.rank != 0) { k_shade_pre4<false, true><<<grid4, 256, 0, c->stream>>>(hp); c->launches++; }
+            else if (!list_from_ids) { k_shade_list<<<dim3((c->W + 127) / 128, (row1 - row0 + 8 * SL_ROWS - 1) / (8 * SL_ROWS)), 256, 0, c->stream>>>(hp); c->launches++; }
+        }
     } else {
         dim3 grid((c->W + 31) / 32, (row1 - row0 + 7) / 8);
         k_shade_pre<<<grid, 256, 0, c->stream>>>(hp);

@@ -7,26 +7,28 @@
 namespace rr {
 
 // ---- counters (one uint32 array per context) ----------------------------------------------------------------------
+// The counters that many warps update with atomics while a kernel runs each sit on a 128-byte line of their own: atomics on one
+// line retire one after the other in its L2 slice (about one per nanosecond), so hot counters that share a line share that rate.
 enum {
     CTR_NCUT = 0,      // id_cutdown_tris of the main pass
     CTR_NFRAG = 1,     // id_buffer_atomc of the main pass
     CTR_OVERFLOW = 2,  // bit0 fragments, bit1 cutdown, bit2 look-back watchdog
-    CTR_TICKET = 3,    // block ticket of the single-pass scan
-    CTR_S_NFRAG = 4,   // shadow pass allocation counter, one 64-bit word at [4..5]: (projected triangles << 32) | fragments,
-    CTR_S_NCUT = 5,    //   i.e. word 4 = fragment count, word 5 = projected-triangle count (little endian)
     CTR_S_TOTAL = 6,   // running total of shadow fragments in this frame (statistics)
-    CTR_NEXTRA = 7,    // fragments rasterised inline whose samples did not fit the sample list: kernel2 walks them (k_raster_warp<RM_IDS>)
-    CTR_UNUSED8 = 8,
-    CTR_NWORK = 9,     // fragments k_setup_main did not rasterise inline: the work list of k_raster_warp
-    CTR_NSHADE = 10,   // covered pixels in the shading list
-    CTR_NSAMPLES = 11, // entries reserved in the sample list (inline-rasterised triangles)
+    CTR_NEXTRA = 7,    // fragments whose samples did not fit the sample list: kernel2 walks them (tail of k_ids_list)
     CTR_NDESC = 12,    // descriptors in the sample list
     CTR_NACTIVE = 13,  // k_frame_prologue: setup blocks with at least one cluster that is not culled
     CTR_CUT_SKIPPED = 14,  // ... and the projected-triangle slots of the blocks that were skipped
     CTR_PROLOGUE_TICKET = 15,  // last-CTA detection of k_frame_prologue (self-resetting)
     CTR_STICKY = 16,   // overflow flags of earlier frames / passes: the per-frame zeroing ORs CTR_OVERFLOW in here before clearing it,
                        // so a pipelined caller still sees an overflow at its next rr_sync (which reads and clears both words)
-    CTR_COUNT = 17
+    // ---- one line each
+    CTR_TICKET = 32,   // block ticket of the single-pass scan
+    CTR_NWORK = 64,    // fragments k_setup_main did not rasterise inline: the work list of k_raster_warp_depth
+    CTR_NSAMPLES = 96, // entries reserved in the sample list
+    CTR_NSHADE = 128,  // covered pixels in the shading list
+    CTR_S_NFRAG = 160, // shadow pass allocation counter, one 64-bit word at [160..161]: (projected triangles << 32) | fragments,
+    CTR_S_NCUT = 161,  //   i.e. word 160 = fragment count, word 161 = projected-triangle count (little endian)
+    CTR_COUNT = 192
 };
 
 // per-row ownership bits of the sort-first split (rr_config.band_tile): built on the host at rr_create
@@ -312,7 +314,7 @@ __device__ __forceinline__ bool tri_exact_arith(float3 xr, float3 yr) {
 // The covered samples (pixel, depth, fragment index) of every triangle are appended to a sample list so that kernel2's work
 // for these triangles is a stream over that list (k_ids_list) instead of a second walk. Coverage is determined first (a bit
 // mask per triangle), so exactly popc(mask) entries are reserved, with one warp-aggregated atomicAdd per drain; a triangle
-// whose samples do not fit goes to the `extra` list and is walked again by k_raster_warp<RM_IDS>.
+// whose samples do not fit goes to the `extra` list and is walked again by the tail of k_ids_list.
 #define IQ_SLOTS 64
 #define IQ_FIELDS 12            // rounded x of the 3 vertices, rounded y, camera z, rconst, fragment index, flags
 #define IQ_EXACT 1u
@@ -413,7 +415,11 @@ struct InlineRaster {
         const bool rec = (unsigned long long)b0 + (unsigned long long)total <= (unsigned long long)sl.cap;
         if (n == 0) return;
         const uint32_t first = b0 + (uint32_t)(inc - n);
-        if (!rec) sl.extra[atomicAdd(sl.extra_count, 1u)] = fidx;                 // sample list full: kernel2 walks this fragment again
+        if (!rec) {                                                               // sample list full: kernel2 walks this fragment again
+            sl.extra[atomicAdd(sl.extra_count, 1u)] = fidx;
+            // the part of the failed reservation that lies inside the list is streamed by k_ids_list: mark it as holding no sample
+            for (uint32_t k = 0; k < (uint32_t)n && first + k < sl.cap; k++) sl.samples[first + k] = make_uint2(0xFFFFFFFFu, 0u);
+        }
         // plane of 1 / (z / far), cl2.cl:5029-5040
         float3 d = make_float3(f[6 * IQ_SLOTS] / RR_DEPTH_FAR, f[7 * IQ_SLOTS] / RR_DEPTH_FAR, f[8 * IQ_SLOTS] / RR_DEPTH_FAR);     // dcalc
         d = make_float3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);                                                                        // native_recip
@@ -815,7 +821,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, RR_LB_SETUP_MAIN) k_setup_main(
 // longest walk (measured: 82 us for a pass whose total work is ~10 us). Here:
 //   * a triangle whose whole walk is one chunk of at most RASTER_SMALL_MAX slots is rasterised by the setup kernel itself,
 //     through a per-warp queue (InlineRaster / k_shadow_setup's stage C): no record round trip, no second kernel;
-//   * every other fragment goes to a work list and gets a whole warp (k_raster_warp / k_raster_shadow_warp), which
+//   * every other fragment goes to a work list and gets a whole warp (k_raster_warp_depth / k_raster_shadow_warp), which
 //     resolves its pixel slots 32 at a time with the closed form of the walk (rr_math.cuh walk_pixel).
 // Depth goes out as red.global.min.u32 on the L2-resident buffer; ids as red.global.max.u32 (canonical last writer).
 // =====================================================================================================================
@@ -830,6 +836,7 @@ struct RasterParams {
     float width, height; int W;
     int row_lo, row_hi;             // rows this context needs (band +- halo)
     const uint8_t* rowmask; uint32_t rowbit;   // interleaved bands: rows whose mask has `rowbit` set (nullptr: all of [row_lo, row_hi))
+    uint32_t* shade_list; uint32_t* shade_count;   // k_ids_list<true>: the covered-pixel list of kernel3, appended to by whoever resolves a pixel first
 };
 
 template <int MODE>
@@ -875,38 +882,151 @@ __device__ __forceinline__ bool chunk_rows_outside(const float4 mm, int op_size,
     return y_hi < row_lo || y_lo >= row_hi;
 }
 
-// kernel2 for the triangles the setup kernel rasterised inline: stream their recorded samples instead of walking again.
-__global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const uint32_t* __restrict__ depth, uint32_t* __restrict__ ids, int W, int row_lo, int row_hi,
-                                                  const uint8_t* __restrict__ rowmask) {
-    const uint32_t n = min(*sl.count, sl.cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint2 sm = sl.samples[i];
-        const int row = (int)(sm.x / (uint32_t)W);
-        if (row < row_lo || row >= row_hi) continue;
-        if (rowmask && !(rowmask[row] & ROW_OWNED)) continue;
-        const uint32_t val = depth[sm.x];
-        if (sm.y > val - RR_BUF_ERROR && sm.y < val + RR_BUF_ERROR) red_max_u32(ids + sm.x, sl.frag[i] + 1u);
+// kernel1 (cl2.cl:4986-5127) for the fragments k_setup_main did not rasterise inline: one warp per fragment of the work list, the
+// lanes take the chunk's pixel slots 32 at a time through the closed form of the walk (rr_math.cuh walk_pixel). A chunk has at
+// most 501 slots, so a warp's work is bounded and consecutive chunks of a large triangle land on different warps. Depth goes out
+// as red.global.min.u32 on the L2-resident buffer. The covered samples (pixel, depth, fragment) are collected in a per-warp stash
+// in shared memory and appended to the sample list, so that kernel2 never walks the fragment again: its work is a stream over the
+// list (k_ids_list). Fragments whose samples do not fit the list go to the `extra` list instead.
+//  * No vote inside the walk: a lane that found a sample takes its place in the stash with a shared-memory atomic and goes on, so
+//    the divergent paths of a step interleave like independent warps.
+//  * A warp keeps the samples of consecutive fragments in its stash and reserves list space for all of them at once, when the
+//    next 128 slots might not fit or at the end of its work. With one reservation per fragment the 17 k atomicAdds of config 3 on
+//    the one list counter took as long as the whole walk: same-address atomics retire at about one per nanosecond and every warp
+//    waited for its own to come back (34 us instead of 18; profiles/r3_raster_depth_atomics.txt).
+#define RW_WARPS 8
+#define RW_STASH 256            // samples a warp holds before it flushes
+#define RW_BLOCK 128            // slots walked between two capacity checks
+struct RasterStash { uint2 sample[RW_STASH]; uint32_t frag[RW_STASH]; };
+
+__device__ __forceinline__ void raster_stash_flush(const SampleList& sl, RasterStash& st, uint32_t* s_run, int lane) {
+    __syncwarp();
+    const uint32_t run = *s_run;
+    __syncwarp();
+    if (run == 0) return;
+    uint32_t b0 = 0;
+    if (lane == 0) { b0 = atomicAdd(sl.count, run); *s_run = 0u; }
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    if ((unsigned long long)b0 + run <= (unsigned long long)sl.cap) {
+        for (uint32_t q = lane; q < run; q += 32u) { sl.samples[b0 + q] = st.sample[q]; sl.frag[b0 + q] = st.frag[q]; }
+    } else {                                                    // sample list full: kernel2 walks these fragments again
+        for (uint32_t q = lane; q < run; q += 32u) {
+            if (q == 0 || st.frag[q] != st.frag[q - 1]) sl.extra[atomicAdd(sl.extra_count, 1u)] = st.frag[q];      // (a fragment listed twice is walked twice: harmless)
+            if (b0 + q < sl.cap) sl.samples[b0 + q] = make_uint2(0xFFFFFFFFu, 0u);                                  // (no sample here)
+        }
     }
+    __syncwarp();                                               // the stash is reused
 }
 
-// kernel1 (cl2.cl:4986-5127) / kernel2 (cl2.cl:5391-5546) for the fragments k_setup_main did not rasterise inline: one warp per
-// fragment of the work list, the lanes take the chunk's pixel slots 32 at a time through the closed form of the walk
-// (rr_math.cuh walk_pixel). A chunk has at most 501 slots, so a warp's work is bounded and consecutive chunks of a large
-// triangle land on different warps. Depth goes out as red.global.min.u32 on the L2-resident buffer, ids as
-// red.global.max.u32 (canonical last writer).
-template <int MODE>
-__global__ void __launch_bounds__(256) k_raster_warp(const RasterParams P) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(RW_WARPS * 32) k_raster_warp_depth(const RasterParams P, const SampleList sl) {
+    __shared__ RasterStash s_stash[RW_WARPS];
+    __shared__ uint32_t s_run[RW_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    RasterStash& st = s_stash[wid];
+    if (lane == 0) s_run[wid] = 0u;
+    __syncwarp();
     const uint32_t n_work = min(P.counters[CTR_NWORK], P.cap_frags);
-    const uint32_t n_all = n_work + (MODE == RM_IDS ? min(P.counters[CTR_NEXTRA], P.cap_frags) : 0u);
-    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_all; i += warps) {
-        const uint32_t f = i < n_work ? __ldg(P.worklist + i) : __ldg(P.extra + (i - n_work));
+    const uint32_t warps = gridDim.x * RW_WARPS;
+    uint32_t held = 0;                                          // upper bound of the samples in the stash (warp-uniform)
+    for (uint32_t i = blockIdx.x * RW_WARPS + wid; i < n_work; i += warps) {
+        const uint32_t f = __ldg(P.worklist + i);
         const uint32_t cnt = __ldg(P.fragcnt + f) & FRAGCNT_MASK;
         if (cnt == 0) continue;
         uint32_t face, distance;
         FragGeom g;
-        load_fragment<MODE>(P, f, face, distance, g);          // the same record for every lane: broadcast loads
+        load_fragment<RM_DEPTH>(P, f, face, distance, g);      // the same record for every lane: broadcast loads
+        if (chunk_rows_outside(g.mm, RR_OP_SIZE, distance, P.row_lo, P.row_hi)) continue;
+        const int width = (int)(g.mm.y - g.mm.x), k0 = RR_OP_SIZE * (int)distance;
+        const float iw = 1.f / (float)width;
+        for (uint32_t s0 = 0; s0 < cnt; s0 += RW_BLOCK) {
+            const uint32_t s1 = min(cnt, s0 + (uint32_t)RW_BLOCK);
+            if (held + (s1 - s0) > (uint32_t)RW_STASH) { raster_stash_flush(sl, st, &s_run[wid], lane); held = 0; }
+            held += s1 - s0;
+            for (uint32_t s = s0 + lane; s < s1; s += 32u) {
+                float x, y;
+                if (!walk_pixel(k0 + (int)s, k0, width, iw, g.mm, x, y)) continue;
+                const int iy = (int)y;
+                if (iy < P.row_lo || iy >= P.row_hi) continue;
+                if (P.rowmask && !(P.rowmask[iy] & P.rowbit)) continue;
+                if (!point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) continue;
+                const float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
+                const uint32_t d = sat_u32(RR_U32MAXF / fd);
+                const uint32_t px = (uint32_t)((int)(y * P.width) + (int)x);
+                red_min_u32(P.depth + px, d);
+                const uint32_t at = atomicAdd(&s_run[wid], 1u);     // at most `held` <= RW_STASH samples
+                st.sample[at] = make_uint2(px, d);
+                st.frag[at] = f;
+            }
+        }
+    }
+    raster_stash_flush(sl, st, &s_run[wid], lane);
+}
+
+// kernel2 (cl2.cl:5391-5546). Every covered sample of the frame was recorded by the kernels that wrote its depth (the inline
+// rasteriser of k_setup_main, k_raster_warp_depth), so the id resolve is a fully parallel stream over the sample list: a sample
+// within +-20 of the final depth proposes its fragment, red.global.max.u32 keeps the canonical winner (highest fragment index).
+// The fragments whose samples did not fit the list (`extra`, normally none) are walked again, one warp each.
+// LIST: the kernel also builds kernel3's list of covered pixels. The id image is all zero when the frame's id resolve starts, so the
+// sample that turns a pixel's id from 0 into something is the first to resolve it: it appends the pixel (a covered pixel is one
+// with a resolved id, k_shade_pre4). The appends of a CTA's step are collected in shared memory and reserved with one atomicAdd.
+// The list then follows the order of the samples (triangle order) instead of screen order, which k_shade does not care about.
+#define IL_STEP 4
+template <bool LIST>
+__global__ void __launch_bounds__(256) k_ids_list(const SampleList sl, const RasterParams P) {
+    __shared__ uint32_t s_px[LIST ? 256 * IL_STEP : 1];
+    __shared__ uint32_t s_n, s_base;
+    const uint32_t* __restrict__ depth = P.depth;
+    uint32_t* __restrict__ ids = P.ids;
+    const uint32_t n = min(*sl.count, sl.cap);
+    // IL_STEP samples per thread and step: the loads of a step are independent of each other (sample -> depth is the only chain)
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t c0 = blockIdx.x * blockDim.x; c0 < n; c0 += IL_STEP * stride) {        // (CTA-uniform trip count: barriers inside)
+        const uint32_t i0 = c0 + threadIdx.x;
+        uint2 sm[IL_STEP];
+        uint32_t fr[IL_STEP], val[IL_STEP];
+        bool ok[IL_STEP];
+        if (LIST) { if (threadIdx.x == 0) s_n = 0u; __syncthreads(); }
+#pragma unroll
+        for (int k = 0; k < IL_STEP; k++) {
+            const uint32_t i = i0 + (uint32_t)k * stride;
+            ok[k] = i < n;
+            sm[k] = ok[k] ? sl.samples[i] : make_uint2(0xFFFFFFFFu, 0u);
+            fr[k] = ok[k] ? sl.frag[i] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < IL_STEP; k++) {
+            const int row = (int)(sm[k].x / (uint32_t)P.W);      // (0xFFFFFFFF marks the inside part of a reservation that did not fit: row >= H)
+            ok[k] = ok[k] && row >= P.row_lo && row < P.row_hi && (!P.rowmask || (P.rowmask[row] & ROW_OWNED));
+            val[k] = ok[k] ? depth[sm[k].x] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < IL_STEP; k++) {
+            if (!(ok[k] && sm[k].y > val[k] - RR_BUF_ERROR && sm[k].y < val[k] + RR_BUF_ERROR)) continue;
+            if (!LIST) red_max_u32(ids + sm[k].x, fr[k] + 1u);
+            else if (atomicMax(ids + sm[k].x, fr[k] + 1u) == 0u && val[k] != 0xFFFFFFFFu) s_px[atomicAdd(&s_n, 1u)] = sm[k].x;
+        }
+        if (LIST) {
+            __syncthreads();
+            const uint32_t cn = s_n;
+            if (cn) {
+                if (threadIdx.x == 0) s_base = atomicAdd(P.shade_count, cn);
+                __syncthreads();
+                for (uint32_t q = threadIdx.x; q < cn; q += blockDim.x) P.shade_list[s_base + q] = s_px[q];
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t n_extra = min(*sl.extra_count, P.cap_frags);
+    if (n_extra == 0) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_extra; i += warps) {
+        const uint32_t f = __ldg(sl.extra + i);
+        const uint32_t cnt = __ldg(P.fragcnt + f) & FRAGCNT_MASK;
+        if (cnt == 0) continue;
+        uint32_t face, distance;
+        FragGeom g;
+        load_fragment<RM_IDS>(P, f, face, distance, g);
         if (chunk_rows_outside(g.mm, RR_OP_SIZE, distance, P.row_lo, P.row_hi)) continue;
         const int width = (int)(g.mm.y - g.mm.x), k0 = RR_OP_SIZE * (int)distance;
         const float iw = 1.f / (float)width;
@@ -917,7 +1037,15 @@ __global__ void __launch_bounds__(256) k_raster_warp(const RasterParams P) {
             if (iy < P.row_lo || iy >= P.row_hi) continue;
             if (P.rowmask && !(P.rowmask[iy] & P.rowbit)) continue;
             if (!point_in_tri(x, y, g.xr.x, g.yr.x, g.xr.y, g.yr.y, g.xr.z, g.yr.z)) continue;
-            emit_sample<MODE>(P, x, y, g.A, g.B, g.C, face, f);
+            if (!LIST) emit_sample<RM_IDS>(P, x, y, g.A, g.B, g.C, face, f);
+            else {                                              // emit_sample<RM_IDS> with the first-resolver append
+                const float fd = fmaf(g.A, x, fmaf(g.B, y, g.C));
+                const uint32_t d = sat_u32(RR_U32MAXF / fd);
+                const int px = (int)y * P.W + (int)x;
+                const uint32_t val = P.depth[px];
+                if (d > val - RR_BUF_ERROR && d < val + RR_BUF_ERROR && atomicMax(P.ids + px, f + 1u) == 0u && val != 0xFFFFFFFFu)
+                    P.shade_list[atomicAdd(P.shade_count, 1u)] = (uint32_t)px;
+            }
         }
     }
 }
@@ -2070,6 +2198,11 @@ __global__ void __launch_bounds__(256) k_shade_pre(const ShadeParams P) {
 }
 
 // k_shade_pre4: same, four consecutive pixels per thread with 128-bit loads and stores (W % 4 == 0). Tile = 128 x 8.
+// CLEAR_NEXT / CLEAR_RGBA: whether this launch also does the streaming stores (next frame's depth / id clear, clear colour of
+// uncovered pixels). <true, true> is all of kernel3's streaming part in one launch; the frame driver normally runs the stores
+// in k_clear_next on a side stream, beside the issue-bound setup kernels, and launches <false, false> here: a read-only pass
+// over the depth buffer (ids only where something was drawn) that builds the list.
+template <bool CLEAR_NEXT, bool CLEAR_RGBA>
 __global__ void __launch_bounds__(256) k_shade_pre4(const ShadeParams P) {
     __shared__ int s_warp[8];
     __shared__ uint32_t s_base;
@@ -2087,15 +2220,17 @@ __global__ void __launch_bounds__(256) k_shade_pre4(const ShadeParams P) {
             d = *reinterpret_cast<const uint4*>(P.depth + px);
             const bool any = (d.x & d.y & d.z & d.w) != 0xFFFFFFFFu;
             if (any) idv = *reinterpret_cast<const uint4*>(P.ids + px);
-            *reinterpret_cast<uint4*>(P.depth_next + px) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            *reinterpret_cast<uint4*>(P.ids_next + px) = make_uint4(0, 0, 0, 0);
+            if (CLEAR_NEXT) {
+                *reinterpret_cast<uint4*>(P.depth_next + px) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                *reinterpret_cast<uint4*>(P.ids_next + px) = make_uint4(0, 0, 0, 0);
+            }
         }
         if (y >= P.band_y0 && y < P.band_y1 && (rbits & ROW_OWNED)) {
             const uint32_t nfr = P.n_frags[0];
             // ids hold fragment index + 1 (0 = unresolved): covered <=> 1 <= id <= nfr
             cov = (unsigned)(d.x != 0xFFFFFFFFu && idv.x - 1u < nfr) | ((unsigned)(d.y != 0xFFFFFFFFu && idv.y - 1u < nfr) << 1) |
                   ((unsigned)(d.z != 0xFFFFFFFFu && idv.z - 1u < nfr) << 2) | ((unsigned)(d.w != 0xFFFFFFFFu && idv.w - 1u < nfr) << 3);
-            if (cov != 0xFu) {          // covered pixels are overwritten by k_shade afterwards
+            if (CLEAR_RGBA && cov != 0xFu) {          // covered pixels are overwritten by k_shade afterwards
                 const uchar4 c = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
                 const uint32_t cw = *reinterpret_cast<const uint32_t*>(&c);
                 *reinterpret_cast<uint4*>(P.rgba8 + px) = make_uint4(cw, cw, cw, cw);
@@ -2117,6 +2252,76 @@ __global__ void __launch_bounds__(256) k_shade_pre4(const ShadeParams P) {
     uint32_t at = s_base + off + inc - mine;
 #pragma unroll
     for (int i = 0; i < 4; i++) if (cov & (1u << i)) P.shade_list[at++] = px + i;
+}
+
+// k_shade_list: the covered-pixel list alone (what k_shade_pre4<false, false> computes), shaped for a read-only pass: a thread takes
+// four pixels in each of four rows, all four depth loads in flight at once, ids only where something was drawn; a tile is
+// 128 x 32 pixels with one atomicAdd. Nine tenths of config 3's screen is empty: such threads do four loads and leave.
+#define SL_ROWS 4
+__global__ void __launch_bounds__(256) k_shade_list(const ShadeParams P) {
+    __shared__ int s_warp[8];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x = blockIdx.x * 128 + lane * 4;
+    const int y0 = P.row0 + (blockIdx.y * 8 + warp) * SL_ROWS;
+    uint4 d[SL_ROWS];
+    bool use[SL_ROWS];
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+    for (int r = 0; r < SL_ROWS; r++) {
+        const int y = y0 + r;
+        use[r] = x < P.W && y < P.row1 && y >= P.band_y0 && y < P.band_y1 && (!P.rowmask || (P.rowmask[y] & ROW_OWNED));
+        d[r] = use[r] ? *reinterpret_cast<const uint4*>(P.depth + (size_t)y * P.W + x) : ones;
+    }
+    const uint32_t nfr = P.n_frags[0];
+    unsigned cov = 0;                   // bit 4 r + i: pixel (x + i, y0 + r) is covered
+#pragma unroll
+    for (int r = 0; r < SL_ROWS; r++) {
+        if ((d[r].x & d[r].y & d[r].z & d[r].w) == 0xFFFFFFFFu) continue;
+        const uint4 idv = *reinterpret_cast<const uint4*>(P.ids + (size_t)(y0 + r) * P.W + x);
+        // ids hold fragment index + 1 (0 = unresolved): covered <=> 1 <= id <= nfr
+        cov |= ((unsigned)(d[r].x != 0xFFFFFFFFu && idv.x - 1u < nfr) | ((unsigned)(d[r].y != 0xFFFFFFFFu && idv.y - 1u < nfr) << 1) |
+                ((unsigned)(d[r].z != 0xFFFFFFFFu && idv.z - 1u < nfr) << 2) | ((unsigned)(d[r].w != 0xFFFFFFFFu && idv.w - 1u < nfr) << 3)) << (4 * r);
+    }
+    const int mine = __popc(cov);
+    int inc = mine;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const int c = s_warp[w]; if (w < warp) off += c; total += c; }
+    if (total == 0) return;
+    if (tid == 0) s_base = atomicAdd(P.shade_count, (uint32_t)total);
+    __syncthreads();
+    uint32_t at = s_base + off + inc - mine;
+    for (unsigned m = cov; m; m &= m - 1u) {
+        const int b = __ffs(m) - 1;
+        P.shade_list[at++] = (uint32_t)(y0 + (b >> 2)) * (uint32_t)P.W + (uint32_t)(x + (b & 3));
+    }
+}
+
+// k_clear_next: the streaming stores of kernel3 — the next frame's depth buffer back to UINT_MAX and its id image to 0 (to_clear,
+// cl2.cl:5820), and the clear colour (cl2.cl:5835-5862; k_shade overwrites the covered pixels afterwards). None of them depends on
+// anything this frame computes, so the frame driver runs them on a side stream at the start of the frame: 100 MB of stores at 4K that
+// overlap the issue-bound setup kernels instead of sitting on the critical path in front of the shading. W % 4 == 0.
+__global__ void __launch_bounds__(256) k_clear_next(const ShadeParams P, int with_rgba) {
+    const uint32_t w4 = (uint32_t)P.W / 4u, total = (uint32_t)(P.row1 - P.row0) * w4;
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), zero = make_uint4(0, 0, 0, 0);
+    const uchar4 c = make_uchar4(quant8(P.clear.x), quant8(P.clear.y), quant8(P.clear.z), quant8(P.clear.w));
+    const uint32_t cw = *reinterpret_cast<const uint32_t*>(&c);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t r = i / w4;
+        const int y = P.row0 + (int)r;
+        const size_t px = (size_t)y * P.W + (size_t)(i - r * w4) * 4;
+        const uint32_t rbits = P.rowmask ? P.rowmask[y] : (uint32_t)(ROW_NEEDED | ROW_OWNED);
+        if (rbits & ROW_NEEDED) {
+            *reinterpret_cast<uint4*>(P.depth_next + px) = ones;
+            *reinterpret_cast<uint4*>(P.ids_next + px) = zero;
+        }
+        if (with_rgba && y >= P.band_y0 && y < P.band_y1 && (rbits & ROW_OWNED)) *reinterpret_cast<uint4*>(P.rgba8 + px) = make_uint4(cw, cw, cw, cw);
+    }
 }
 
 // k_shade: the expensive part of kernel3 (~6000 instructions per covered pixel) over the compacted list — every warp

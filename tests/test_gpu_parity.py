@@ -222,6 +222,16 @@ def test_async_rebuild_flips_between_scenes():
     assert g.scene_build_ready() is False                                # nothing in flight
 
 
+@pytest.mark.parametrize("cap", [1, 5000])
+def test_sample_list_overflow_falls_back_to_walking(cap, monkeypatch):
+    """kernel2 normally streams the samples the depth kernels recorded; fragments whose samples did not fit the list (depth complexity
+    above 4 on the whole screen — forced here with a tiny list) are walked again by the tail of k_ids_list: same ids either way."""
+    monkeypatch.setenv("RR_SAMPLE_CAP", str(cap))
+    for s in (scene.scene_c2(640, 360, 256), _soup(11, 300, 320, 200, big=True)):
+        g, o = render_both(s, frames=2, threads=0)
+        assert_frame_parity(g, o, label=f"{s.name} sample cap {cap}")
+
+
 def test_overflow_is_reported():
     s = _soup(5, 400, 320, 200, True)
     cfg = s.cfg.copy(max_fragments=64)
