@@ -539,7 +539,7 @@ def run_ours(args):
         dom = max(ms_of, key=lambda k: ms_of[k])
         achieved = B[dom] / (ms_of[dom] * 1e-3) / 1e9
         peak = hbm * world                     # N contexts: the frame's bytes over the max-over-ranks stage time against N x the measured copy bandwidth
-        line["roofline"] = {"bound": "hbm", "limiter": "instruction issue (ncu: DRAM 3-7 % of peak, issue slots 50-68 % busy; profiles/r2_ncu_top_kernels.txt)",
+        line["roofline"] = {"bound": "hbm", "limiter": "instruction issue (ncu: DRAM 3-7 % of peak, issue slots 50-68 % busy; profiles/r2b_ncu_top_kernels.txt)",
                             "kernel": {"setup": "k_setup_main (+ inline depth of small triangles)",
                                        "shadow": "k_shadow_setup (all %d lights, inline raster) + k_raster_shadow_warp" % S,
                                        "depth": "k_raster_warp_depth (work list of the fragments not rasterised inline)",

@@ -893,7 +893,7 @@ __device__ __forceinline__ bool chunk_rows_outside(const float4 mm, int op_size,
 //  * A warp keeps the samples of consecutive fragments in its stash and reserves list space for all of them at once, when the
 //    next 128 slots might not fit or at the end of its work. With one reservation per fragment the 17 k atomicAdds of config 3 on
 //    the one list counter took as long as the whole walk: same-address atomics retire at about one per nanosecond and every warp
-//    waited for its own to come back (34 us instead of 18; profiles/r3_raster_depth_atomics.txt).
+//    waited for its own to come back (34 us instead of 18; profiles/r2b_raster_depth_atomics.txt).
 #define RW_WARPS 8
 #define RW_STASH 256            // samples a warp holds before it flushes
 #define RW_BLOCK 128            // slots walked between two capacity checks
