@@ -168,7 +168,12 @@ struct rr_ctx {
     // side stream of kernel3's streaming stores (k_clear_next): forked at the top of rr_frame_draw, joined in front of the shading list
     cudaStream_t stream5 = nullptr;
     cudaEvent_t ev_fork_clear = nullptr, ev_clear_done = nullptr;
-    bool split_clear = true;                     // RR_SPLIT_CLEAR=0: the stores stay in k_shade_pre4 on the main stream (A/B)
+    // A/B knobs, read at rr_create
+    bool split_clear = true;                     // RR_SPLIT_CLEAR=0: the stores stay in k_shade_pre4 on the main stream
+    bool list_from_ids = true;                   // RR_LIST_FROM_IDS=0: the covered-pixel list comes from a pass over the screen (k_shade_list)
+    int clear_at = 0;                            // RR_CLEAR_AT=1: the side stream forks behind k_setup_main instead of at the start of the frame
+    int clear_grid = 2;                          // RR_CLEAR_GRID: CTAs per SM of k_clear_next (a small footprint: it runs beside other kernels)
+    int raster_grid = 6;                         // RR_RASTER_GRID: CTAs per SM of k_raster_warp_depth (24 KB of sample stash per CTA of eight warps)
     bool shadow_pending = false;
     uint32_t *d_sfrags = nullptr, *d_sfragcnt = nullptr, *d_scounters = nullptr;
     float4* d_scutdown = nullptr;
@@ -290,8 +295,7 @@ int ensure_objlite(rr_ctx* c) {
 
 // kernel1 for the work list (k_raster_warp_depth): depth + the covered samples kernel2 streams afterwards
 int raster_depth(rr_ctx* c, cudaStream_t st, const RasterParams& rp, const SampleList& sl) {
-    static const int per_sm = getenv("RR_RASTER_GRID") ? atoi(getenv("RR_RASTER_GRID")) : 6;      // 24 KB of sample stash per CTA of eight warps
-    k_raster_warp_depth<<<grid_for(c, per_sm), RW_WARPS * 32, 0, st>>>(rp, sl);
+    k_raster_warp_depth<<<grid_for(c, c->raster_grid), RW_WARPS * 32, 0, st>>>(rp, sl);
     c->launches++;
     CU(cudaGetLastError());
     return RR_OK;
@@ -526,6 +530,10 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (cudaEventCreateWithFlags(&c->ev_fork_clear, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (cudaEventCreateWithFlags(&c->ev_clear_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (const char* e = getenv("RR_SPLIT_CLEAR")) c->split_clear = atoi(e) != 0;
+    if (const char* e = getenv("RR_LIST_FROM_IDS")) c->list_from_ids = atoi(e) != 0;
+    if (const char* e = getenv("RR_CLEAR_AT")) c->clear_at = atoi(e);
+    if (const char* e = getenv("RR_CLEAR_GRID")) c->clear_grid = std::max(1, atoi(e));
+    if (const char* e = getenv("RR_RASTER_GRID")) c->raster_grid = std::max(1, atoi(e));
     {
         const size_t srec = (size_t)c->cap_frags * RR_FRAG_WORDS / RR_SFRAG_WORDS;     // shadow records are 4 words
         if (cudaMalloc((void**)&c->d_sfrags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("shadow fragment buffer");
@@ -1161,12 +1169,11 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     // the work list) and the rest of the shadow pass instead of taking SM slots from the issue-bound setup kernels (RR_CLEAR_AT=0: at
     // the start of the frame). A peer of the composite target stores its clear colour later, behind the fb_free wait.
     const bool split_clear = c->split_clear && c->W % 4 == 0;
-    static const int clear_at = getenv("RR_CLEAR_AT") ? atoi(getenv("RR_CLEAR_AT")) : 0;
+    const int clear_at = c->clear_at;
     auto fork_clear = [&]() -> int {
         CU(cudaEventRecord(c->ev_fork_clear, c->stream));
         CU(cudaStreamWaitEvent(c->stream5, c->ev_fork_clear, 0));
-        static const int clear_per_sm = getenv("RR_CLEAR_GRID") ? atoi(getenv("RR_CLEAR_GRID")) : 2;      // a small footprint: it runs beside other kernels
-        k_clear_next<<<grid_for(c, clear_per_sm), 256, 0, c->stream5>>>(hp, (mg_composite && c->mg.rank != 0) ? 0 : 1);
+        k_clear_next<<<grid_for(c, c->clear_grid), 256, 0, c->stream5>>>(hp, (mg_composite && c->mg.rank != 0) ? 0 : 1);
         c->launches++;
         CU(cudaEventRecord(c->ev_clear_done, c->stream5));
         return RR_OK;
@@ -1224,8 +1231,7 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     rp.row_lo = band0; rp.row_hi = band1; rp.rowbit = ROW_OWNED;
     // kernel2: a stream over the samples both depth kernels recorded; with the streaming stores on the side stream it also builds
     // kernel3's covered-pixel list (the first sample to resolve a pixel appends it), so no pass over the screen is left in the frame
-    static const bool list_env = !(getenv("RR_LIST_FROM_IDS") && atoi(getenv("RR_LIST_FROM_IDS")) == 0);
-    const bool list_from_ids = list_env && split_clear && !(mg_composite && c->mg.rank != 0);
+    const bool list_from_ids = c->list_from_ids && split_clear && !(mg_composite && c->mg.rank != 0);
     rp.shade_list = c->d_shade_list; rp.shade_count = c->d_counters + CTR_NSHADE;
     if (list_from_ids) k_ids_list<true><<<grid_for(c, 6), 256, 0, c->stream>>>(sp.sl, rp);
     else k_ids_list<false><<<grid_for(c, 8), 256, 0, c->stream>>>(sp.sl, rp);
