@@ -543,7 +543,7 @@ def run_ours(args):
                             "kernel": {"setup": "k_setup_main (+ inline depth of small triangles)",
                                        "shadow": "k_shadow_setup (all %d lights, inline raster) + k_raster_shadow_warp" % S,
                                        "depth": "k_raster_warp_depth (work list of the fragments not rasterised inline)",
-                                       "id": "k_ids_list (stream over the recorded samples)", "shade": "k_shade_pre4 (list) + k_shade; k_clear_next on a side stream"}[dom],
+                                       "id": "k_ids_list (stream over the recorded samples; builds kernel3's pixel list)", "shade": "k_shade over the covered-pixel list (built by k_ids_list); k_clear_next on a side stream"}[dom],
                             "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                             "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""), "algorithmic_bytes_per_launch": int(B[dom]), "avg_ms": round(ms_of[dom], 4)}
         if world == 1:
