@@ -37,6 +37,15 @@ if "single" in which:
         r.post_pseudo_aa()
         r.sync()
         r.swap_buffers()
+    # rr_frame_e2e: ring of host buffers, plain copies and the dirty-tile read-back (stores into mapped host memory)
+    r.set_pipeline_depth(2)
+    bufs = [rr.host_alloc((s.cfg.height, s.cfg.width, 4)) for _ in range(2)]
+    for tiles in (0, 1):
+        r.set_readback_tiles(tiles)
+        for i in range(5):
+            r.frame_e2e((s.c_pos[0] + 60.0 * i, s.c_pos[1], s.c_pos[2]), s.c_rot, s.clear, 1, bufs[i % 2])
+        r.sync()
+    r.set_readback_tiles(0)
     r.atlas_fill_colour(0, (255, 0, 0, 255), 64, 64)
     r.atlas_upload_mono(1, np.arange(32 * 32, dtype=np.uint8).reshape(32, 32), 32, 32)
     r.sync()

@@ -236,6 +236,20 @@ void  rr_host_free(void* p);
 int rr_frame_e2e(rr_ctx*, const float c_pos[4], const float c_rot[4], const float clear_rgba[4],
                  int with_shadows, uint8_t* host_rgba8);
 int rr_set_pipeline_depth(rr_ctx*, int depth);     /* 2..RR_RING_MAX */
+/* Dirty-tile read-back for rr_frame_e2e (off by default). on = 1: instead of copying 4*W*H bytes every frame, the library stores
+ * into the host buffer only the 32x4-pixel tiles that can differ from what that buffer already holds: tiles with a shaded pixel
+ * in this frame or in the frame it last wrote into the SAME host buffer with the same clear colour (everything else there is
+ * already the clear colour). The host buffer is bit-identical to the device frame after every call, as with the full copy.
+ * Contract: the host buffers are page-locked (rr_host_alloc / rr_host_register), the caller cycles through them in ring order and
+ * does not write into them; a buffer the library has not seen in that ring slot, a changed clear colour, a post pass since the
+ * last frame, rr_set_readback_tiles itself, or a previous copy that needed more than half of the tiles make the next copy a full
+ * one (through the copy engine, as without this mode). Whole-frame, single-context frames only (a split or
+ * connected context keeps copying its rows). The reference has no counterpart: its frame stays in a GL texture
+ * (cl_gl_interop_texture.hpp); this is the headless replacement's way around the PCIe link.
+ * rr_readback_tile_bytes: bytes rr_frame_e2e has moved into host buffers in this mode since the last call — tiles stored plus the
+ * whole frames that went through the copy engine (statistics). */
+int rr_set_readback_tiles(rr_ctx*, int on);
+int rr_readback_tile_bytes(rr_ctx*, uint64_t* bytes);
 
 /* ---- roofline micro-benchmarks (R_atomic is not in MEASURED_PEAKS.json) ------------------------- */
 int rr_microbench_atomic_min(rr_ctx*, size_t footprint_bytes, uint64_t n_ops, float* ms_out);

@@ -168,11 +168,26 @@ struct rr_ctx {
     // side stream of kernel3's streaming stores (k_clear_next): forked at the top of rr_frame_draw, joined in front of the shading list
     cudaStream_t stream5 = nullptr;
     cudaEvent_t ev_fork_clear = nullptr, ev_clear_done = nullptr;
+    // dirty-tile read-back of rr_frame_e2e (rr_set_readback_tiles): per ring slot, the tiles shaded in the frame being copied (now) and
+    // in the frame last written into the slot's host buffer (prev), that buffer and the clear colour it was filled with
+    bool tiles_on = false;
+    uint8_t* d_tile_now[RR_RING_MAX] = {};
+    uint8_t* d_tile_prev[RR_RING_MAX] = {};
+    const void* tile_host[RR_RING_MAX] = {};
+    float tile_clear[RR_RING_MAX][4] = {};
+    bool tile_valid[RR_RING_MAX] = {};
+    uint32_t* d_tile_sent = nullptr;             // [0]: tiles stored by k_tile_copy since rr_readback_tile_bytes; [1 + k]: tiles of slot k's last copy
+    uint32_t* h_tile_last = nullptr;             // pinned: [k] = tiles that slot k's last copy needed (what sizes the next grids)
+    uint32_t tile_estimate = 0;
+    uint64_t tile_dma_bytes = 0;                 // whole frames copied by the copy engine while the tile mode is on (statistics)
+    uint8_t* tile_mark_target = nullptr;         // set by rr_frame_e2e around rr_frame_draw: where the id resolve marks the frame's tiles
+    bool tiles_marked = false;                   // ... and whether it did (otherwise k_tile_mark runs over the covered-pixel list)
     // A/B knobs, read at rr_create
     bool split_clear = true;                     // RR_SPLIT_CLEAR=0: the stores stay in k_shade_pre4 on the main stream
     bool list_from_ids = true;                   // RR_LIST_FROM_IDS=0: the covered-pixel list comes from a pass over the screen (k_shade_list)
     int clear_at = 0;                            // RR_CLEAR_AT=1: the side stream forks behind k_setup_main instead of at the start of the frame
     int clear_grid = 2;                          // RR_CLEAR_GRID: CTAs per SM of k_clear_next (a small footprint: it runs beside other kernels)
+    int tile_grid = 4;                           // RR_TILE_GRID: least number of CTAs of k_tile_copy (see the kernel: few on purpose)
     int raster_grid = 6;                         // RR_RASTER_GRID: CTAs per SM of k_raster_warp_depth (24 KB of sample stash per CTA of eight warps)
     bool shadow_pending = false;
     uint32_t *d_sfrags = nullptr, *d_sfragcnt = nullptr, *d_scounters = nullptr;
@@ -431,7 +446,7 @@ static int preload_kernels() {
         (const void*)k_signal_flag, (const void*)k_signal_flags, (const void*)k_wait_flags, (const void*)k_push_faces, (const void*)k_fill_faces,
         (const void*)k_raster_shadow_warp, (const void*)k_fill_u32, (const void*)k_atlas_upload, (const void*)k_atlas_mip, (const void*)k_atlas_upload_batch, (const void*)k_atlas_mip_batch,
         (const void*)k_atlas_fill_colour, (const void*)k_atlas_from_raw,
-        (const void*)k_shade_pre, (const void*)k_shade_pre4<true, true>, (const void*)k_shade_pre4<false, true>, (const void*)k_shade_list, (const void*)k_clear_next, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_motion_blur, (const void*)k_motion_history, (const void*)k_godrays, (const void*)k_copy_u32,
+        (const void*)k_shade_pre, (const void*)k_shade_pre4<true, true>, (const void*)k_shade_pre4<false, true>, (const void*)k_shade_list, (const void*)k_clear_next, (const void*)k_shade, (const void*)k_pseudo_aa, (const void*)k_motion_blur, (const void*)k_motion_history, (const void*)k_godrays, (const void*)k_copy_u32, (const void*)k_tile_mark, (const void*)k_tile_copy,
     };
     for (const void* f : fns) {
         cudaFuncAttributes a;
@@ -534,6 +549,7 @@ rr_ctx* rr_create(const rr_config* cfg) {
     if (const char* e = getenv("RR_CLEAR_AT")) c->clear_at = atoi(e);
     if (const char* e = getenv("RR_CLEAR_GRID")) c->clear_grid = std::max(1, atoi(e));
     if (const char* e = getenv("RR_RASTER_GRID")) c->raster_grid = std::max(1, atoi(e));
+    if (const char* e = getenv("RR_TILE_GRID")) c->tile_grid = std::max(1, atoi(e));
     {
         const size_t srec = (size_t)c->cap_frags * RR_FRAG_WORDS / RR_SFRAG_WORDS;     // shadow records are 4 words
         if (cudaMalloc((void**)&c->d_sfrags, (size_t)c->cap_frags * RR_FRAG_WORDS * 4) != cudaSuccess) return bail("shadow fragment buffer");
@@ -576,6 +592,9 @@ void rr_destroy(rr_ctx* c) {
     if (c->ev_shadow_done) cudaEventDestroy(c->ev_shadow_done);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream5) { cudaStreamSynchronize(c->stream5); cudaStreamDestroy(c->stream5); }
+    for (int i = 0; i < RR_RING_MAX; i++) { cudaFree(c->d_tile_now[i]); cudaFree(c->d_tile_prev[i]); }
+    cudaFree(c->d_tile_sent);
+    if (c->h_tile_last) cudaFreeHost(c->h_tile_last);
     if (c->ev_fork_clear) cudaEventDestroy(c->ev_fork_clear);
     if (c->ev_clear_done) cudaEventDestroy(c->ev_clear_done);
     cudaFree(c->d_tris); cudaFree(c->d_pa); cudaFree(c->d_pb); cudaFree(c->d_pc); cudaFree(c->d_objs); cudaFree(c->d_objlite); cudaFree(c->d_obj_r2); cudaFree(c->d_obj_rows);
@@ -1051,7 +1070,7 @@ static int shadow_pass(rr_ctx* c, int only_static) {
         k_shadow_setup<<<(c->n_tris + 127) / 128, 128, 0, st>>>(sp);
         c->launches++;
         dp.frags = c->d_sfrags; dp.cutdown = c->d_scutdown; dp.fragcnt = c->d_sfragcnt; dp.counters = c->d_scounters; dp.cap_frags = sp.cap_frags;
-        dp.worklist = nullptr; dp.extra = nullptr; dp.shade_list = nullptr; dp.shade_count = nullptr;
+        dp.worklist = nullptr; dp.extra = nullptr; dp.shade_list = nullptr; dp.shade_count = nullptr; dp.tile_now = nullptr; dp.tiles_x = 0;
         dp.n_index = CTR_S_NFRAG;
         dp.depth = buffer; dp.ids = nullptr; dp.width = (float)c->L; dp.height = (float)c->L; dp.W = c->L;
         dp.row_lo = 0; dp.row_hi = c->L; dp.rowmask = nullptr; dp.rowbit = 0;
@@ -1233,6 +1252,8 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     // kernel3's covered-pixel list (the first sample to resolve a pixel appends it), so no pass over the screen is left in the frame
     const bool list_from_ids = c->list_from_ids && split_clear && !(mg_composite && c->mg.rank != 0);
     rp.shade_list = c->d_shade_list; rp.shade_count = c->d_counters + CTR_NSHADE;
+    rp.tile_now = c->tile_mark_target; rp.tiles_x = (c->W + TILE_W - 1) / TILE_W;      // rr_frame_e2e with the dirty-tile read-back: the id resolve marks the tiles
+    c->tiles_marked = list_from_ids && c->tile_mark_target != nullptr;
     if (list_from_ids) k_ids_list<true><<<grid_for(c, 6), 256, 0, c->stream>>>(sp.sl, rp);
     else k_ids_list<false><<<grid_for(c, 8), 256, 0, c->stream>>>(sp.sl, rp);
     c->launches++;
@@ -1286,6 +1307,7 @@ static int post_begin(rr_ctx* c, const char* who) {
 }
 static int post_publish(rr_ctx* c) {
     const size_t P = (size_t)c->W * c->H;
+    for (int i = 0; i < RR_RING_MAX; i++) c->tile_valid[i] = false;      // a post pass may touch any pixel: the next tile read-back is a full one
     CU(cudaGetLastError());
     if (c->ext_rgba8) {                                               // caller-owned target: put the result back where the caller expects it
         k_copy_u32<<<grid_for(c, 8), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_post), reinterpret_cast<uint4*>(c->d_rgba8), P / 4,
@@ -1714,6 +1736,29 @@ int rr_set_pipeline_depth(rr_ctx* c, int depth) {
     return RR_OK;
 }
 
+int rr_set_readback_tiles(rr_ctx* c, int on) {
+    if (!c) return fail(RR_ERR_INVALID, "null ctx");
+    int r = rr_sync(c);
+    if (r && r != RR_ERR_OVERFLOW) return r;
+    c->tiles_on = on != 0;
+    c->tile_estimate = 0;
+    for (int i = 0; i < RR_RING_MAX; i++) c->tile_valid[i] = false;
+    return RR_OK;
+}
+
+int rr_readback_tile_bytes(rr_ctx* c, uint64_t* bytes) {
+    if (!c || !bytes) return fail(RR_ERR_INVALID, "null argument");
+    *bytes = 0;
+    if (!c->d_tile_sent) return RR_OK;
+    CU(cudaStreamSynchronize(c->stream3));
+    uint32_t n = 0;
+    CU(cudaMemcpy(&n, c->d_tile_sent, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(c->d_tile_sent, 0, 4));
+    *bytes = (uint64_t)n * TILE_W * TILE_H * 4 + c->tile_dma_bytes;
+    c->tile_dma_bytes = 0;
+    return RR_OK;
+}
+
 int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const float clear_rgba[4], int with_shadows, uint8_t* host_rgba8) {
     if (!c || !host_rgba8) return fail(RR_ERR_INVALID, "null argument");
     int r;
@@ -1742,11 +1787,58 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     // then publishes the draw epoch in every peer's control block (fb_free, rr_frame_draw); a peer's first store into rank 0's
     // target waits for it.
     if (pipelined && c->copy_pending[k]) CU(cudaStreamWaitEvent(c->stream, c->ev_copy_done[k], 0));
-    if (with_shadows && (r = rr_frame_shadows(c, 0))) return r;
-    if ((r = rr_frame_draw(c, c_pos, c_rot, clear_rgba))) return r;
+    // dirty-tile read-back (rr_set_readback_tiles): the frame's tiles are marked by the id resolve (or, when that does not build the
+    // pixel list, by k_tile_mark behind k_shade), the copy stream stores the tiles that need it into the mapped host buffer
+    bool tiles_enqueued = false;
+    uchar4* host_dev = nullptr;
+    const bool tiles = c->tiles_on && !mg && pipelined && c->W % 4 == 0 && !c->banded && c->own_lo == 0 && c->own_hi == c->H && c->n_tris > 0 &&
+                       cudaHostGetDevicePointer((void**)&host_dev, host_rgba8, 0) == cudaSuccess && host_dev;
+    if (c->tiles_on && !tiles) (void)cudaGetLastError();        // (a host buffer that is not page-locked: the plain copy below)
+    const int tiles_x = (c->W + TILE_W - 1) / TILE_W, tiles_y = (c->H + TILE_H - 1) / TILE_H;
+    const uint32_t n_tiles = (uint32_t)tiles_x * (uint32_t)tiles_y;
+    if (tiles) {
+        if (!c->d_tile_sent) {
+            CU(cudaMalloc((void**)&c->d_tile_sent, 4 * (1 + RR_RING_MAX))); CU(cudaMemsetAsync(c->d_tile_sent, 0, 4 * (1 + RR_RING_MAX), c->stream));
+            CU(cudaMallocHost((void**)&c->h_tile_last, 4 * RR_RING_MAX)); memset(c->h_tile_last, 0, 4 * RR_RING_MAX);
+        }
+        if (!c->d_tile_now[k]) {
+            CU(cudaMalloc((void**)&c->d_tile_now[k], n_tiles)); CU(cudaMalloc((void**)&c->d_tile_prev[k], n_tiles));
+            CU(cudaMemsetAsync(c->d_tile_now[k], 0, n_tiles, c->stream)); CU(cudaMemsetAsync(c->d_tile_prev[k], 0, n_tiles, c->stream));
+            c->tile_valid[k] = false;
+        }
+        c->tile_mark_target = c->d_tile_now[k];
+    }
+    c->tiles_marked = false;
+    if (with_shadows && (r = rr_frame_shadows(c, 0))) { c->tile_mark_target = nullptr; return r; }
+    r = rr_frame_draw(c, c_pos, c_rot, clear_rgba);
+    c->tile_mark_target = nullptr;
+    if (r) return r;
+    if (tiles && !c->tiles_marked) {
+        k_tile_mark<<<grid_for(c, 4), 256, 0, c->stream>>>(c->d_shade_list, c->d_counters + CTR_NSHADE, c->W, tiles_x, c->d_tile_now[k]);
+        c->launches++;
+    }
     CU(cudaEventRecord(c->ev_draw_done, c->stream));
     CU(cudaStreamWaitEvent(c->stream3, c->ev_draw_done, 0));
     const uint8_t* src = (const uint8_t*)c->d_rgba8;
+    if (tiles) {
+        const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* cl = clear_rgba ? clear_rgba : zero4;
+        // the whole buffer must be rewritten (first use of it in this slot, another clear colour), or the last completed copy needed
+        // more than half of the tiles: one DMA copy of the frame, the kernel only keeps the books
+        const bool all = !c->tile_valid[k] || c->tile_host[k] != (const void*)host_rgba8 || memcmp(c->tile_clear[k], cl, 16) != 0 ||
+                         c->tile_estimate > n_tiles / 2;
+        CU(cudaMemsetAsync(c->d_tile_sent + 1 + k, 0, 4, c->stream3));
+        if (all) { CU(cudaMemcpyAsync(host_rgba8, src, P * 4, cudaMemcpyDeviceToHost, c->stream3)); c->tile_dma_bytes += P * 4; }
+        // grid: about one CTA per 2 000 tiles (1 MB) the last completed copy sent, at least c->tile_grid (RR_TILE_GRID, 4)
+        const int grid = all ? 8 : std::min(64, std::max(c->tile_grid, (int)(c->tile_estimate / 2000u)));
+        k_tile_copy<<<grid, 256, 0, c->stream3>>>(c->d_rgba8, all ? nullptr : host_dev, c->W, c->H, tiles_x, n_tiles, c->d_tile_now[k], c->d_tile_prev[k], 0,
+                                                 c->d_tile_sent, c->d_tile_sent + 1 + k);
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(c->h_tile_last + k, c->d_tile_sent + 1 + k, 4, cudaMemcpyDeviceToHost, c->stream3));
+        c->tile_host[k] = host_rgba8; memcpy(c->tile_clear[k], cl, 16); c->tile_valid[k] = true;
+        tiles_enqueued = true;
+    }
     if (mg && c->mg.local_readback) {
         // distributed read-back: this context's rows only, from its own target, over its own PCIe link
         if (c->cfg.band_tile > 0 && c->cfg.band_world > 1) {
@@ -1768,9 +1860,10 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     } else if (mg) {
         // composite on rank 0 (every context stored its rows there over NVLink): rank 0 alone reads the frame back
         if (c->mg.rank == 0) CU(cudaMemcpyAsync(host_rgba8, src, P * 4, cudaMemcpyDeviceToHost, c->stream3));
-    } else {
+    } else if (!tiles_enqueued) {
         const size_t off = (size_t)c->own_lo * rowb, len = (size_t)(c->own_hi - c->own_lo) * rowb;
         if (len) CU(cudaMemcpyAsync(host_rgba8 + off, src + off, len, cudaMemcpyDeviceToHost, c->stream3));   // direct DMA when host_rgba8 is page-locked
+        if (pipelined) c->tile_valid[k] = false;                 // (the tile path, when it comes back, starts from a full copy)
     }
     CU(cudaEventRecord(c->ev_copy_done[k], c->stream3));
     c->copy_pending[k] = true;
@@ -1780,6 +1873,7 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     } else {
         const int j = (k + 1) % D;                        // the frame issued D-1 calls ago
         if (c->copy_pending[j]) { CU(cudaEventSynchronize(c->ev_copy_done[j])); c->copy_pending[j] = false; }
+        if (c->tiles_on && c->h_tile_last) c->tile_estimate = c->h_tile_last[j];      // tiles that copy needed: sizes the next grids
     }
     c->ring_pos = (k + 1) % D;
     return rr_swap_buffers(c);

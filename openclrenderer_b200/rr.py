@@ -65,6 +65,10 @@ def load_library():
         _LIB.rr_host_register.argtypes = [_P, C.c_size_t]
         _LIB.rr_host_unregister.restype = C.c_int
         _LIB.rr_host_unregister.argtypes = [_P]
+        _LIB.rr_set_readback_tiles.restype = C.c_int
+        _LIB.rr_set_readback_tiles.argtypes = [_P, C.c_int]
+        _LIB.rr_readback_tile_bytes.restype = C.c_int
+        _LIB.rr_readback_tile_bytes.argtypes = [_P, C.POINTER(C.c_uint64)]
         _LIB.rr_microbench_copy.restype = C.c_int
         _LIB.rr_microbench_copy.argtypes = [_P, C.c_size_t, C.POINTER(C.c_float)]
     return _LIB
@@ -133,6 +137,20 @@ class Renderer(CApi):
         r = self._lib.rr_set_pipeline_depth(self._ctx, int(depth))
         if r != RR_OK:
             raise RRError(r, self.last_error())
+
+    def set_readback_tiles(self, on):
+        """dirty-tile read-back of frame_e2e (include/rr.h rr_set_readback_tiles)"""
+        r = self._lib.rr_set_readback_tiles(self._ctx, int(bool(on)))
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+
+    def readback_tile_bytes(self):
+        """bytes the tile path has stored into host buffers since the last call"""
+        n = C.c_uint64(0)
+        r = self._lib.rr_readback_tile_bytes(self._ctx, C.byref(n))
+        if r != RR_OK:
+            raise RRError(r, self.last_error())
+        return int(n.value)
 
     def frame_e2e(self, c_pos, c_rot, clear, with_shadows, host_rgba8):
         def f4(v):

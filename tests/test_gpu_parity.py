@@ -318,6 +318,55 @@ def test_frame_e2e_pipelined_readback_matches_plain_frames(depth):
         assert np.array_equal(got[i], want[i]), f"frame {i}"
 
 
+@pytest.mark.parametrize("depth,size", [(2, (640, 360)), (3, (644, 363)), (4, (640, 360))])
+def test_frame_e2e_dirty_tile_readback_is_bit_identical(depth, size):
+    """rr_set_readback_tiles: only the 32x4-pixel tiles that can differ from what the host buffer holds cross the PCIe link, and the
+    host buffers are still the frames bit for bit — camera moving by whole spheres (tiles covered D frames ago must be rewritten with
+    the clear colour), an odd frame size (partial tiles at the right and bottom edges), a changed clear colour and a foreign host
+    buffer in the middle of the run (both force a full copy), and fewer bytes than full copies on the way."""
+    from openclrenderer_b200 import rr
+    W, H = size
+    s = scene.scene_spheres(W, H, n_spheres=8, grid=(4, 2), seed=21, n_lights=2, light_dim=128, tex_sizes=(128, 64))
+    n = 11
+    cams = [((s.c_pos[0] + 300.0 * (i % 5), s.c_pos[1] + 50.0 * i, s.c_pos[2]), (s.c_rot[0] + 0.02 * i, 0.0, 0.0)) for i in range(n)]
+    clears = [s.clear if i < 6 else (0.3, 0.1, 0.2, 1.0) for i in range(n)]
+    a = Renderer(s.cfg)
+    s.upload(a)
+    want = []
+    for i, (p, r) in enumerate(cams):
+        a.frame_shadows(1 if i == 0 else 0)
+        a.frame_draw(p, r, clears[i])
+        a.sync()
+        want.append(a.read_rgba8())
+        a.swap_buffers()
+    b = Renderer(s.cfg)
+    s.upload(b)
+    b.frame_shadows(1)
+    b.set_pipeline_depth(depth)
+    b.set_readback_tiles(True)
+    bufs = [rr.host_alloc((H, W, 4)) for _ in range(depth)]
+    foreign = rr.host_alloc((H, W, 4))
+    foreign[:] = 77                                                     # a buffer the library has never written: must come back complete
+    used = []
+    for i, (p, r) in enumerate(cams):
+        buf = foreign if i == 8 else bufs[i % depth]
+        b.frame_e2e(p, r, clears[i], 1, buf)
+        used.append(buf)
+        if i >= depth - 1:
+            j = i - depth + 1
+            assert np.array_equal(used[j], want[j]), f"frame {j} (complete on return of call {i})"
+    b.sync()
+    for j in range(n - depth + 1, n):
+        assert np.array_equal(used[j], want[j]), f"frame {j}"
+    sent = b.readback_tile_bytes()
+    assert 0 < sent < n * W * H * 4, f"{sent} bytes for {n} frames of {W * H * 4}"      # (first uses, the new clear colour and the foreign buffer are whole frames)
+    # switching it off goes back to plain copies of whole frames
+    b.set_readback_tiles(False)
+    b.frame_e2e(cams[0][0], cams[0][1], clears[0], 1, bufs[0])
+    b.sync()
+    assert np.array_equal(bufs[0], want[0]) and b.readback_tile_bytes() == 0
+
+
 def test_object_transform_patches_match_oracle():
     """object::g_flush (object.cpp:652-857): 12/16-byte writes of world_pos / world_rot_quat / scale into the descriptor
     array between frames; both sides re-render the moved scene identically."""
