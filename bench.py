@@ -375,7 +375,10 @@ def run_ours(args):
     dummy = np.zeros(4, np.uint8)
     e2e_i = [0]
 
+    last_cam = [0]
+
     def frame_e2e(i):
+        last_cam[0] = i
         c_pos, c_rot = camera(s, i)
         if world == 1:
             r.frame_e2e(c_pos, c_rot, s.clear, 1, host_ring[e2e_i[0] % D])   # pipelined read-back over a ring of D targets; swaps buffers itself
@@ -420,34 +423,44 @@ def run_ours(args):
            "readback": ("distributed: every GPU DMAs the rows it shaded into one shared, page-locked host frame" if dist_rb else
                         "GPU 0 reads the whole frame back") if world > 1 else "pipelined",
            "ring_depth": D if (world == 1 or p2p) else 1}
-    if world == 1:
+    if world == 1 or dist_rb:
         # the same loop with the dirty-tile read-back (rr_set_readback_tiles): the host buffers hold the same frames bit for bit
-        # (tests/test_gpu_parity.py), but only the tiles that can differ from what a buffer already holds cross the PCIe link.
-        # Reported beside `e2e` (which stays the plain copy of the whole frame every step), with the bytes it really moved.
+        # (tests/test_gpu_parity.py, test_gpu_mgpu.py), but only the tiles that can differ from what a buffer already holds cross
+        # the PCIe link(s). Reported beside `e2e` (which stays the plain copy of the whole frame every step), with the bytes moved.
         r.sync()
         r.set_readback_tiles(True)
         for i in range(2 * D):
             frame_e2e(1000 + i)
         r.sync()
         r.readback_tile_bytes()
+        barrier()
         td0 = time.perf_counter()
         for i in range(args.steps):
             frame_e2e(1000 + 2 * D + i)
         r.sync()
+        barrier()
         dt_ms = 1e3 * (time.perf_counter() - td0) / args.steps
-        tile_bytes = r.readback_tile_bytes() / args.steps
-        last = (e2e_i[0] - 1) % D
-        c_pos, c_rot = camera(s, 1000 + 2 * D + args.steps - 1)
-        r.set_readback_tiles(False)
-        r.frame_shadows(0)
-        r.frame_draw(c_pos, c_rot, s.clear)
-        r.sync()
-        same = bool(np.array_equal(r.read_rgba8(), host_ring[last]))
-        r.swap_buffers()
+        tb = torch.tensor([dt_ms, float(r.readback_tile_bytes()) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmx = tb.clone()
+            dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+            dt_ms, tile_bytes = float(tmx[0]), float(tb[1])
+        else:
+            dt_ms, tile_bytes = float(tb[0]), float(tb[1])
         e2e["dirty_tiles"] = {"value": round(T / (dt_ms * 1e-3) / 1e6, 3), "unit": UNIT, "ms_per_step": round(dt_ms, 4),
-                              "d2h_bytes_per_step": int(tile_bytes), "host_frame_equals_device_frame": same,
+                              "d2h_bytes_per_step": int(tile_bytes),
                               "what": "rr_set_readback_tiles(1): 32x4-pixel tiles that hold a shaded pixel now or held one in the frame last written "
                                       "into the same host buffer are stored into the page-locked host frame; the rest of it already holds the clear colour"}
+        if world == 1:
+            last = (e2e_i[0] - 1) % D
+            c_pos, c_rot = camera(s, last_cam[0])
+            r.set_readback_tiles(False)
+            r.frame_shadows(0)
+            r.frame_draw(c_pos, c_rot, s.clear)
+            r.sync()
+            e2e["dirty_tiles"]["host_frame_equals_device_frame"] = bool(np.array_equal(r.read_rgba8(), host_ring[last]))
+            r.swap_buffers()
     e2e_check = None
     if dist_rb:
         # the last frame of the e2e loop, as the consumer sees it in host memory, against the device composite of the same camera
@@ -455,7 +468,8 @@ def run_ours(args):
         dist.barrier()
         last = e2e_i[0] - 1
         r.mgpu_set_readback(0)
-        c_pos, c_rot = camera(s, 3 + args.steps - 1)
+        r.set_readback_tiles(False)
+        c_pos, c_rot = camera(s, last_cam[0])
         r.frame_shadows(0)
         r.frame_draw(c_pos, c_rot, s.clear)
         barrier()

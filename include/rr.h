@@ -243,8 +243,9 @@ int rr_set_pipeline_depth(rr_ctx*, int depth);     /* 2..RR_RING_MAX */
  * Contract: the host buffers are page-locked (rr_host_alloc / rr_host_register), the caller cycles through them in ring order and
  * does not write into them; a buffer the library has not seen in that ring slot, a changed clear colour, a post pass since the
  * last frame, rr_set_readback_tiles itself, or a previous copy that needed more than half of the tiles make the next copy a full
- * one (through the copy engine, as without this mode). Whole-frame, single-context frames only (a split or
- * connected context keeps copying its rows). The reference has no counterpart: its frame stays in a GL texture
+ * one (through the copy engine, as without this mode). Applies to whole frames of one context and to the distributed read-back of
+ * connected contexts (rr_mgpu_set_readback(1), interleaved row tiles that are multiples of 4 rows: every context stores the tiles
+ * of its own rows into the shared host frame); any other split keeps copying its rows. The reference has no counterpart: its frame stays in a GL texture
  * (cl_gl_interop_texture.hpp); this is the headless replacement's way around the PCIe link.
  * rr_readback_tile_bytes: bytes rr_frame_e2e has moved into host buffers in this mode since the last call — tiles stored plus the
  * whole frames that went through the copy engine (statistics). */

@@ -1791,7 +1791,11 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     // pixel list, by k_tile_mark behind k_shade), the copy stream stores the tiles that need it into the mapped host buffer
     bool tiles_enqueued = false;
     uchar4* host_dev = nullptr;
-    const bool tiles = c->tiles_on && !mg && pipelined && c->W % 4 == 0 && !c->banded && c->own_lo == 0 && c->own_hi == c->H && c->n_tris > 0 &&
+    // whole frames of one context, or — distributed read-back of a connected context — its interleaved row tiles (whole multiples of
+    // the 4-row read-back tiles, so that no tile belongs to two contexts)
+    const bool tiles_whole = !mg && !c->banded && c->own_lo == 0 && c->own_hi == c->H;
+    const bool tiles_rows = mg && c->mg.local_readback && c->cfg.band_tile > 0 && c->cfg.band_world > 1 && c->cfg.band_tile % TILE_H == 0;
+    const bool tiles = c->tiles_on && (tiles_whole || tiles_rows) && pipelined && c->W % 4 == 0 && c->n_tris > 0 &&
                        cudaHostGetDevicePointer((void**)&host_dev, host_rgba8, 0) == cudaSuccess && host_dev;
     if (c->tiles_on && !tiles) (void)cudaGetLastError();        // (a host buffer that is not page-locked: the plain copy below)
     const int tiles_x = (c->W + TILE_W - 1) / TILE_W, tiles_y = (c->H + TILE_H - 1) / TILE_H;
@@ -1823,12 +1827,13 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     if (tiles) {
         const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
         const float* cl = clear_rgba ? clear_rgba : zero4;
-        // the whole buffer must be rewritten (first use of it in this slot, another clear colour), or the last completed copy needed
-        // more than half of the tiles: one DMA copy of the frame, the kernel only keeps the books
+        // the whole buffer (this context's rows of it) must be rewritten — first use of it in this slot, another clear colour — or the
+        // last completed copy needed more than half of the tiles: the copy engine moves the frame as without this mode (below), the
+        // kernel only keeps the books
+        const uint32_t own_tiles = tiles_rows ? n_tiles / (uint32_t)c->cfg.band_world : n_tiles;
         const bool all = !c->tile_valid[k] || c->tile_host[k] != (const void*)host_rgba8 || memcmp(c->tile_clear[k], cl, 16) != 0 ||
-                         c->tile_estimate > n_tiles / 2;
+                         c->tile_estimate > own_tiles / 2;
         CU(cudaMemsetAsync(c->d_tile_sent + 1 + k, 0, 4, c->stream3));
-        if (all) { CU(cudaMemcpyAsync(host_rgba8, src, P * 4, cudaMemcpyDeviceToHost, c->stream3)); c->tile_dma_bytes += P * 4; }
         // grid: about one CTA per 2 000 tiles (1 MB) the last completed copy sent, at least c->tile_grid (RR_TILE_GRID, 4)
         const int grid = all ? 8 : std::min(64, std::max(c->tile_grid, (int)(c->tile_estimate / 2000u)));
         k_tile_copy<<<grid, 256, 0, c->stream3>>>(c->d_rgba8, all ? nullptr : host_dev, c->W, c->H, tiles_x, n_tiles, c->d_tile_now[k], c->d_tile_prev[k], 0,
@@ -1837,9 +1842,12 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(c->h_tile_last + k, c->d_tile_sent + 1 + k, 4, cudaMemcpyDeviceToHost, c->stream3));
         c->tile_host[k] = host_rgba8; memcpy(c->tile_clear[k], cl, 16); c->tile_valid[k] = true;
-        tiles_enqueued = true;
+        tiles_enqueued = !all;                                  // the tiles are on their way; otherwise the copies below move the frame
+        if (all) c->tile_dma_bytes += tiles_rows ? (P * 4) / (size_t)c->cfg.band_world : P * 4;
     }
-    if (mg && c->mg.local_readback) {
+    if (tiles_enqueued) {
+        // (stored by k_tile_copy)
+    } else if (mg && c->mg.local_readback) {
         // distributed read-back: this context's rows only, from its own target, over its own PCIe link
         if (c->cfg.band_tile > 0 && c->cfg.band_world > 1) {
             const int tile = c->cfg.band_tile, world = c->cfg.band_world, rank = c->cfg.band_rank;
@@ -1860,11 +1868,11 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
     } else if (mg) {
         // composite on rank 0 (every context stored its rows there over NVLink): rank 0 alone reads the frame back
         if (c->mg.rank == 0) CU(cudaMemcpyAsync(host_rgba8, src, P * 4, cudaMemcpyDeviceToHost, c->stream3));
-    } else if (!tiles_enqueued) {
+    } else {
         const size_t off = (size_t)c->own_lo * rowb, len = (size_t)(c->own_hi - c->own_lo) * rowb;
         if (len) CU(cudaMemcpyAsync(host_rgba8 + off, src + off, len, cudaMemcpyDeviceToHost, c->stream3));   // direct DMA when host_rgba8 is page-locked
-        if (pipelined) c->tile_valid[k] = false;                 // (the tile path, when it comes back, starts from a full copy)
     }
+    if (!tiles && pipelined) c->tile_valid[k] = false;           // (the tile path, when it comes back, starts from a full copy)
     CU(cudaEventRecord(c->ev_copy_done[k], c->stream3));
     c->copy_pending[k] = true;
     if (!pipelined) {                                     // one caller-owned target: nothing to overlap with

@@ -83,11 +83,12 @@ def test_peer_exchange_e2e_pipelined():
         assert np.array_equal(got[i], want[i][0]), f"frame {i}"
 
 
-@pytest.mark.parametrize("depth", [2, 3])
-def test_distributed_readback_shared_host_frame(depth):
-    """rr_mgpu_set_readback(1): every context keeps its rows and copies exactly those into ONE shared host frame."""
+@pytest.mark.parametrize("depth,tiles", [(2, 0), (3, 0), (2, 1), (3, 1)])
+def test_distributed_readback_shared_host_frame(depth, tiles):
+    """rr_mgpu_set_readback(1): every context keeps its rows and copies exactly those into ONE shared host frame — as whole rows,
+    or (tiles = 1, rr_set_readback_tiles) as the 32x4-pixel tiles of its rows that can differ from what the frame already holds."""
     s = scene.scene_spheres(640, 360, n_spheres=8, grid=(4, 2), seed=21, n_lights=2, light_dim=128, tex_sizes=(128, 64))
-    cams = _cams(s, 5)
+    cams = _cams(s, 9 if tiles else 5)
     want = _frames_single(s, cams)
     world, tile = 4, 32                                  # 360 rows: 11 full tiles and a partial one (rank 3's)
     rs = [Renderer(rrd.tile_config(s.cfg, world, k, tile, 24)) for k in range(world)]
@@ -97,6 +98,7 @@ def test_distributed_readback_shared_host_frame(depth):
     for r in rs:
         r.mgpu_set_readback(1)
         r.set_pipeline_depth(depth)
+        r.set_readback_tiles(tiles)
         r.frame_shadows(1)
     bufs = [rr.host_alloc((s.cfg.height, s.cfg.width, 4)) for _ in range(depth)]
     for b in bufs:
@@ -113,6 +115,9 @@ def test_distributed_readback_shared_host_frame(depth):
         got.append(bufs[i % depth].copy())
     for i in range(len(cams)):
         assert np.array_equal(got[i], want[i][0]), f"frame {i}"
+    if tiles:
+        sent = sum(r.readback_tile_bytes() for r in rs)
+        assert 0 < sent < len(cams) * s.cfg.height * s.cfg.width * 4
 
 
 def test_interleaved_rows_without_exchange():
