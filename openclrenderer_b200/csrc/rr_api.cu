@@ -174,6 +174,7 @@ struct rr_ctx {
     uint8_t* d_tile_now[RR_RING_MAX] = {};
     uint8_t* d_tile_prev[RR_RING_MAX] = {};
     const void* tile_host[RR_RING_MAX] = {};
+    uint64_t tile_seq[RR_RING_MAX] = {}, tile_calls = 0;   // when each slot last wrote its host buffer (a buffer that another slot has written since is stale for this one)
     float tile_clear[RR_RING_MAX][4] = {};
     bool tile_valid[RR_RING_MAX] = {};
     uint32_t* d_tile_sent = nullptr;             // [0]: tiles stored by k_tile_copy since rr_readback_tile_bytes; [1 + k]: tiles of slot k's last copy
@@ -1733,6 +1734,7 @@ int rr_set_pipeline_depth(rr_ctx* c, int depth) {
     int r = rr_sync(c);
     if (r && r != RR_ERR_OVERFLOW) return r;
     c->ring_depth = depth; c->ring_pos = 0;
+    for (int i = 0; i < RR_RING_MAX; i++) c->tile_valid[i] = false;      // (dirty-tile read-back: the slots' host buffers change)
     return RR_OK;
 }
 
@@ -1831,8 +1833,11 @@ int rr_frame_e2e(rr_ctx* c, const float c_pos[4], const float c_rot[4], const fl
         // last completed copy needed more than half of the tiles: the copy engine moves the frame as without this mode (below), the
         // kernel only keeps the books
         const uint32_t own_tiles = tiles_rows ? n_tiles / (uint32_t)c->cfg.band_world : n_tiles;
-        const bool all = !c->tile_valid[k] || c->tile_host[k] != (const void*)host_rgba8 || memcmp(c->tile_clear[k], cl, 16) != 0 ||
-                         c->tile_estimate > own_tiles / 2;
+        bool all = !c->tile_valid[k] || c->tile_host[k] != (const void*)host_rgba8 || memcmp(c->tile_clear[k], cl, 16) != 0 ||
+                   c->tile_estimate > own_tiles / 2;
+        for (int j = 0; j < RR_RING_MAX; j++)                   // the same buffer written through another slot since: what this slot remembers of it is stale
+            if (j != k && c->tile_host[j] == (const void*)host_rgba8 && c->tile_seq[j] > c->tile_seq[k]) all = true;
+        c->tile_seq[k] = ++c->tile_calls;
         CU(cudaMemsetAsync(c->d_tile_sent + 1 + k, 0, 4, c->stream3));
         // grid: about one CTA per 2 000 tiles (1 MB) the last completed copy sent, at least c->tile_grid (RR_TILE_GRID, 4)
         const int grid = all ? 8 : std::min(64, std::max(c->tile_grid, (int)(c->tile_estimate / 2000u)));

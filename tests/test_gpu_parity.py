@@ -360,8 +360,15 @@ def test_frame_e2e_dirty_tile_readback_is_bit_identical(depth, size):
         assert np.array_equal(used[j], want[j]), f"frame {j}"
     sent = b.readback_tile_bytes()
     assert 0 < sent < n * W * H * 4, f"{sent} bytes for {n} frames of {W * H * 4}"      # (first uses, the new clear colour and the foreign buffer are whole frames)
+    # the same host buffer for every call (against the contract, but it must not produce a stale frame): whole frames again
+    b.readback_tile_bytes()
+    for i in range(4):
+        b.frame_e2e(cams[i][0], cams[i][1], clears[i], 1, bufs[0])
+        b.sync()
+        assert np.array_equal(bufs[0], want[i]), f"single buffer, frame {i}"
     # switching it off goes back to plain copies of whole frames
     b.set_readback_tiles(False)
+    b.readback_tile_bytes()
     b.frame_e2e(cams[0][0], cams[0][1], clears[0], 1, bufs[0])
     b.sync()
     assert np.array_equal(bufs[0], want[0]) and b.readback_tile_bytes() == 0
