@@ -1232,7 +1232,8 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
         if (cull) { sp.cluster_vis = c->d_cluster_vis; sp.active = c->d_active; sp.skipped_before = c->d_skipped; }
     }
     sp.sl.samples = c->d_samples; sp.sl.frag = c->d_sample_frag; sp.sl.cap = c->cap_samples; sp.sl.count = c->d_counters + CTR_NSAMPLES;
-    sp.sl.extra = c->d_extra; sp.sl.extra_count = c->d_counters + CTR_NEXTRA; sp.worklist = c->d_worklist;
+    sp.sl.extra = c->d_extra; sp.sl.extra_count = c->d_counters + CTR_NEXTRA; sp.sl.extra_cap = c->cap_frags; sp.sl.overflow = c->d_counters + CTR_OVERFLOW;
+    sp.worklist = c->d_worklist;
     if (c->banded) k_setup_main<true><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     else k_setup_main<false><<<c->lookback_blocks, SETUP_THREADS, 0, c->stream>>>(sp);
     c->launches++;

@@ -321,7 +321,13 @@ __device__ __forceinline__ bool tri_exact_arith(float3 xr, float3 yr) {
 struct InlineQueue { float f[IQ_FIELDS][IQ_SLOTS]; };
 
 struct SampleList { uint2* samples; uint32_t* frag; uint32_t cap; uint32_t* count;      // (pixel, depth), fragment index
-                    uint32_t* extra; uint32_t* extra_count; };                              // fragments whose samples did not fit
+                    uint32_t* extra; uint32_t* extra_count; uint32_t extra_cap; uint32_t* overflow; };   // fragments whose samples did not fit
+
+// a fragment kernel2 has to walk again; the list itself is bounded (a fragment can be listed once per failed reservation)
+__device__ __forceinline__ void extra_push(const SampleList& sl, uint32_t f) {
+    const uint32_t at = atomicAdd(sl.extra_count, 1u);
+    if (at < sl.extra_cap) sl.extra[at] = f; else atomicOr(sl.overflow, 1u);
+}
 
 struct RowFilter { int lo, hi; const uint8_t* mask; };     // rows rasterised here: [lo, hi), and bit 0 of mask[y] when mask != nullptr
 __device__ __forceinline__ bool row_wanted(const RowFilter& rf, int y) { return y >= rf.lo && y < rf.hi && (!rf.mask || (rf.mask[y] & 1)); }
@@ -416,7 +422,7 @@ struct InlineRaster {
         if (n == 0) return;
         const uint32_t first = b0 + (uint32_t)(inc - n);
         if (!rec) {                                                               // sample list full: kernel2 walks this fragment again
-            sl.extra[atomicAdd(sl.extra_count, 1u)] = fidx;
+            extra_push(sl, fidx);
             // the part of the failed reservation that lies inside the list is streamed by k_ids_list: mark it as holding no sample
             for (uint32_t k = 0; k < (uint32_t)n && first + k < sl.cap; k++) sl.samples[first + k] = make_uint2(0xFFFFFFFFu, 0u);
         }
@@ -914,7 +920,7 @@ __device__ __forceinline__ void raster_stash_flush(const SampleList& sl, RasterS
         for (uint32_t q = lane; q < run; q += 32u) { sl.samples[b0 + q] = st.sample[q]; sl.frag[b0 + q] = st.frag[q]; }
     } else {                                                    // sample list full: kernel2 walks these fragments again
         for (uint32_t q = lane; q < run; q += 32u) {
-            if (q == 0 || st.frag[q] != st.frag[q - 1]) sl.extra[atomicAdd(sl.extra_count, 1u)] = st.frag[q];      // (a fragment listed twice is walked twice: harmless)
+            if (q == 0 || st.frag[q] != st.frag[q - 1]) extra_push(sl, st.frag[q]);       // (a fragment listed twice is walked twice: harmless)
             if (b0 + q < sl.cap) sl.samples[b0 + q] = make_uint2(0xFFFFFFFFu, 0u);                                  // (no sample here)
         }
     }
