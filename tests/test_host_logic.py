@@ -162,3 +162,29 @@ def test_product_has_no_cpu_fallback():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in txt and "import oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_dirty_tile_readback_rule_keeps_the_host_buffers_exact():
+    """the rule of rr_set_readback_tiles (k_tile_copy, include/rr.h), modelled on the CPU: a tile is sent when it holds a shaded pixel
+    in this frame or held one in the frame last written into the same host buffer; everything else in that buffer is already the clear
+    colour. With a ring of D buffers, random coverage per frame, a clear-colour change and a foreign buffer, every buffer equals its
+    frame after every copy — and strictly fewer tiles travel than with whole-frame copies."""
+    rng = np.random.Generator(np.random.PCG64(3))
+    n_tiles, D, n_frames = 200, 3, 40
+    host = [np.full(n_tiles, -1, np.int64) for _ in range(D + 1)]             # what each host buffer holds per tile (-1: never written)
+    prev = [np.zeros(n_tiles, bool) for _ in range(D)]                        # per ring slot: tiles shaded in the frame last written through it
+    slot_buf, slot_clear, valid = [None] * D, [None] * D, [False] * D
+    sent = 0
+    for f in range(n_frames):
+        clear = 1000 if f < 25 else 2000                                      # "colour" of unshaded tiles; shaded tiles get a per-frame value
+        shaded = rng.uniform(size=n_tiles) < 0.15
+        frame = np.where(shaded, 10 * f + 7, clear)
+        k = f % D
+        buf = D if f == 17 else k                                             # frame 17 goes into a buffer the slot has never seen
+        everything = (not valid[k]) or slot_buf[k] != buf or slot_clear[k] != clear
+        need = np.ones(n_tiles, bool) if everything else (shaded | prev[k])
+        host[buf][need] = frame[need]
+        sent += int(need.sum())
+        prev[k], slot_buf[k], slot_clear[k], valid[k] = shaded, buf, clear, True
+        assert np.array_equal(host[buf], frame), f"frame {f}"
+    assert sent < 0.5 * n_frames * n_tiles
