@@ -183,6 +183,7 @@ struct rr_ctx {
     uint64_t tile_dma_bytes = 0;                 // whole frames copied by the copy engine while the tile mode is on (statistics)
     uint8_t* tile_mark_target = nullptr;         // set by rr_frame_e2e around rr_frame_draw: where the id resolve marks the frame's tiles
     bool tiles_marked = false;                   // ... and whether it did (otherwise k_tile_mark runs over the covered-pixel list)
+    bool swapped = true;                         // rr_swap_buffers since the last rr_frame_draw: this frame's id image starts all zero
     // A/B knobs, read at rr_create
     bool split_clear = true;                     // RR_SPLIT_CLEAR=0: the stores stay in k_shade_pre4 on the main stream
     bool list_from_ids = true;                   // RR_LIST_FROM_IDS=0: the covered-pixel list comes from a pass over the screen (k_shade_list)
@@ -1185,9 +1186,8 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     // The streaming stores of kernel3 — next frame's depth / id clear and the clear colour — depend on nothing this frame computes:
     // they run on a side stream (k_clear_next) and are joined in front of the shading list. Everything that last read those buffers
     // (the previous frame's shading and post passes, the copy of the ring slot) is ordered before this call on the main stream. The
-    // fork sits behind k_setup_main: the 100 MB of stores then overlap the latency-bound kernels that follow it (kernel1 / kernel2 of
-    // the work list) and the rest of the shadow pass instead of taking SM slots from the issue-bound setup kernels (RR_CLEAR_AT=0: at
-    // the start of the frame). A peer of the composite target stores its clear colour later, behind the fb_free wait.
+    // fork sits at the start of the frame (RR_CLEAR_AT=1: behind k_setup_main, beside the latency-bound kernels that follow it —
+    // measured equal or slightly slower). A peer of the composite target stores its clear colour later, behind the fb_free wait.
     const bool split_clear = c->split_clear && c->W % 4 == 0;
     const int clear_at = c->clear_at;
     auto fork_clear = [&]() -> int {
@@ -1252,7 +1252,10 @@ int rr_frame_draw(rr_ctx* c, const float c_pos[4], const float c_rot[4], const f
     rp.row_lo = band0; rp.row_hi = band1; rp.rowbit = ROW_OWNED;
     // kernel2: a stream over the samples both depth kernels recorded; with the streaming stores on the side stream it also builds
     // kernel3's covered-pixel list (the first sample to resolve a pixel appends it), so no pass over the screen is left in the frame
-    const bool list_from_ids = c->list_from_ids && split_clear && !(mg_composite && c->mg.rank != 0);
+    // (a second draw without rr_swap_buffers in between finds the ids of the first one: "first to resolve" is then no criterion and
+    // the list comes from the pass over the screen, as it did before)
+    const bool list_from_ids = c->list_from_ids && split_clear && !(mg_composite && c->mg.rank != 0) && c->swapped;
+    c->swapped = false;
     rp.shade_list = c->d_shade_list; rp.shade_count = c->d_counters + CTR_NSHADE;
     rp.tile_now = c->tile_mark_target; rp.tiles_x = (c->W + TILE_W - 1) / TILE_W;      // rr_frame_e2e with the dirty-tile read-back: the id resolve marks the tiles
     c->tiles_marked = list_from_ids && c->tile_mark_target != nullptr;
@@ -1379,6 +1382,7 @@ int rr_post_godrays(rr_ctx* c) {
 int rr_swap_buffers(rr_ctx* c) {
     if (!c) return fail(RR_ERR_INVALID, "null ctx");
     c->cur ^= 1;                                           // depth_buffer.flip(), object_context.cpp:21
+    c->swapped = true;
     c->cam_old = c->cam_last;                              // c_pos_old / c_rot_old, object_context.cpp:23-24
     return RR_OK;
 }

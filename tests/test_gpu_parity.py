@@ -244,6 +244,21 @@ def test_alternative_frame_paths_render_the_same_frame(knobs, monkeypatch):
         assert_frame_parity(g, o, label=f"{s.name} {knobs}")
 
 
+def test_second_draw_without_swap_still_shades_every_covered_pixel():
+    """rr_frame_draw twice without rr_swap_buffers (the id image of the second draw is not empty): the covered-pixel list must not
+    rely on 'first sample to resolve a pixel' then — every pixel with a depth is shaded, as in a frame drawn once."""
+    s = scene.scene_c1("A")
+    g = Renderer(s.cfg)
+    s.upload(g)
+    g.frame_shadows(1)
+    g.frame_draw(s.c_pos, s.c_rot, s.clear)
+    g.sync()
+    once = g.read_rgba8()
+    g.frame_draw(s.c_pos, s.c_rot, s.clear)                              # same camera, no swap: same depth, same winners
+    g.sync()
+    assert np.array_equal(g.read_rgba8(), once)
+
+
 def test_overflow_is_reported():
     s = _soup(5, 400, 320, 200, True)
     cfg = s.cfg.copy(max_fragments=64)
