@@ -184,7 +184,7 @@ struct rr_ctx {
     uint8_t* tile_mark_target = nullptr;         // set by rr_frame_e2e around rr_frame_draw: where the id resolve marks the frame's tiles
     bool tiles_marked = false;                   // ... and whether it did (otherwise k_tile_mark runs over the covered-pixel list)
     bool swapped = true;                         // rr_swap_buffers since the last rr_frame_draw: this frame's id image starts all zero
-    // A/B knobs, read at rr_create (INTEGRATION.md §5)
+    // A/B knobs, read at rr_create (INTEGRATION.md §6)
     bool split_clear = true;                     // RR_SPLIT_CLEAR=0: the stores stay in k_shade_pre4 on the main stream
     bool list_from_ids = true;                   // RR_LIST_FROM_IDS=0: the covered-pixel list comes from a pass over the screen (k_shade_list)
     int clear_at = 0;                            // RR_CLEAR_AT=1: the side stream forks behind k_setup_main instead of at the start of the frame

@@ -234,7 +234,7 @@ def test_sample_list_overflow_falls_back_to_walking(cap, monkeypatch):
 
 @pytest.mark.parametrize("knobs", [{"RR_SPLIT_CLEAR": "0"}, {"RR_LIST_FROM_IDS": "0"}, {"RR_CLEAR_AT": "1", "RR_CLEAR_GRID": "1"}])
 def test_alternative_frame_paths_render_the_same_frame(knobs, monkeypatch):
-    """the A/B knobs of INTEGRATION.md §5 select other arrangements of the same work — kernel3's streaming stores inside
+    """the A/B knobs of INTEGRATION.md §6 select other arrangements of the same work — kernel3's streaming stores inside
     k_shade_pre4 instead of on the side stream, the covered-pixel list from a pass over the screen instead of from the id resolve,
     the side stream forked behind the setup kernel: same frame, two frames in a row (the clears of frame 1 are frame 2's start)."""
     for k, v in knobs.items():
